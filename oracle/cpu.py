@@ -1,0 +1,183 @@
+"""ctypes front-end of the C oracle (oracle/natrium_oracle.c).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "_build", "liboracle.so")
+    srcs = [os.path.join(_HERE, s) for s in ("natrium_oracle.c", "entropic_oracle.c", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _d(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(_dp)
+
+
+class Stencil:
+    def __init__(self, name, scaling=1.0):
+        from . import stencils
+        self.name = name
+        self.e, self.w, self.cs2, self.max_speed = stencils.make(name, scaling)
+        self.e = np.ascontiguousarray(self.e)
+        self.w = np.ascontiguousarray(self.w)
+        self.Q, self.D = self.e.shape
+        self.scaling = float(scaling)
+
+
+def spmv_csr(m, x, y=None, add=False):
+    """y (+)= m @ x with the oracle's Epetra-order row loop; m is scipy CSR."""
+    n = m.shape[0]
+    if y is None:
+        y = np.zeros(n)
+    rowptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(m.indices, dtype=np.int32)
+    val = np.ascontiguousarray(m.data, dtype=np.float64)
+    lib().orc_spmv_csr(C.c_int64(n), rowptr.ctypes.data_as(_i64p), col.ctypes.data_as(_i32p), _d(val),
+                       _d(x), _d(y), C.c_int(1 if add else 0))
+    return y
+
+
+def stream(blocks, f, n_owned=None):
+    """f: (Q, stride) array.  Reference order: f_tmp = copy(f); f[1:] = M f_tmp[1:]
+    (CFDSolver.cpp:671-672).  Returns the new array (input untouched)."""
+    Q = f.shape[0]
+    f_tmp = f.copy()
+    out = f.copy()
+    seen = set()
+    for (bi, bj) in sorted(blocks.keys()):
+        m = blocks[(bi, bj)]
+        n = m.shape[0]
+        y = out[bi + 1, :n]
+        spmv_csr(m, np.ascontiguousarray(f_tmp[bj + 1]), y, add=(bi in seen))
+        seen.add(bi)
+    return out
+
+
+def collide_bgk(st, f, viscosity, dt, equilibrium=0, in_init=False, u_init=None, n=None):
+    """In-place collideAll (f only).  Returns (rho, u[D,n], status)."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    rho = np.zeros(n)
+    u = np.zeros((st.D, n)) if u_init is None else np.ascontiguousarray(u_init, dtype=np.float64)
+    rc = lib().orc_collide_bgk(C.c_int(st.D), C.c_int(Q), C.c_int64(n), C.c_int64(stride), _d(f), _d(rho), _d(u),
+                               _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2),
+                               C.c_double(viscosity), C.c_double(dt), C.c_int(equilibrium),
+                               C.c_int(1 if in_init else 0))
+    return rho, u, rc
+
+
+def collide_bgk_fg(st, f, g, viscosity, dt, equilibrium=1, gamma=1.4, prandtl=None, sutherland=False, n=None):
+    """In-place collideAll (f and g).  Returns (rho, u, T, maskShockSensor, status).
+    ``prandtl=None`` mirrors isPrandtlNumberSet()==false with getPrandtlNumber()==1 default."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    rho, T, mss = np.zeros(n), np.zeros(n), np.zeros(n)
+    u = np.zeros((st.D, n))
+    rc = lib().orc_collide_bgk_fg(
+        C.c_int(st.D), C.c_int(Q), C.c_int64(n), C.c_int64(stride), _d(f), _d(g), _d(rho), _d(u), _d(T), _d(mss),
+        _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2), C.c_double(viscosity), C.c_double(dt),
+        C.c_int(equilibrium), C.c_double(gamma), C.c_int(0 if prandtl is None else 1),
+        C.c_double(1.0 if prandtl is None else prandtl), C.c_int(1 if sutherland else 0), C.c_int(0))
+    return rho, u, T, mss, rc
+
+
+def equilibrium(st, rho, u_unscaled, T=1.0, kind=0):
+    feq = np.zeros(st.Q)
+    uu = np.zeros(3)
+    uu[:st.D] = u_unscaled
+    lib().orc_equilibrium(C.c_int(st.D), C.c_int(st.Q), _d(st.e), _d(st.w), C.c_double(st.scaling),
+                          C.c_double(st.cs2), C.c_int(kind), C.c_double(rho), _d(uu), C.c_double(T), _d(feq))
+    return feq
+
+
+def legacy_feq(st, rho, u):
+    feq = np.zeros(st.Q)
+    uu = np.ascontiguousarray(u, dtype=np.float64)
+    lib().orc_legacy_feq(C.c_int(st.D), C.c_int(st.Q), _d(st.e), _d(st.w), C.c_double(st.cs2),
+                         C.c_double(rho), _d(uu), _d(feq))
+    return feq
+
+
+def legacy_collide_single_point(st, f, tau_legacy):
+    f = np.ascontiguousarray(f, dtype=np.float64).copy()
+    lib().orc_legacy_collide_single_point(C.c_int(st.D), C.c_int(st.Q), _d(st.e), _d(st.w), C.c_double(st.cs2),
+                                          C.c_double(tau_legacy), _d(f))
+    return f
+
+
+class _Blocks:
+    """Keeps contiguous CSR arrays alive and exposes pointer tables for orc_step_*."""
+
+    def __init__(self, blocks):
+        keys = sorted(blocks.keys())
+        self.n = len(keys)
+        self.row = np.array([k[0] for k in keys], dtype=np.int32)
+        self.col = np.array([k[1] for k in keys], dtype=np.int32)
+        self._rp = [np.ascontiguousarray(blocks[k].indptr, dtype=np.int64) for k in keys]
+        self._ci = [np.ascontiguousarray(blocks[k].indices, dtype=np.int32) for k in keys]
+        self._va = [np.ascontiguousarray(blocks[k].data, dtype=np.float64) for k in keys]
+        self.rowptr = (_i64p * self.n)(*[a.ctypes.data_as(_i64p) for a in self._rp])
+        self.colidx = (_i32p * self.n)(*[a.ctypes.data_as(_i32p) for a in self._ci])
+        self.val = (_dp * self.n)(*[a.ctypes.data_as(_dp) for a in self._va])
+        self.nnz = int(sum(len(a) for a in self._va))
+
+
+class ReferenceOrderStepper:
+    """CFDSolver::stream()+collide() in reference order on the CPU (CFDSolver.cpp:659-843;
+    CompressibleCFDSolver.h:181-314,739-788).  Used as checker and as the CPU baseline."""
+
+    def __init__(self, st, blocks, n, viscosity, dt, equilibrium=0, with_g=False, gamma=1.4,
+                 prandtl=None, sutherland=False):
+        self.st, self.n, self.nu, self.dt, self.eq = st, n, viscosity, dt, equilibrium
+        self.with_g, self.gamma, self.prandtl, self.sutherland = with_g, gamma, prandtl, sutherland
+        self.b = _Blocks(blocks)
+        self.tmp = np.zeros((st.Q, n))
+        self.rho = np.zeros(n)
+        self.u = np.zeros((st.D, n))
+        self.T = np.zeros(n)
+        self.mss = np.zeros(n)
+
+    def step(self, f, g=None):
+        st, b = self.st, self.b
+        if not self.with_g:
+            return lib().orc_step_f(
+                C.c_int(st.D), C.c_int(st.Q), C.c_int64(self.n), C.c_int64(f.shape[1]), _d(f), _d(self.tmp),
+                C.c_int(b.n), b.row.ctypes.data_as(_i32p), b.col.ctypes.data_as(_i32p), b.rowptr, b.colidx, b.val,
+                _d(self.rho), _d(self.u), _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2),
+                C.c_double(self.nu), C.c_double(self.dt), C.c_int(self.eq))
+        return lib().orc_step_fg(
+            C.c_int(st.D), C.c_int(st.Q), C.c_int64(self.n), C.c_int64(f.shape[1]), _d(f), _d(g), _d(self.tmp),
+            C.c_int(b.n), b.row.ctypes.data_as(_i32p), b.col.ctypes.data_as(_i32p), b.rowptr, b.colidx, b.val,
+            _d(self.rho), _d(self.u), _d(self.T), _d(self.mss), _d(st.e), _d(st.w), C.c_double(st.scaling),
+            C.c_double(st.cs2), C.c_double(self.nu), C.c_double(self.dt), C.c_int(self.eq),
+            C.c_double(self.gamma), C.c_int(0 if self.prandtl is None else 1),
+            C.c_double(1.0 if self.prandtl is None else self.prandtl), C.c_int(1 if self.sutherland else 0))
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(C.c_int(int(n)))
