@@ -1,0 +1,172 @@
+/*
+ * natrium_b200.h -- C ABI of libnatrium_b200: the B200-native implementation of NATriuM's
+ * per-timestep hot path (semi-Lagrangian stream + collide, device-resident
+ * DistributionFunctions, NCCL ghost exchange).
+ *
+ * Plain C, POD only: no C++/torch/deal.II types cross this boundary.  One context per MPI
+ * rank / GPU; a context is NOT re-entrant (the reference is single-threaded per rank,
+ * L/utilities/MPIGuard.cpp:14-16).  Every call returns NB200_OK (0) or a negative error
+ * code; nb200_last_error() gives the text.  No exception crosses; the host shim re-throws
+ * CollisionException / DensityZeroException on NB200_ERR_DENSITY.
+ *
+ * Citations are into /root/reference, L = src/library/natrium.
+ *
+ * Ownership: the host owns every pointer it passes in; the library copies before it
+ * returns.  After an upload the device copy of the populations is authoritative until the
+ * next download.  The streaming matrix is immutable between nb200_finalize_matrix() calls
+ * (re-upload after SemiLagrangian::reassemble()/setDeltaT()).
+ */
+#ifndef NATRIUM_B200_H_
+#define NATRIUM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nb200_ctx nb200_ctx;
+
+enum nb200_status {
+    NB200_OK = 0,
+    NB200_ERR_ARG = -1,         /* bad argument / wrong call order */
+    NB200_ERR_CUDA = -2,        /* CUDA runtime error (text in nb200_last_error) */
+    NB200_ERR_NCCL = -3,        /* NCCL error */
+    NB200_ERR_UNSUPPORTED = -4, /* "Collision model not implemented yet", CollisionSelection.h:102-110 */
+    NB200_ERR_DENSITY = -5,     /* density < 1e-10 met in collide: CollisionException
+                                   (AuxiliaryCollisionFunctions.h:53-56) / DensityZeroException
+                                   (CollisionOperator.h:106-109) */
+    NB200_ERR_NO_DEVICE = -6    /* no CUDA device: there is NO CPU fallback */
+};
+
+/* CollisionSchemeName / EquilibriumSchemeName subset on the hot path (L/utilities/ConfigNames.h) */
+enum nb200_collision_scheme {
+    NB200_BGK_STANDARD = 0,     /* collision_advanced BGKCollision, CollisionSchemes.h:17-119 */
+    NB200_KBC_STANDARD = 1,     /* legacy KBCStandard::collideAll (D2Q9, D3Q15), L/collision/KBCStandard.cpp:88-1028 */
+    NB200_MRT_ENTROPIC = 2      /* legacy MRTEntropic::collideAllD3Q19, L/collision/MRTEntropic.cpp:167-305 */
+};
+enum nb200_equilibrium_scheme {
+    NB200_BGK_EQUILIBRIUM = 0,     /* Equilibria.h:17-83 */
+    NB200_QUARTIC_EQUILIBRIUM = 1  /* Equilibria.h:87-267 */
+};
+
+/* Flat mirror of what GeneralCollisionData (AuxiliaryCollisionFunctions.h:105-202) pulls out
+ * of SolverConfiguration / ProblemDescription / Stencil for the path. */
+typedef struct nb200_collision_params {
+    int32_t scheme;            /* nb200_collision_scheme */
+    int32_t equilibrium;       /* nb200_equilibrium_scheme */
+    int32_t with_g;            /* 0: selectCollision(f) overload; 1: selectCollision(f,g) overload */
+    int32_t in_init;           /* inInitializationProcedure (CollisionOperator.h:79-91) */
+    double viscosity;          /* problemDescription.getViscosity() */
+    double dt;                 /* delta_t; tau = nu/(dt*cs2_scaled)+0.5 (Aux...h:63-68,177) */
+    double gamma;              /* getHeatCapacityRatioGamma() (f+g only) */
+    int32_t prandtl_set;       /* isPrandtlNumberSet() */
+    int32_t sutherland_set;    /* isSutherlandLawSet() */
+    double prandtl;            /* getPrandtlNumber() (default 1) */
+} nb200_collision_params;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+
+/* Writes an opaque 128-byte NCCL unique id (rank 0 calls it, the host broadcasts it over its
+ * own MPI/torch.distributed).  Replaces nothing in the reference (MPI_COMM_WORLD is implicit there). */
+int nb200_get_unique_id(void *out128);
+
+/* One context per rank; rank r <-> GPU `device`.  nccl_unique_id may be NULL when nranks==1.
+ * Mirrors the per-rank objects built in CFDSolver<dim>::CFDSolver (L/solver/CFDSolver.cpp:77-395). */
+int nb200_create(nb200_ctx **out, int device, int rank, int nranks, const void *nccl_unique_id);
+void nb200_destroy(nb200_ctx *ctx);
+const char *nb200_last_error(const nb200_ctx *ctx);
+
+/* ---- static data: stencil, layout, streaming matrix, ghost plan -------------------------- */
+
+/* Stencil tables: e is Q x D row-major *scaled* directions (Stencil::getDirections()), w the
+ * weights, cs2_scaled = getSpeedOfSoundSquare() (L/stencils/Stencil.h:53-171). */
+int nb200_set_stencil(nb200_ctx *ctx, int D, int Q, const double *e_scaled, const double *w,
+                      double scaling, double cs2_scaled);
+
+/* n_owned = |getLocallyOwnedDofs()|, n_ghost = |getLocallyRelevantDofs()| - n_owned
+ * (L/advection/AdvectionOperator.h:106-112).  Local index space: [0,n_owned) owned, then ghosts.
+ * with_g allocates the second distribution (CompressibleCFDSolver::m_g). */
+int nb200_set_layout(nb200_ctx *ctx, int64_t n_owned, int64_t n_ghost, int with_g);
+
+/* One block (bi,bj) of getSystemMatrix() (distributed_sparse_block_matrix, (Q-1)x(Q-1) blocks,
+ * SemiLagrangian.cpp:101,116-134) as local CSR: exactly what
+ * block(bi,bj).trilinos_matrix().ExtractMyRowView gives row by row (idiom in
+ * L/smoothing/VmultLimiter.cpp:32-60).  col < n_owned: owned column, else ghost slot. */
+int nb200_upload_block_csr(nb200_ctx *ctx, int bi, int bj, int64_t n_rows, const int64_t *rowptr,
+                           const int32_t *col_local, const double *val);
+
+/* Builds the device streaming format from the uploaded blocks (after reassemble()). */
+int nb200_finalize_matrix(nb200_ctx *ctx);
+
+/* Ghost plan derived from the column map / IndexSets: for neighbour k, owned local indices
+ * send_idx[send_off[k]..send_off[k+1]) go to rank nbr_rank[k]; ghost slots
+ * [recv_off[k], recv_off[k+1]) (relative to n_owned) are filled from it.  Replaces the Epetra
+ * Import inside vmult and DistributionFunctions::updateGhosted() (DistributionFunctions.h:282-293). */
+int nb200_set_halo(nb200_ctx *ctx, int n_nbr, const int32_t *nbr_rank, const int64_t *send_off,
+                   const int32_t *send_idx, const int64_t *recv_off);
+
+/* ---- DistributionFunctions storage (L/solver/DistributionFunctions.h:47-300) -------------- */
+
+/* which: 0 = f, 1 = g.  q in [0,Q): f.at(q).  host: n_owned contiguous doubles, the array
+ * ExtractView returns (CollisionOperator.h:38-48). */
+int nb200_upload_population(nb200_ctx *ctx, int which, int q, const double *host, int64_t n);
+int nb200_download_population(nb200_ctx *ctx, int which, int q, double *host, int64_t n);
+/* All Q populations at once, host layout [Q][n_owned]. */
+int nb200_upload_populations(nb200_ctx *ctx, int which, const double *host, int64_t n);
+int nb200_download_populations(nb200_ctx *ctx, int which, double *host, int64_t n);
+/* Same with page-locked host buffers and async copies on the context stream (e2e path). */
+int nb200_upload_populations_async(nb200_ctx *ctx, int which, const double *pinned_host, int64_t n);
+int nb200_download_populations_async(nb200_ctx *ctx, int which, double *pinned_host, int64_t n);
+
+/* Initial macroscopic velocity for in_init collisions (u_raw is an input then). u: [D][n_owned]. */
+int nb200_upload_velocity(nb200_ctx *ctx, const double *u, int64_t n);
+
+/* ---- per-step operators ------------------------------------------------------------------ */
+
+int nb200_set_collision(nb200_ctx *ctx, const nb200_collision_params *p);
+
+/* DistributionFunctions::updateGhosted() for f (and g): NCCL neighbour exchange. No-op on 1 rank. */
+int nb200_update_ghosted(nb200_ctx *ctx);
+
+/* SemiLagrangian::stream / the vmult site: f.FStream = M * f_old.FStream, f0 untouched
+ * (SemiLagrangian.h:150-161; CFDSolver.cpp:671-672; gStream CompressibleCFDSolver.h:279-314).
+ * Includes the ghost refresh the Epetra column-map import performs inside vmult. */
+int nb200_stream(nb200_ctx *ctx, int which);
+
+/* selectCollision(...)->collideAll: in place on the current populations; writes rho, u (,T, sensor)
+ * (CollisionOperator.h:26-224). */
+int nb200_collide(nb200_ctx *ctx);
+
+/* n_steps x { stream(f); [stream(g);] collide } fused into one pass over the populations per
+ * step, device resident (CFDSolver::run loop body, CFDSolver.cpp:877-902 without output()). */
+int nb200_step(nb200_ctx *ctx, int n_steps);
+
+/* ---- results ----------------------------------------------------------------------------- */
+
+/* rho [n], u [D][n] (scaled, as written to m_velocity), T [n], sensor [n]; any pointer may be NULL. */
+int nb200_download_moments(nb200_ctx *ctx, double *rho, double *u, double *T, double *sensor, int64_t n);
+
+/* Global (all-rank) sums over owned DoFs of the current populations:
+ * out = { sum rho, sum rho*u_x, sum rho*u_y, sum rho*u_z, sum energy } with
+ * energy = 0.5*rho*|u|^2 (+ rho*Cv*T when with_g), u scaled.  Diagnostic mirror of
+ * PhysicalProperties::mass / kineticEnergy (L/solver/PhysicalProperties.cpp:29-131) as plain sums. */
+int nb200_conserved(nb200_ctx *ctx, double out[5]);
+
+/* Blocks until queued work is done; returns NB200_ERR_DENSITY if the sticky density flag is set. */
+int nb200_synchronize(nb200_ctx *ctx);
+
+/* ---- measurement helpers (CUDA events on the context's own stream) ------------------------ */
+int nb200_timer_start(nb200_ctx *ctx);
+int nb200_timer_stop(nb200_ctx *ctx, float *elapsed_ms);   /* synchronizes */
+/* Number of kernels this library launched since context creation. */
+int64_t nb200_kernel_launches(const nb200_ctx *ctx);
+/* Writes a description of the device streaming format and its byte size. */
+int nb200_matrix_info(const nb200_ctx *ctx, int64_t *nnz, int64_t *device_bytes, int64_t *padded_entries);
+/* Raw cudaStream_t of the context (for profilers / external event timing). */
+void *nb200_stream_handle(const nb200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NATRIUM_B200_H_ */

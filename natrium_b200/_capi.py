@@ -1,0 +1,262 @@
+"""ctypes binding of libnatrium_b200 (include/natrium_b200.h).
+
+The CUDA library is the product: there is no CPU or eager-PyTorch fallback.  Importing this
+module never needs a GPU (so symbol/export tests run on CPU), but creating a context on a
+machine without a CUDA device raises, and a missing shared library raises at import.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnatrium_b200.so")
+
+NB200_OK = 0
+NB200_ERR_ARG = -1
+NB200_ERR_CUDA = -2
+NB200_ERR_NCCL = -3
+NB200_ERR_UNSUPPORTED = -4
+NB200_ERR_DENSITY = -5
+NB200_ERR_NO_DEVICE = -6
+
+BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = 0, 1, 2
+BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = 0, 1
+
+
+class CollisionParams(C.Structure):
+    _fields_ = [("scheme", C.c_int32), ("equilibrium", C.c_int32), ("with_g", C.c_int32), ("in_init", C.c_int32),
+                ("viscosity", C.c_double), ("dt", C.c_double), ("gamma", C.c_double),
+                ("prandtl_set", C.c_int32), ("sutherland_set", C.c_int32), ("prandtl", C.c_double)]
+
+
+class NatriumB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libnatrium_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CollisionException(NatriumB200Error):
+    """Mirror of natrium::CollisionException (density < 1e-10 / model not implemented)."""
+
+
+_vp, _dp = C.c_void_p, C.POINTER(C.c_double)
+_i32p, _i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+
+# every symbol include/natrium_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "nb200_get_unique_id": (C.c_int, [_vp]),
+    "nb200_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _vp]),
+    "nb200_destroy": (None, [_vp]),
+    "nb200_last_error": (C.c_char_p, [_vp]),
+    "nb200_set_stencil": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double]),
+    "nb200_set_layout": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int]),
+    "nb200_upload_block_csr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _i64p, _i32p, _dp]),
+    "nb200_finalize_matrix": (C.c_int, [_vp]),
+    "nb200_set_halo": (C.c_int, [_vp, C.c_int, _i32p, _i64p, _i32p, _i64p]),
+    "nb200_upload_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
+    "nb200_download_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
+    "nb200_upload_populations": (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),
+    "nb200_download_populations": (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),
+    "nb200_upload_populations_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
+    "nb200_download_populations_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
+    "nb200_upload_velocity": (C.c_int, [_vp, _dp, C.c_int64]),
+    "nb200_set_collision": (C.c_int, [_vp, C.POINTER(CollisionParams)]),
+    "nb200_update_ghosted": (C.c_int, [_vp]),
+    "nb200_stream": (C.c_int, [_vp, C.c_int]),
+    "nb200_collide": (C.c_int, [_vp]),
+    "nb200_step": (C.c_int, [_vp, C.c_int]),
+    "nb200_download_moments": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int64]),
+    "nb200_conserved": (C.c_int, [_vp, _dp]),
+    "nb200_synchronize": (C.c_int, [_vp]),
+    "nb200_timer_start": (C.c_int, [_vp]),
+    "nb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "nb200_kernel_launches": (C.c_int64, [_vp]),
+    "nb200_matrix_info": (C.c_int, [_vp, _i64p, _i64p, _i64p]),
+    "nb200_stream_handle": (_vp, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library; fails loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C natrium_b200/csrc). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """Thin OO wrapper over one nb200_ctx.  All arrays are numpy (host) arrays."""
+
+    def __init__(self, device=0, rank=0, nranks=1, unique_id=None):
+        self.lib = load()
+        self._h = _vp()
+        uid = None
+        if unique_id is not None:
+            uid = C.create_string_buffer(bytes(unique_id), 128)
+        rc = self.lib.nb200_create(C.byref(self._h), device, rank, nranks, C.cast(uid, _vp) if uid is not None else None)
+        if rc != NB200_OK:
+            self._h = None
+            reason = {NB200_ERR_NO_DEVICE: "no CUDA device visible (there is no CPU fallback)",
+                      NB200_ERR_NCCL: "NCCL initialisation failed", NB200_ERR_CUDA: "CUDA initialisation failed"}.get(rc, "bad argument")
+            raise NatriumB200Error(rc, reason)
+        self.D = self.Q = 0
+        self.n_owned = self.n_ghost = 0
+        self.with_g = False
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = load().nb200_get_unique_id(C.cast(buf, _vp))
+        if rc != NB200_OK:
+            raise NatriumB200Error(rc, "ncclGetUniqueId failed")
+        return buf.raw
+
+    def _check(self, rc):
+        if rc == NB200_OK:
+            return
+        msg = self.lib.nb200_last_error(self._h).decode()
+        if rc in (NB200_ERR_DENSITY, NB200_ERR_UNSUPPORTED):
+            raise CollisionException(rc, msg)
+        raise NatriumB200Error(rc, msg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.nb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- static data
+    def set_stencil(self, e_scaled, w, scaling, cs2_scaled):
+        e = _as_f64(e_scaled)
+        w = _as_f64(w)
+        self.Q, self.D = e.shape
+        self._check(self.lib.nb200_set_stencil(self._h, self.D, self.Q, _dptr(e), _dptr(w), scaling, cs2_scaled))
+
+    def set_layout(self, n_owned, n_ghost=0, with_g=False):
+        self._check(self.lib.nb200_set_layout(self._h, n_owned, n_ghost, 1 if with_g else 0))
+        self.n_owned, self.n_ghost, self.with_g = int(n_owned), int(n_ghost), bool(with_g)
+
+    def upload_block_csr(self, bi, bj, rowptr, col, val):
+        rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        val = _as_f64(val)
+        self._check(self.lib.nb200_upload_block_csr(self._h, bi, bj, len(rowptr) - 1, rowptr.ctypes.data_as(_i64p),
+                                                    col.ctypes.data_as(_i32p), _dptr(val)))
+
+    def finalize_matrix(self):
+        self._check(self.lib.nb200_finalize_matrix(self._h))
+
+    def set_halo(self, nbr_rank, send_off, send_idx, recv_off):
+        nbr = np.ascontiguousarray(nbr_rank, dtype=np.int32)
+        so = np.ascontiguousarray(send_off, dtype=np.int64)
+        si = np.ascontiguousarray(send_idx, dtype=np.int32)
+        ro = np.ascontiguousarray(recv_off, dtype=np.int64)
+        self._check(self.lib.nb200_set_halo(self._h, len(nbr), nbr.ctypes.data_as(_i32p), so.ctypes.data_as(_i64p),
+                                            si.ctypes.data_as(_i32p), ro.ctypes.data_as(_i64p)))
+
+    # ---- populations
+    def upload_population(self, which, q, host):
+        host = _as_f64(host)
+        self._check(self.lib.nb200_upload_population(self._h, which, q, _dptr(host), host.shape[0]))
+
+    def download_population(self, which, q):
+        out = np.empty(self.n_owned)
+        self._check(self.lib.nb200_download_population(self._h, which, q, _dptr(out), self.n_owned))
+        return out
+
+    def upload_populations(self, which, host):
+        host = _as_f64(host)
+        assert host.shape == (self.Q, self.n_owned), host.shape
+        self._check(self.lib.nb200_upload_populations(self._h, which, _dptr(host), self.n_owned))
+
+    def download_populations(self, which, out=None):
+        if out is None:
+            out = np.empty((self.Q, self.n_owned))
+        self._check(self.lib.nb200_download_populations(self._h, which, _dptr(out), self.n_owned))
+        return out
+
+    def upload_populations_async(self, which, host_ptr):
+        self._check(self.lib.nb200_upload_populations_async(self._h, which, host_ptr, self.n_owned))
+
+    def download_populations_async(self, which, host_ptr):
+        self._check(self.lib.nb200_download_populations_async(self._h, which, host_ptr, self.n_owned))
+
+    def upload_velocity(self, u):
+        u = _as_f64(u)
+        self._check(self.lib.nb200_upload_velocity(self._h, _dptr(u), u.shape[1]))
+
+    # ---- operators
+    def set_collision(self, viscosity, dt, scheme=BGK_STANDARD, equilibrium=BGK_EQUILIBRIUM, with_g=False,
+                      in_init=False, gamma=1.4, prandtl=None, sutherland=False):
+        p = CollisionParams(scheme, equilibrium, 1 if with_g else 0, 1 if in_init else 0, viscosity, dt, gamma,
+                            0 if prandtl is None else 1, 1 if sutherland else 0, 1.0 if prandtl is None else prandtl)
+        self._check(self.lib.nb200_set_collision(self._h, C.byref(p)))
+
+    def update_ghosted(self):
+        self._check(self.lib.nb200_update_ghosted(self._h))
+
+    def stream(self, which=0):
+        self._check(self.lib.nb200_stream(self._h, which))
+
+    def collide(self):
+        self._check(self.lib.nb200_collide(self._h))
+
+    def step(self, n_steps=1):
+        self._check(self.lib.nb200_step(self._h, n_steps))
+
+    def synchronize(self):
+        self._check(self.lib.nb200_synchronize(self._h))
+
+    # ---- results
+    def download_moments(self, want_T=False):
+        n = self.n_owned
+        rho, u = np.empty(n), np.empty((self.D, n))
+        T = np.empty(n) if want_T else None
+        s = np.empty(n) if want_T else None
+        self._check(self.lib.nb200_download_moments(self._h, _dptr(rho), _dptr(u), _dptr(T) if want_T else None,
+                                                    _dptr(s) if want_T else None, n))
+        return (rho, u, T, s) if want_T else (rho, u)
+
+    def conserved(self):
+        out = np.zeros(5)
+        self._check(self.lib.nb200_conserved(self._h, _dptr(out)))
+        return out
+
+    def timer_start(self):
+        self._check(self.lib.nb200_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._check(self.lib.nb200_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_launches(self):
+        return int(self.lib.nb200_kernel_launches(self._h))
+
+    def matrix_info(self):
+        nnz, nbytes, padded = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.nb200_matrix_info(self._h, C.byref(nnz), C.byref(nbytes), C.byref(padded)))
+        return dict(nnz=nnz.value, device_bytes=nbytes.value, padded_entries=padded.value)

@@ -1,0 +1,273 @@
+// collide.cuh -- device-side collision operators of libnatrium_b200 (sm_100a).
+//
+// Pointwise, register-resident: every function works on one DoF's populations held in a
+// thread's registers, so the same code is the epilogue of the fused stream+collide kernel
+// and the body of the stand-alone collide kernel.  fp64 throughout; no tensor cores (the
+// path is HBM-bound).
+//
+// What each function computes follows the reference (L = src/library/natrium):
+//   density / velocity      L/collision_advanced/AuxiliaryCollisionFunctions.h:45-59,231-287
+//   temperature             ...:289-307
+//   BGK equilibrium         L/collision_advanced/Equilibria.h:33-83
+//   quartic equilibrium     L/collision_advanced/Equilibria.h:119-267 (H3/H4 :519-566)
+//   BGK relax               L/collision_advanced/CollisionSchemes.h:28-41
+//   f+g relax (Prandtl fix, Sutherland, sensor)   CollisionSchemes.h:43-118, Aux...h:420-515
+// Unlike the reference, the Hermite tensors are reduced once on the host to their 10+15
+// unique symmetric components and kept in constant memory (the reference recomputes the
+// full tensors per DoF, CollisionOperator.h:68-69).
+#pragma once
+#include <cstdint>
+
+#include "nbconst.h"
+
+__constant__ NbConst cP;
+
+template <int Q>
+__device__ __forceinline__ double nb_density(const double (&f)[Q])
+{
+    double rho = 0.0;
+#pragma unroll
+    for (int p = 0; p < Q; ++p) rho += f[p];
+    return rho;
+}
+
+// calculateVelocity: hard-coded index sums for D2Q9 and D3Q19, generic loop otherwise.
+template <int D, int Q>
+__device__ __forceinline__ void nb_velocity(const double (&f)[Q], double rho, double (&u)[3])
+{
+    u[0] = u[1] = u[2] = 0.0;
+    if (D == 2 && Q == 9) {
+        u[0] = 1.0 / rho * (f[1] + f[5] + f[8] - f[3] - f[6] - f[7]);
+        u[1] = 1.0 / rho * (f[2] + f[5] + f[6] - f[4] - f[7] - f[8]);
+    } else if (D == 3 && Q == 19) {
+        u[0] = 1.0 / rho * (f[1] - f[3] + f[7] - f[8] - f[9] + f[10] + f[11] + f[12] - f[13] - f[14]);
+        u[1] = 1.0 / rho * (-f[5] + f[6] - f[11] + f[12] + f[13] - f[14] - f[15] + f[16] + f[17] - f[18]);
+        u[2] = 1.0 / rho * (f[2] - f[4] + f[7] + f[8] - f[9] - f[10] + f[15] + f[16] - f[17] - f[18]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < Q; i++) s += cP.e[i][j] * f[i];
+            u[j] = s * 1.0 / rho;
+        }
+    }
+}
+
+// BGKEquilibrium::calc
+template <int D, int Q>
+__device__ __forceinline__ void nb_feq_bgk(double rho, const double (&u)[3], double (&feq)[Q])
+{
+    const double cs2 = cP.cs2;
+    if (D == 2 && Q == 9) {
+        const double prefactor = 1. / cs2;
+        const double scalar_product = u[0] * u[0] + u[1] * u[1];
+        const double uSquareTerm = -scalar_product / (2 * cs2);
+        double weighting = 4. / 9. * rho;
+        double mixedTerm;
+        feq[0] = weighting * (1 + uSquareTerm);
+        weighting = 1. / 9. * rho;
+        mixedTerm = prefactor * (u[0]);
+        feq[1] = weighting * (1 + mixedTerm * (1 + 0.5 * mixedTerm) + uSquareTerm);
+        feq[3] = weighting * (1 - mixedTerm * (1 - 0.5 * mixedTerm) + uSquareTerm);
+        mixedTerm = prefactor * (u[1]);
+        feq[2] = weighting * (1 + mixedTerm * (1 + 0.5 * mixedTerm) + uSquareTerm);
+        feq[4] = weighting * (1 - mixedTerm * (1 - 0.5 * mixedTerm) + uSquareTerm);
+        weighting = 1. / 36. * rho;
+        mixedTerm = prefactor * (u[0] + u[1]);
+        feq[5] = weighting * (1 + mixedTerm * (1 + 0.5 * mixedTerm) + uSquareTerm);
+        feq[7] = weighting * (1 - mixedTerm * (1 - 0.5 * mixedTerm) + uSquareTerm);
+        mixedTerm = prefactor * (-u[0] + u[1]);
+        feq[6] = weighting * (1 + mixedTerm * (1 + 0.5 * mixedTerm) + uSquareTerm);
+        feq[8] = weighting * (1 - mixedTerm * (1 - 0.5 * mixedTerm) + uSquareTerm);
+        return;
+    }
+    double uu_term = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) / (2.0 * cs2);
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        double ue_term = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) / cs2;
+        feq[i] = cP.w[i] * rho * (1 + ue_term * (1 + 0.5 * (ue_term)) + uu_term);
+    }
+}
+
+// QuarticEquilibrium::polynomial
+template <int D, int Q>
+__device__ __forceinline__ void nb_feq_quartic(double rho, const double (&u)[3], double T, double (&feq)[Q])
+{
+    const double cs2 = cP.cs2;
+    double uu_term = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) / (2.0 * cs2);
+    const double T1 = cs2 * (T - 1);
+    const double a_xxx = u[0] * u[0] * u[0] + T1 * (u[0] + u[0] + u[0]);
+    const double a_xxy = u[0] * u[0] * u[1] + T1 * (u[1]);
+    const double a_xyy = u[0] * u[1] * u[1] + T1 * (u[0]);
+    const double a_yyy = u[1] * u[1] * u[1] + T1 * (u[1] + u[1] + u[1]);
+    const double a_xxxx = u[0] * u[0] * u[0] * u[0] + T1 * u[0] * u[0] * 6.0 + T1 * T1 * 3.0;
+    const double a_yyyy = u[1] * u[1] * u[1] * u[1] + T1 * u[1] * u[1] * 6.0 + T1 * T1 * 3.0;
+    const double a_xxxy = u[0] * u[0] * u[0] * u[1] + T1 * (u[0] * u[1] * 3.0);
+    const double a_xyyy = u[0] * u[1] * u[1] * u[1] + T1 * (u[0] * u[1] * 3.0);
+    const double a_xxyy = u[0] * u[0] * u[1] * u[1] + T1 * (u[0] * u[0] + u[1] * u[1]) + T1 * T1;
+    double a_zzz = 0.0, a_xxz = 0.0, a_xzz = 0.0, a_yzz = 0.0, a_yyz = 0.0, a_xyz = 0.0;
+    double a_zzzz = 0.0, a_xzzz = 0.0, a_xxzz = 0.0, a_xxxz = 0.0, a_yzzz = 0.0, a_yyzz = 0.0,
+           a_yyyz = 0.0, a_xxyz = 0.0, a_xyyz = 0.0, a_xyzz = 0.0;
+    if (D == 3) {
+        a_zzz = u[2] * u[2] * u[2] + T1 * (u[2] + u[2] + u[2]);
+        a_xxz = u[0] * u[0] * u[2] + T1 * (u[2]);
+        a_xzz = u[0] * u[2] * u[2] + T1 * (u[0]);
+        a_yzz = u[1] * u[2] * u[2] + T1 * (u[1]);
+        a_yyz = u[1] * u[1] * u[2] + T1 * (u[2]);
+        a_xyz = u[0] * u[1] * u[2];
+        a_zzzz = u[2] * u[2] * u[2] * u[2] + T1 * u[2] * u[2] * 6.0 + T1 * T1 * 3.0;
+        a_xxxz = u[0] * u[0] * u[0] * u[2] + T1 * (u[0] * u[2] * 3.0);
+        a_yyyz = u[1] * u[1] * u[1] * u[2] + T1 * (u[1] * u[2] * 3.0);
+        a_xzzz = u[0] * u[2] * u[2] * u[2] + T1 * (u[0] * u[2] * 3.0);
+        a_yzzz = u[1] * u[2] * u[2] * u[2] + T1 * (u[1] * u[2] * 3.0);
+        a_xxzz = u[0] * u[0] * u[2] * u[2] + T1 * (u[0] * u[0] + u[2] * u[2]) + T1 * T1;
+        a_yyzz = u[1] * u[1] * u[2] * u[2] + T1 * (u[1] * u[1] + u[2] * u[2]) + T1 * T1;
+        a_xyzz = u[0] * u[1] * u[2] * u[2] + T1 * (u[0] * u[1]);
+        a_xyyz = u[0] * u[1] * u[1] * u[2] + T1 * (u[0] * u[2]);
+        a_xxyz = u[0] * u[0] * u[1] * u[2] + T1 * (u[1] * u[2]);
+    }
+    const double c3 = 6. * cs2 * cs2 * cs2;
+    const double c4 = 24. * cs2 * cs2 * cs2 * cs2;
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        const double w = cP.w[i];
+        double ue_term = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) / cs2;
+        double fe = w * rho * (1 + ue_term * (1 + 0.5 * (ue_term)) + uu_term);
+        // (T-1) trace term: the reference's alp/bet double loop only has diagonal contributions
+#pragma unroll
+        for (int a = 0; a < D; a++)
+            fe += rho * w / (2.0 * cs2) * ((T - 1) * cP.e[i][a] * cP.e[i][a] - cs2 * (T - 1));
+        const double* H3 = cP.H3[i];
+        const double* H4 = cP.H4[i];
+        fe += w * rho / c3 * (a_xxx * H3[0] + 3 * (a_xxy * H3[1] + a_xyy * H3[2]) + a_yyy * H3[3]);
+        if (D == 3)
+            fe += w * rho / c3
+                * (a_zzz * H3[4] + 3 * (a_xxz * H3[5] + a_xzz * H3[6] + a_yzz * H3[7] + a_yyz * H3[8])
+                   + 6.0 * a_xyz * H3[9]);
+        fe += w * rho / c4
+            * (H4[0] * a_xxxx + H4[1] * a_yyyy + 6.0 * H4[4] * a_xxyy + 4.0 * H4[3] * a_xyyy + 4.0 * H4[2] * a_xxxy);
+        if (D == 3)
+            fe += w * rho / c4
+                * (H4[5] * a_zzzz + 4.0 * (H4[6] * a_xzzz + H4[9] * a_yzzz + H4[8] * a_xxxz + H4[11] * a_yyyz)
+                   + 6.0 * (H4[7] * a_xxzz + H4[10] * a_yyzz)
+                   + 12.0 * (H4[12] * a_xxyz + H4[13] * a_xyyz + H4[14] * a_xyzz));
+        feq[i] = fe;
+    }
+}
+
+// collideAll body, f only: returns rho, u (unscaled); relaxes f in registers.
+// u_override != nullptr mirrors inInitializationProcedure (velocity taken from the global vector).
+template <int D, int Q, int EQ>
+__device__ __forceinline__ void nb_collide_bgk(double (&f)[Q], double& rho, double (&u)[3], const double* u_override)
+{
+    rho = nb_density<Q>(f);
+    nb_velocity<D, Q>(f, rho, u);
+    if (u_override) {
+#pragma unroll
+        for (int j = 0; j < D; j++) u[j] = u_override[j] / cP.scaling;
+    }
+    double feq[Q];
+    if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, feq);
+    else nb_feq_quartic<D, Q>(rho, u, 1.0, feq);
+    const double tau = cP.tau;
+#pragma unroll
+    for (int p = 0; p < Q; ++p) f[p] -= 1. / tau * (f[p] - feq[p]);
+}
+
+// collideAll body, f + g (relaxWithG).  Writes T and the Knudsen-estimate sensor.
+template <int D, int Q, int EQ>
+__device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q], double& rho, double (&u)[3],
+                                                  double& T, double& sensor, const double* u_override)
+{
+    const double cs2 = cP.cs2;
+    rho = nb_density<Q>(f);
+    nb_velocity<D, Q>(f, rho, u);
+    // calculateTemperature
+    double Tacc = 0.0;
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        double sum = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; a++) sum += (cP.e[i][a] - u[a]) * (cP.e[i][a] - u[a]);
+        Tacc += sum * f[i] / cs2 + g[i];
+    }
+    const double C_v = cP.Cv;
+    T = Tacc * 0.5 / (rho * C_v);
+    if (u_override) {
+#pragma unroll
+        for (int j = 0; j < D; j++) u[j] = u_override[j] / cP.scaling;
+    }
+    double feq[Q];
+    if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, feq);
+    else nb_feq_quartic<D, Q>(rho, u, T, feq);
+    const double gfac = (T) * (2.0 * C_v - D);
+
+    // non-equilibrium moments for the Prandtl correction
+    double Qn[3][3][3];
+    double qg[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Qn[a][b][c] = 0.0;
+    double knudsen = 0.0;
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        const double fneq = f[i] - feq[i];
+        const double gneq = g[i] - feq[i] * gfac;
+        knudsen += fabs(f[i] - feq[i]) / cP.w[i];
+        if (cP.prandtl_set) {
+            double c[3];
+#pragma unroll
+            for (int a = 0; a < D; a++) c[a] = cP.e[i][a] - u[a];
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int b = 0; b < D; b++)
+#pragma unroll
+                    for (int cc = 0; cc < D; cc++) Qn[a][b][cc] += (c[a] * c[b] * c[cc]) * fneq;
+#pragma unroll
+            for (int a = 0; a < D; a++) qg[a] += c[a] * gneq;
+        }
+    }
+    sensor = knudsen / Q;
+
+    double sutherland_factor = 1.0;
+    if (cP.sutherland_set) sutherland_factor = pow(T / 0.85, 0.7);
+    const double visc_tau = (cP.tau - 0.5) * sutherland_factor / (T * rho) + 0.5;
+    const double prandtl_tau = (visc_tau - 0.5) / cP.prandtl + 0.5;
+    const double visc_omega = 1. / visc_tau;
+    const double prandtl_omega = 1. / prandtl_tau;
+    const double prandtl_diff = visc_omega - prandtl_omega;
+    const double cs6 = 6.0 * cs2 * cs2 * cs2;
+#pragma unroll
+    for (int i = 0; i < Q; i++) {
+        double fStar = 0.0, gStar = 0.0;
+        if (cP.prandtl_set) {
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int b = 0; b < D; b++)
+#pragma unroll
+                    for (int c = 0; c < D; c++)
+                        fStar += cP.w[i] * (Qn[a][b][c] * (cP.e[i][a] * cP.e[i][b] * cP.e[i][c]
+                                                            - 3 * cs2 * cP.e[i][c] * (a == b ? 1.0 : 0.0))) / cs6;
+#pragma unroll
+            for (int a = 0; a < D; a++) gStar += cP.w[i] * (qg[a] * cP.e[i][a]) / T;
+        }
+        const double fneq = f[i] - feq[i];
+        const double gneq = g[i] - feq[i] * gfac;
+        f[i] -= visc_omega * fneq - prandtl_diff * fStar;
+        g[i] -= visc_omega * gneq - prandtl_diff * gStar;
+    }
+}

@@ -1,0 +1,99 @@
+// inst.cu -- one translation unit per stencil: compile with -DNB_D=<D> -DNB_Q=<Q> -DNB_NAME=<fn>
+// [-DNB_WITH_G=1] [-DNB_FUSE_G=1].  Each unit owns its own copy of the constant block cP.
+#include "launch.h"
+#include "kernels.cuh"
+
+#ifndef NB_WITH_G
+#define NB_WITH_G 0
+#endif
+#ifndef NB_FUSE_G
+#define NB_FUSE_G 0
+#endif
+#ifndef NB_FUSE_F
+#define NB_FUSE_F 1
+#endif
+
+namespace {
+
+constexpr int D = NB_D;
+constexpr int Q = NB_Q;
+
+const void* s_owner = nullptr;
+uint64_t s_version = 0;
+
+int bind(const NbLaunch& L)
+{
+    if (s_owner != L.owner || s_version != L.version) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(cP, L.hc, sizeof(NbConst), 0, cudaMemcpyHostToDevice, L.stream);
+        if (e != cudaSuccess) return (int)e;
+        s_owner = L.owner;
+        s_version = L.version;
+    }
+    return 0;
+}
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+int fused(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    const unsigned grid = grid_for(L.A.n_slices * 32, 128);
+    if (!L.with_g) {
+#if NB_FUSE_F
+        if (L.eq == NB_EQ_BGK) k_stream_collide_f<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag);
+        else k_stream_collide_f<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag);
+#else
+        return -1;
+#endif
+    } else {
+#if NB_WITH_G && NB_FUSE_G
+        if (L.eq == NB_EQ_BGK) k_stream_collide_fg<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag);
+        else k_stream_collide_fg<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag);
+#else
+        return -1;
+#endif
+    }
+    return (int)cudaGetLastError();
+}
+
+int collide(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    const int64_t n = L.A.n_owned;
+    const unsigned grid = grid_for(n, 128);
+    if (!L.with_g) {
+        if (L.eq == NB_EQ_BGK) k_collide_f<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);
+        else k_collide_f<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);
+    } else {
+#if NB_WITH_G
+        if (L.eq == NB_EQ_BGK) k_collide_fg<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);
+        else k_collide_fg<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);
+#else
+        return -1;
+#endif
+    }
+    return (int)cudaGetLastError();
+}
+
+int conserved(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    k_conserved_partial<D, Q><<<L.n_partial_blocks, 256, 0, L.stream>>>(L.A.n_owned, L.A.stride, L.xf, L.with_g ? L.xg : nullptr, L.partial);
+    k_conserved_final<<<1, 32, 0, L.stream>>>(L.n_partial_blocks, L.partial, L.out);
+    return (int)cudaGetLastError();
+}
+
+const NbStencilOps ops = {D, Q,
+#if NB_FUSE_F || (NB_WITH_G && NB_FUSE_G)
+                          fused,
+#else
+                          nullptr,
+#endif
+                          collide, conserved};
+
+}  // namespace
+
+const NbStencilOps* NB_NAME() { return &ops; }

@@ -1,0 +1,181 @@
+// kernels.cuh -- fused stream+collide and stand-alone collide kernels, templated on the stencil.
+// Instantiated once per (D,Q) by inst.cu (one translation unit per stencil so that the
+// build parallelises and each unit owns its constant-memory block).
+#pragma once
+#include "stream_common.cuh"
+#include "collide.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// kernels: hot path
+// ---------------------------------------------------------------------------------------------
+// Fused stream + collide, f only.  x: current populations (owned + ghosts), y: next.
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(128)
+k_stream_collide_f(StreamArgs A, const double* __restrict__ x, double* __restrict__ y,
+                   double* __restrict__ rho_out, double* __restrict__ u_out, int* __restrict__ flag)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t slice = row >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slice >= A.n_slices) return;
+    const bool active = row < A.n_owned;
+    double f[Q];
+    f[0] = active ? x[row] : 0.0;
+#pragma unroll
+    for (int a = 1; a < Q; a++) {
+        double dummy;
+        nb_row_dot<1>(A, a - 1, slice, lane, x, nullptr, f[a], dummy);
+    }
+    if (!active) return;
+    double rho, u[3];
+    nb_collide_bgk<D, Q, EQ>(f, rho, u, nullptr);
+    if (rho < 1e-10) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) y[(int64_t)q * A.stride + row] = f[q];
+    rho_out[row] = rho;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
+}
+
+// Fused stream + collide for f and g (one pass over the matrix for both distributions).
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(128)
+k_stream_collide_fg(StreamArgs A, const double* __restrict__ xf, const double* __restrict__ xg,
+                    double* __restrict__ yf, double* __restrict__ yg, double* __restrict__ rho_out,
+                    double* __restrict__ u_out, double* __restrict__ T_out, double* __restrict__ s_out,
+                    int* __restrict__ flag)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t slice = row >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slice >= A.n_slices) return;
+    const bool active = row < A.n_owned;
+    double f[Q], g[Q];
+    f[0] = active ? xf[row] : 0.0;
+    g[0] = active ? xg[row] : 0.0;
+#pragma unroll
+    for (int a = 1; a < Q; a++) nb_row_dot<2>(A, a - 1, slice, lane, xf, xg, f[a], g[a]);
+    if (!active) return;
+    double rho, u[3], T, sensor;
+    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, nullptr);
+    if (rho < 1e-10) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        yf[(int64_t)q * A.stride + row] = f[q];
+        yg[(int64_t)q * A.stride + row] = g[q];
+    }
+    rho_out[row] = rho;
+    T_out[row] = T;
+    s_out[row] = sensor;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
+}
+
+// Stand-alone collide (in place), f only.
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(128)
+k_collide_f(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __restrict__ rho_out,
+            double* __restrict__ u_out, int in_init, int* __restrict__ flag)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = fbuf[(int64_t)q * stride + row];
+    double rho, u[3], uo[3];
+    if (in_init) {
+#pragma unroll
+        for (int j = 0; j < D; j++) uo[j] = u_out[(int64_t)j * n + row];
+    }
+    nb_collide_bgk<D, Q, EQ>(f, rho, u, in_init ? uo : nullptr);
+    if (rho < 1e-10) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) fbuf[(int64_t)q * stride + row] = f[q];
+    rho_out[row] = rho;
+    if (!in_init) {
+#pragma unroll
+        for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = u[j] * cP.scaling;
+    }
+}
+
+// Stand-alone collide (in place), f and g.
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(128)
+k_collide_fg(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf,
+             double* __restrict__ rho_out, double* __restrict__ u_out, double* __restrict__ T_out,
+             double* __restrict__ s_out, int in_init, int* __restrict__ flag)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        f[q] = fbuf[(int64_t)q * stride + row];
+        g[q] = gbuf[(int64_t)q * stride + row];
+    }
+    double rho, u[3], uo[3], T, sensor;
+    if (in_init) {
+#pragma unroll
+        for (int j = 0; j < D; j++) uo[j] = u_out[(int64_t)j * n + row];
+    }
+    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, in_init ? uo : nullptr);
+    if (rho < 1e-10) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        fbuf[(int64_t)q * stride + row] = f[q];
+        gbuf[(int64_t)q * stride + row] = g[q];
+    }
+    rho_out[row] = rho;
+    T_out[row] = T;
+    s_out[row] = sensor;
+    if (!in_init) {
+#pragma unroll
+        for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = u[j] * cP.scaling;
+    }
+}
+
+// Conserved sums: deterministic two-stage reduction.  partial[blk*5 + m].
+template <int D, int Q>
+__global__ void __launch_bounds__(256)
+k_conserved_partial(int64_t n, int64_t stride, const double* __restrict__ f,
+                    const double* __restrict__ g, double* __restrict__ partial)
+{
+    __shared__ double sm[5][256];
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double rho = 0.0, m[3] = {0, 0, 0}, e2 = 0.0, gs = 0.0;
+        for (int q = 0; q < Q; q++) {
+            const double v = f[(int64_t)q * stride + i];
+            rho += v;
+            double ee = 0.0;
+            for (int j = 0; j < D; j++) {
+                m[j] += cP.es[q][j] * v;
+                ee += cP.e[q][j] * cP.e[q][j];
+            }
+            e2 += ee * v;
+            if (g) gs += g[(int64_t)q * stride + i];
+        }
+        acc[0] += rho;
+        for (int j = 0; j < 3; j++) acc[1 + j] += m[j];
+        if (g) acc[4] += 0.5 * (e2 / cP.cs2 + gs);
+        else acc[4] += 0.5 * (m[0] * m[0] + m[1] * m[1] + m[2] * m[2]) / rho;
+    }
+    for (int k = 0; k < 5; k++) sm[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s)
+            for (int k = 0; k < 5; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 5) partial[blockIdx.x * 5 + threadIdx.x] = sm[threadIdx.x][0];
+}
+
+static __global__ void k_conserved_final(int n_blocks, const double* __restrict__ partial, double* __restrict__ out)
+{
+    if (threadIdx.x < 5) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; b++) s += partial[b * 5 + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+}
+

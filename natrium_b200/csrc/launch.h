@@ -1,0 +1,37 @@
+// launch.h -- host-side interface between the C-ABI unit (nb200.cu) and the per-stencil
+// kernel units (inst.cu compiled once per (D,Q)).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "stream_common.cuh"
+
+struct NbConst;
+
+struct NbLaunch {
+    cudaStream_t stream;
+    StreamArgs A;
+    const double* xf; const double* xg;   // current populations (fused: read)
+    double* yf; double* yg;               // next populations (fused: write) / in-place buffers (collide)
+    double* rho; double* u; double* T; double* sensor;
+    int* flag;
+    int eq;        // NB_EQ_BGK / NB_EQ_QUARTIC
+    int with_g;
+    int in_init;
+    // constant-block ownership: the unit re-uploads when (owner, version) changed
+    const NbConst* hc; const void* owner; uint64_t version;
+    // conserved sums
+    double* partial; int n_partial_blocks; double* out;
+};
+
+struct NbStencilOps {
+    int D, Q;
+    int (*fused)(const NbLaunch&);       // stream + collide in one kernel; nullptr if not built
+    int (*collide)(const NbLaunch&);     // in-place collide
+    int (*conserved)(const NbLaunch&);   // deterministic conserved sums
+};
+
+const NbStencilOps* nb_ops_d2q9();
+const NbStencilOps* nb_ops_d3q19();
+const NbStencilOps* nb_ops_d3q15();
+const NbStencilOps* nb_ops_d2q25();
+const NbStencilOps* nb_ops_d3q45();

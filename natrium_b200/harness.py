@@ -1,0 +1,312 @@
+"""Synthetic host side: what deal.II/p4est + SemiLagrangian::fillSparseObject hand to the GPU.
+
+In a real NATriuM build the mesh, DoFHandler and the assembled streaming matrix come from
+the reference's host C++.  This module produces the same *kind* of input for
+tests and benchmarks on machines without deal.II: Cartesian (optionally stretched) periodic
+meshes, continuous FE_Q(p) on Gauss-Lobatto points, the per-direction semi-Lagrangian
+interpolation matrix as local CSR blocks, a slab partition with its ghost plan, and the
+Taylor-Green initial fields.  Everything is vectorised numpy so the 129^3-DoF / 7e8-nnz
+benchmark matrix is built in about a minute, block by block.
+
+It is an input generator, not part of the accelerated path, and it is independent of
+``oracle/`` (tests check one against the other).
+
+What it produces follows (L = src/library/natrium):
+  matrix entries   L/advection/SemiLagrangian.cpp:201-242,476-501 (N_j(x_i - dt e_alpha), drop < 1e-10)
+  unit-cell snap   L/advection/SemiLagrangianTools.cpp:41-47
+  dt               L/utilities/CFDSolverUtilities.cpp:92-100
+  TGV fields       L/benchmarks/TaylorGreenVortex2D.cpp:36-60, TaylorGreenVortex3D.cpp:38-72
+  f = f_eq init    L/solver/CFDSolver.cpp:1104-1129, L/solver/CompressibleCFDSolver.h:790-901
+"""
+import math
+
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------
+# 1D building blocks
+# ------------------------------------------------------------------------------------------
+def gauss_lobatto_points(p):
+    """Gauss-Lobatto-Legendre nodes on [0,1] (p+1 of them)."""
+    if p == 1:
+        return np.array([0.0, 1.0])
+    # eigenvalues of the Jacobi matrix for the interior nodes (roots of P'_p = Jacobi(1,1) of degree p-1)
+    k = np.arange(1, p - 1, dtype=np.float64)
+    beta = np.sqrt(k * (k + 2) / ((2 * k + 1) * (2 * k + 3)))
+    J = np.diag(beta, 1) + np.diag(beta, -1)
+    x = np.linalg.eigvalsh(J) if p > 2 else np.array([0.0])
+    # polish with Newton on q(x) = (1-x^2) P_p'(x)
+    for _ in range(5):
+        P0, P1 = np.ones_like(x), x.copy()
+        for n in range(2, p + 1):
+            P0, P1 = P1, ((2 * n - 1) * x * P1 - (n - 1) * P0) / n
+        x = x - (p * (P0 - x * P1)) / (-p * (p + 1) * P1)
+    x = np.sort(np.concatenate([[-1.0], x, [1.0]]))
+    x = 0.5 * (x - x[::-1])          # exact antisymmetry
+    return 0.5 * (x + 1.0)
+
+
+def lagrange_basis(nodes, xi):
+    """All p+1 Lagrange polynomials at points xi: shape (len(xi), p+1); product form."""
+    xi = np.asarray(xi, dtype=np.float64)
+    n = len(nodes)
+    out = np.ones((xi.shape[0], n))
+    for j in range(n):
+        for m in range(n):
+            if m != j:
+                out[:, j] *= (xi - nodes[m]) / (nodes[j] - nodes[m])
+    return out
+
+
+def _snap01(v):
+    v = np.where(np.abs(v) < 1e-10, 0.0, v)
+    return np.where(np.abs(v - 1.0) < 1e-10, 1.0, v)
+
+
+class Axis:
+    """One coordinate axis: cell vertices, the continuous 1D DoF grid and departure tracking."""
+
+    def __init__(self, verts, p, nodes):
+        self.v = np.asarray(verts, dtype=np.float64)
+        self.n = len(self.v) - 1
+        self.p = p
+        self.nodes = nodes
+        self.nd = self.n * p + 1
+        g = np.arange(self.nd)
+        self.home = np.where(g > 0, (g - 1) // p, 0)          # first cell (lexicographic) that sees the DoF
+        self.loc = g - self.home * p
+        h = self.v[self.home + 1] - self.v[self.home]
+        self.x = self.v[self.home] + nodes[self.loc] * h
+
+    def track(self, delta):
+        """Departure of every 1D DoF displaced by ``delta`` through periodic cells.
+        Returns (cols, wts): per DoF the k 1D DoF indices / weights with k = 1 if delta == 0 else p+1."""
+        p, n, v = self.p, self.n, self.v
+        L = v[-1] - v[0]
+        c = self.home.copy()
+        xd = self.x + delta
+        for _ in range(60):
+            xi = _snap01((xd - v[c]) / (v[c + 1] - v[c]))
+            lo, hi = xi < 0, xi > 1
+            if not (lo.any() or hi.any()):
+                break
+            wrap_lo, wrap_hi = lo & (c == 0), hi & (c == n - 1)
+            xd = np.where(wrap_lo, xd + L, np.where(wrap_hi, xd - L, xd))
+            c = np.where(lo, np.where(c == 0, n - 1, c - 1), np.where(hi, np.where(c == n - 1, 0, c + 1), c))
+        else:
+            raise RuntimeError("departure point tracking did not terminate")
+        W = lagrange_basis(self.nodes, xi)
+        if delta == 0.0:
+            j = np.argmax(np.abs(W), axis=1)
+            cols = (c * p + j)[:, None]
+            wts = np.take_along_axis(W, j[:, None], axis=1)
+        else:
+            cols = c[:, None] * p + np.arange(p + 1)[None, :]
+            wts = W
+        return cols.astype(np.int64), wts
+
+
+# ------------------------------------------------------------------------------------------
+# problem + partition
+# ------------------------------------------------------------------------------------------
+class CartesianProblem:
+    """Periodic hyper-rectangle, cells[d] cells per axis, FE order p.  DoFs are numbered
+    lexicographically (x fastest); periodic faces are not identified (as in the reference)."""
+
+    def __init__(self, dim, cells, p, length=2 * math.pi, verts=None):
+        self.dim, self.p = dim, p
+        cells = [cells] * dim if np.isscalar(cells) else list(cells)
+        length = [length] * dim if np.isscalar(length) else list(length)
+        if verts is None:
+            verts = [length[d] * np.arange(cells[d] + 1) / cells[d] for d in range(dim)]
+        self.nodes = gauss_lobatto_points(p)
+        self.axes = [Axis(verts[d], p, self.nodes) for d in range(dim)]
+        self.nd = [a.nd for a in self.axes]
+        self.N = int(np.prod(self.nd))
+        self.plane = int(np.prod(self.nd[:-1]))       # DoFs per plane of the last axis
+
+    def min_vertex_distance(self):
+        return min(float(np.min(np.diff(a.v))) for a in self.axes)
+
+    def timestep(self, stencil, cfl):
+        return cfl * self.min_vertex_distance() / (stencil.getMaxParticleVelocityMagnitude() * self.p * self.p)
+
+    def points_of_planes(self, planes):
+        """Support points (n, dim) of all DoFs on the given last-axis planes, lexicographic."""
+        ax = [a.x for a in self.axes[:-1]] + [self.axes[-1].x[np.asarray(planes)]]
+        grids = np.meshgrid(*ax[::-1], indexing="ij")[::-1]   # last axis slowest, x fastest
+        return np.stack([g.reshape(-1) for g in grids], axis=1)
+
+
+class SlabPartition:
+    """Rank r owns a contiguous range of planes of the last axis (cells split evenly; the shared
+    plane between two slabs belongs to the lower rank, rank 0 also owns plane 0).  Ghosts are whole
+    planes, ordered by owner rank then lexicographic id."""
+
+    def __init__(self, problem, stencil, dt, rank=0, nranks=1):
+        self.pb, self.rank, self.nranks = problem, rank, nranks
+        ax = problem.axes[-1]
+        if nranks > ax.n:
+            raise ValueError("more ranks than cell layers")
+        bounds = [(ax.n * r) // nranks for r in range(nranks + 1)]
+        self.plane_owner = np.empty(ax.nd, dtype=np.int64)
+        for r in range(nranks):
+            lo = 0 if r == 0 else bounds[r] * ax.p + 1
+            hi = bounds[r + 1] * ax.p + 1
+            self.plane_owner[lo:hi] = r
+        deltas = sorted(set(float(-dt * e[-1]) for e in stencil.getDirections()[1:]))
+        self._tracks = {d: ax.track(d) for d in deltas}
+        self.owned_planes = np.nonzero(self.plane_owner == rank)[0]
+        self.ghost_planes = self._ghost_planes_of(rank)
+        self.n_owned = len(self.owned_planes) * problem.plane
+        self.n_ghost = len(self.ghost_planes) * problem.plane
+        # plane -> local base index
+        self.base = np.full(ax.nd, -1, dtype=np.int64)
+        self.base[self.owned_planes] = np.arange(len(self.owned_planes)) * problem.plane
+        self.base[self.ghost_planes] = self.n_owned + np.arange(len(self.ghost_planes)) * problem.plane
+
+    def _ghost_planes_of(self, r):
+        own = np.nonzero(self.plane_owner == r)[0]
+        need = set()
+        for cols, _ in self._tracks.values():
+            need.update(np.unique(cols[own]).tolist())
+        gp = np.array(sorted(need - set(own.tolist())), dtype=np.int64)
+        if len(gp):
+            gp = gp[np.lexsort((gp, self.plane_owner[gp]))]
+        return gp
+
+    def halo_plan(self):
+        """(nbr_rank, send_off, send_idx, recv_off) for nb200_set_halo."""
+        plane = self.pb.plane
+        nbrs = sorted(set(self.plane_owner[self.ghost_planes].tolist())
+                      | {r for r in range(self.nranks) if r != self.rank
+                         and np.any(self.plane_owner[self._ghost_planes_of(r)] == self.rank)})
+        send_off, recv_off, send_idx = [0], [0], []
+        for r in nbrs:
+            theirs = self._ghost_planes_of(r)
+            mine_for_them = theirs[self.plane_owner[theirs] == self.rank]
+            for pl in mine_for_them:
+                send_idx.append(self.base[pl] + np.arange(plane))
+            send_off.append(send_off[-1] + len(mine_for_them) * plane)
+            recv_off.append(recv_off[-1] + int(np.sum(self.plane_owner[self.ghost_planes] == r)) * plane)
+        send_idx = np.concatenate(send_idx).astype(np.int32) if send_idx else np.zeros(0, dtype=np.int32)
+        return (np.array(nbrs, dtype=np.int32), np.array(send_off, dtype=np.int64), send_idx,
+                np.array(recv_off, dtype=np.int64))
+
+    def owned_points(self):
+        return self.pb.points_of_planes(self.owned_planes)
+
+    def owned_global_ids(self):
+        return (self.owned_planes[:, None] * self.pb.plane + np.arange(self.pb.plane)[None, :]).reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------
+# streaming matrix
+# ------------------------------------------------------------------------------------------
+def assemble_direction(problem, part, stencil, dt, alpha):
+    """Local CSR (rowptr int64, col int32, val f64) of block (alpha-1, alpha-1): rows = owned DoFs
+    of ``part`` in local order, columns in local numbering (owned, then ghosts)."""
+    e = stencil.getDirection(alpha)
+    dim = problem.dim
+    tr = [problem.axes[d].track(float(-dt * e[d])) for d in range(dim)]
+    own = part.owned_planes
+    zc, zw = tr[-1][0][own], tr[-1][1][own]
+    zbase = part.base[zc]
+    if (zbase < 0).any():
+        raise RuntimeError("departure point outside owned + ghost planes (time step too large)")
+    if dim == 2:
+        xc, xw = tr[0]
+        col = zbase[:, None, :, None] + xc[None, :, None, :]
+        val = xw[None, :, None, :] * zw[:, None, :, None]
+    else:
+        xc, xw = tr[0]
+        yc, yw = tr[1]
+        ndx = problem.nd[0]
+        col = (zbase[:, None, None, :, None, None] + yc[None, :, None, None, :, None] * ndx
+               + xc[None, None, :, None, None, :])
+        val = (xw[None, None, :, None, None, :] * yw[None, :, None, None, :, None]) * zw[:, None, None, :, None, None]
+    k = int(np.prod(col.shape[dim:]))
+    rows = int(np.prod(col.shape[:dim]))
+    col = np.ascontiguousarray(np.broadcast_to(col, val.shape).reshape(rows, k))
+    val = np.ascontiguousarray(val.reshape(rows, k))
+    keep = np.abs(val) >= 1e-10
+    if keep.all():
+        rowptr = np.arange(rows + 1, dtype=np.int64) * k
+        return rowptr, col.reshape(-1).astype(np.int32), val.reshape(-1)
+    rowptr = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int64)
+    return rowptr, col[keep].astype(np.int32), val[keep]
+
+
+def upload_streaming_matrix(ctx, problem, part, stencil, dt):
+    """Assemble and hand over all diagonal blocks one at a time (peak host memory = one block)."""
+    nnz = 0
+    for alpha in range(1, stencil.getQ()):
+        rowptr, col, val = assemble_direction(problem, part, stencil, dt, alpha)
+        ctx.upload_block_csr(alpha - 1, alpha - 1, rowptr, col, val)
+        nnz += len(val)
+    ctx.finalize_matrix()
+    return nnz
+
+
+# ------------------------------------------------------------------------------------------
+# initial fields
+# ------------------------------------------------------------------------------------------
+def taylor_green_2d(x, length=2 * math.pi):
+    k = 2 * math.pi / length
+    u = np.stack([np.sin(k * x[:, 0]) * np.cos(k * x[:, 1]), -np.cos(k * x[:, 0]) * np.sin(k * x[:, 1])])
+    return np.ones(x.shape[0]), u
+
+
+def taylor_green_3d(x, cs, compressible=False, density_numerator=1.0):
+    u = np.stack([np.sin(x[:, 0]) * np.cos(x[:, 1]) * np.cos(x[:, 2]),
+                  -np.cos(x[:, 0]) * np.sin(x[:, 1]) * np.cos(x[:, 2]), np.zeros(x.shape[0])])
+    pr = (np.cos(2 * x[:, 0]) + np.cos(2 * x[:, 1])) * (np.cos(2 * x[:, 2]) + 2) / 16.
+    rho = 1.0 + (pr * density_numerator if compressible else pr / (cs * cs))
+    return rho, u
+
+
+def equilibrium_distributions(stencil, rho, u):
+    """f_eq(rho, u) to second order (BGKStandard::getEquilibriumDistribution); returns (Q, n)."""
+    e, w, cs2 = stencil.getDirections(), stencil.getWeights(), stencil.getSpeedOfSoundSquare()
+    eu = e @ u / cs2
+    uu = np.sum(u * u, axis=0) / (2 * cs2)
+    return w[:, None] * rho[None, :] * (1 + eu * (1 + 0.5 * eu) - uu[None, :])
+
+
+def quartic_equilibrium_distributions(stencil, rho, u, T, gamma):
+    """Fourth-order Hermite equilibrium with temperature and g = f_eq T (2 Cv - D)
+    (CompressibleCFDSolver::initializeDistributions); tensor form via einsum.  Returns f, g (Q, n)."""
+    s = stencil.getScaling()
+    e = stencil.getDirections() / s
+    w = stencil.getWeights()
+    cs2 = stencil.getSpeedOfSoundSquare() / (s * s)
+    D = e.shape[1]
+    v = u / s
+    I = np.eye(D)
+    T1 = cs2 * (T - 1.0)
+    # Hermite tensors of the directions
+    H2 = np.einsum("ia,ib->iab", e, e) - cs2 * I
+    H3 = (np.einsum("ia,ib,ic->iabc", e, e, e)
+          - cs2 * (np.einsum("ia,bc->iabc", e, I) + np.einsum("ib,ac->iabc", e, I) + np.einsum("ic,ab->iabc", e, I)))
+    ee = np.einsum("ia,ib->iab", e, e)
+    H4 = (np.einsum("ia,ib,ic,id->iabcd", e, e, e, e)
+          - cs2 * (np.einsum("iab,cd->iabcd", ee, I) + np.einsum("iac,bd->iabcd", ee, I) + np.einsum("iad,bc->iabcd", ee, I)
+                   + np.einsum("ibc,ad->iabcd", ee, I) + np.einsum("ibd,ac->iabcd", ee, I) + np.einsum("icd,ab->iabcd", ee, I))
+          + cs2 * cs2 * (np.einsum("ab,cd->abcd", I, I) + np.einsum("ac,bd->abcd", I, I) + np.einsum("ad,bc->abcd", I, I)))
+    # moments of the Maxwellian
+    a2 = np.einsum("an,bn->abn", v, v) + I[:, :, None] * T1
+    a3 = (np.einsum("an,bn,cn->abcn", v, v, v)
+          + T1 * (np.einsum("ab,cn->abcn", I, v) + np.einsum("bc,an->abcn", I, v) + np.einsum("ac,bn->abcn", I, v)))
+    vv = np.einsum("an,bn->abn", v, v)
+    dd = np.einsum("ab,cd->abcd", I, I) + np.einsum("ac,bd->abcd", I, I) + np.einsum("ad,bc->abcd", I, I)
+    a4 = (np.einsum("an,bn,cn,dn->abcdn", v, v, v, v)
+          + T1 * (np.einsum("abn,cd->abcdn", vv, I) + np.einsum("acn,bd->abcdn", vv, I) + np.einsum("adn,bc->abcdn", vv, I)
+                  + np.einsum("bcn,ad->abcdn", vv, I) + np.einsum("bdn,ac->abcdn", vv, I) + np.einsum("cdn,ab->abcdn", vv, I))
+          + T1 * T1 * dd[..., None])
+    series = (1.0 + (e @ v) / cs2
+              + np.einsum("iab,abn->in", H2, a2) / (2 * cs2 ** 2)
+              + np.einsum("iabc,abcn->in", H3, a3) / (6 * cs2 ** 3)
+              + np.einsum("iabcd,abcdn->in", H4, a4) / (24 * cs2 ** 4))
+    f = w[:, None] * rho[None, :] * series
+    g = f * T * (2.0 / (gamma - 1.0) - D)
+    return f, g

@@ -1,0 +1,270 @@
+"""Host-side mirror of the reference interfaces the hot path sits behind.
+
+Same names, argument meaning and error behaviour as the reference (L = src/library/natrium):
+
+  DistributionFunctions   L/solver/DistributionFunctions.h:47-300
+  SemiLagrangian          L/advection/AdvectionOperator.h:118-173,190 + SemiLagrangian.h:150-179
+  selectCollision         L/collision_advanced/CollisionSelection.h:60-67,115-122
+  CFDSolver               L/solver/CFDSolver.cpp:659-754 (stream), 807-843 (collide), 877-902 (run)
+  CompressibleCFDSolver   L/solver/CompressibleCFDSolver.h:181-314,739-788,1006-1051
+
+Storage and arithmetic live in libnatrium_b200 (CUDA); these classes only hold a context
+handle and forward.  The mesh side (ProblemDescription) is the synthetic harness here; in a
+NATriuM build it is deal.II (INTEGRATION.md shows the C++ shim against the real headers).
+"""
+import numpy as np
+
+from . import _capi, harness
+from ._capi import CollisionException  # noqa: F401  (re-exported like natrium::CollisionException)
+from .stencils import Stencil
+
+BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = "BGK_STANDARD", "KBC_STANDARD", "MRT_ENTROPIC"
+BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = "BGK_EQUILIBRIUM", "QUARTIC_EQUILIBRIUM"
+_SCHEMES = {BGK_STANDARD: _capi.BGK_STANDARD, KBC_STANDARD: _capi.KBC_STANDARD, MRT_ENTROPIC: _capi.MRT_ENTROPIC}
+_EQUILIBRIA = {BGK_EQUILIBRIUM: _capi.BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM: _capi.QUARTIC_EQUILIBRIUM}
+
+
+class SolverConfiguration:
+    """The getters GeneralCollisionData / CFDSolver read on the path (defaults of
+    L/solver/SolverConfiguration.cpp:17-293: CFL 0.4, D2Q9, scaling 1, BGK standard, BGK eq, gamma 1.4, Pr 1)."""
+
+    def __init__(self):
+        self._stencil, self._scaling, self._cfl, self._p = "Stencil_D2Q9", 1.0, 0.4, 1
+        self._collision, self._equilibrium = BGK_STANDARD, BGK_EQUILIBRIUM
+        self._gamma, self._prandtl, self._prandtl_set, self._sutherland = 1.4, 1.0, False, False
+        self._n_steps = 0
+
+    def setStencil(self, s): self._stencil = s if s.startswith("Stencil_") else "Stencil_" + s
+    def getStencil(self): return self._stencil
+    def setStencilScaling(self, s): self._scaling = float(s)
+    def getStencilScaling(self): return self._scaling
+    def setCFL(self, c): self._cfl = float(c)
+    def getCFL(self): return self._cfl
+    def setSedgOrderOfFiniteElement(self, p): self._p = int(p)
+    def getSedgOrderOfFiniteElement(self): return self._p
+    def setCollisionScheme(self, c): self._collision = c
+    def getCollisionScheme(self): return self._collision
+    def setEquilibriumScheme(self, e): self._equilibrium = e
+    def getEquilibriumScheme(self): return self._equilibrium
+    def setHeatCapacityRatioGamma(self, g): self._gamma = float(g)
+    def getHeatCapacityRatioGamma(self): return self._gamma
+    def setPrandtlNumber(self, pr): self._prandtl, self._prandtl_set = float(pr), True
+    def getPrandtlNumber(self): return self._prandtl
+    def isPrandtlNumberSet(self): return self._prandtl_set
+    def setSutherlandLaw(self, on=True): self._sutherland = bool(on)
+    def isSutherlandLawSet(self): return self._sutherland
+    def setNumberOfTimeSteps(self, n): self._n_steps = int(n)
+    def getNumberOfTimeSteps(self): return self._n_steps
+
+
+class DistributionFunctions:
+    """Device-resident container: Q direction-major arrays of n_owned (+ghost) doubles.
+    ``which`` 0 = f, 1 = g of the owning context."""
+
+    def __init__(self, ctx, which=0):
+        self._ctx, self._which = ctx, which
+
+    def getQ(self): return self._ctx.Q
+    def size(self): return self._ctx.Q
+    def n_owned(self): return self._ctx.n_owned
+
+    def at(self, i):
+        """Host copy of f.at(i) (owned entries) -- like ExtractView, but a download."""
+        return self._ctx.download_population(self._which, i)
+
+    def set(self, i, values):
+        self._ctx.upload_population(self._which, i, values)
+
+    def getFStream(self):
+        return np.stack([self.at(i) for i in range(1, self.getQ())])
+
+    def to_host(self, out=None):
+        return self._ctx.download_populations(self._which, out)
+
+    def from_host(self, arr):
+        self._ctx.upload_populations(self._which, arr)
+
+    def updateGhosted(self):
+        self._ctx.update_ghosted()
+
+
+class SemiLagrangian:
+    """AdvectionOperator for semi-Lagrangian streaming, device backed."""
+
+    def __init__(self, problem, orderOfFiniteElement, stencil, delta_t=0.0, ctx=None, rank=0, nranks=1):
+        assert orderOfFiniteElement == problem.p
+        self._problem, self._stencil, self._dt = problem, stencil, float(delta_t)
+        self._ctx, self._rank, self._nranks = ctx, rank, nranks
+        self._part = None
+        self._nnz = 0
+
+    # -- setup (host, once)
+    def setupDoFs(self):
+        pass   # DoFs of the synthetic problem are implicit in the Cartesian grid
+
+    def setDeltaT(self, delta_t):
+        """updateSparsityPattern() in the reference; here the partition/ghost plan depends on dt."""
+        self._dt = float(delta_t)
+        self._part = harness.SlabPartition(self._problem, self._stencil, self._dt, self._rank, self._nranks)
+
+    def getDeltaT(self): return self._dt
+    def getPartition(self): return self._part
+    def getLocallyOwnedDofs(self): return self._part.owned_global_ids()
+    def getNumberOfDoFs(self): return self._problem.N
+
+    def reassemble(self):
+        """fillSparseObject(false) + compress on the host, then the blocks go to the device."""
+        ctx = self._ctx
+        self._nnz = harness.upload_streaming_matrix(ctx, self._problem, self._part, self._stencil, self._dt)
+        if self._nranks > 1:
+            ctx.set_halo(*self._part.halo_plan())
+
+    def getSystemMatrix(self):
+        return self._ctx.matrix_info()
+
+    # -- per step
+    def stream(self, f_old, f, t):
+        """f_old = f; f.FStream = M f_old.FStream; boundary handler (no hits for periodic); returns dt."""
+        self._ctx.stream(f._which)
+        return self._dt
+
+    def applyBoundaryConditions(self, f_old, f, t):
+        pass   # periodic problems: SemiLagrangianBoundaryHandler has no hits
+
+
+def selectCollision(configuration, problemDescription, f, *args):
+    """Both reference overloads:
+       selectCollision(cfg, pd, f, densities, velocities, owned, viscosity, delta_t, stencil, inInit)
+       selectCollision(cfg, pd, f, g, densities, velocities, temperature, maskShockSensor, owned, viscosity, delta_t, stencil, inInit)
+    densities / velocities (/temperature/maskShockSensor) are numpy arrays that are overwritten
+    (velocities is read when inInitializationProcedure is true)."""
+    with_g = isinstance(args[0], DistributionFunctions)
+    if with_g:
+        g, densities, velocities, temperature, mask, owned, viscosity, delta_t, stencil, in_init = args
+    else:
+        densities, velocities, owned, viscosity, delta_t, stencil, in_init = args
+    ctx = f._ctx
+    if configuration.getStencil() != stencil.getStencilType():
+        raise CollisionException(_capi.NB200_ERR_UNSUPPORTED, "Severe error: Collision model not implemented yet -- cf. CollisionSelection.h")
+    ctx.set_collision(viscosity, delta_t, scheme=_SCHEMES[configuration.getCollisionScheme()],
+                      equilibrium=_EQUILIBRIA[configuration.getEquilibriumScheme()], with_g=with_g, in_init=in_init,
+                      gamma=configuration.getHeatCapacityRatioGamma(),
+                      prandtl=configuration.getPrandtlNumber() if configuration.isPrandtlNumberSet() else None,
+                      sutherland=configuration.isSutherlandLawSet())
+    if in_init:
+        ctx.upload_velocity(np.asarray(velocities))
+    ctx.collide()
+    ctx.synchronize()     # surfaces the density exception here, like the reference's throw inside collideAll
+    if with_g:
+        rho, u, T, s = ctx.download_moments(want_T=True)
+        temperature[...] = T
+        mask[...] = s
+    else:
+        rho, u = ctx.download_moments()
+    densities[...] = rho
+    if not in_init:
+        np.asarray(velocities)[...] = u
+
+
+class CFDSolver:
+    """Time loop owner.  ``run()`` keeps everything on the device (one fused kernel per step);
+    ``stream()`` / ``collide()`` are the reference-ordered single operators."""
+
+    def __init__(self, configuration, problem, viscosity, device=0, rank=0, nranks=1, unique_id=None, with_g=False):
+        self.m_configuration, self.m_problem, self.m_viscosity = configuration, problem, float(viscosity)
+        self.m_stencil = Stencil(configuration.getStencil(), configuration.getStencilScaling())
+        self.ctx = _capi.Context(device, rank, nranks, unique_id)
+        st = self.m_stencil
+        self.ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+        self.m_advectionOperator = SemiLagrangian(problem, configuration.getSedgOrderOfFiniteElement(), st, 0.0,
+                                                  self.ctx, rank, nranks)
+        self.m_advectionOperator.setupDoFs()
+        dt = problem.timestep(st, configuration.getCFL())
+        self.m_advectionOperator.setDeltaT(dt)
+        part = self.m_advectionOperator.getPartition()
+        self.ctx.set_layout(part.n_owned, part.n_ghost, with_g)
+        self.m_advectionOperator.reassemble()
+        self.m_f = DistributionFunctions(self.ctx, 0)
+        self.m_time, self.m_i = 0.0, 0
+        n = part.n_owned
+        self.m_density = np.ones(n)
+        self.m_velocity = np.zeros((st.getD(), n))
+        self._with_g = with_g
+
+    def getTimeStepSize(self): return self.m_advectionOperator.getDeltaT()
+    def getStencil(self): return self.m_stencil
+    def getAdvectionOperator(self): return self.m_advectionOperator
+    def getNumberOfDoFs(self): return self.m_problem.N
+    def getF(self): return self.m_f
+    def getDensity(self): return self.m_density
+    def getVelocity(self): return self.m_velocity
+
+    def setInitialFields(self, rho, u):
+        """initializeDistributions(): f = f_eq(rho0, u0) on the owned DoFs."""
+        self.m_density[...] = rho
+        self.m_velocity[...] = u
+        self.m_f.from_host(harness.equilibrium_distributions(self.m_stencil, rho, u))
+
+    def _configure_collision(self):
+        cfg = self.m_configuration
+        self.ctx.set_collision(self.m_viscosity, self.getTimeStepSize(), scheme=_SCHEMES[cfg.getCollisionScheme()],
+                               equilibrium=_EQUILIBRIA[cfg.getEquilibriumScheme()], with_g=self._with_g,
+                               gamma=cfg.getHeatCapacityRatioGamma(),
+                               prandtl=cfg.getPrandtlNumber() if cfg.isPrandtlNumberSet() else None,
+                               sutherland=cfg.isSutherlandLawSet())
+
+    def stream(self):
+        self.m_advectionOperator.stream(self.m_f, self.m_f, self.m_time)
+        self.m_time += self.getTimeStepSize()
+
+    def collide(self):
+        selectCollision(self.m_configuration, self.m_problem, self.m_f, self.m_density, self.m_velocity,
+                        None, self.m_viscosity, self.getTimeStepSize(), self.m_stencil, False)
+
+    def run(self, n_steps=None):
+        """collide(); then n x (stream; collide) -- fused on the device."""
+        n = self.m_configuration.getNumberOfTimeSteps() if n_steps is None else n_steps
+        self.collide()
+        self._configure_collision()
+        self.ctx.step(n)
+        self.ctx.synchronize()
+        self.m_i += n
+        self.m_time += n * self.getTimeStepSize()
+        self.m_density[...], self.m_velocity[...] = self.ctx.download_moments()[:2]
+
+
+class CompressibleCFDSolver(CFDSolver):
+    """f + g solver (second distribution carries the internal energy)."""
+
+    def __init__(self, configuration, problem, viscosity, **kw):
+        super().__init__(configuration, problem, viscosity, with_g=True, **kw)
+        self.m_g = DistributionFunctions(self.ctx, 1)
+        n = self.ctx.n_owned
+        self.m_temperature = np.ones(n)
+        self.m_maskShockSensor = np.zeros(n)
+
+    def setInitialFields(self, rho, u, T):
+        self.m_density[...], self.m_velocity[...], self.m_temperature[...] = rho, u, T
+        f, g = harness.quartic_equilibrium_distributions(self.m_stencil, rho, u, T,
+                                                         self.m_configuration.getHeatCapacityRatioGamma())
+        self.m_f.from_host(f)
+        self.m_g.from_host(g)
+
+    def gStream(self):
+        self.m_advectionOperator.stream(self.m_g, self.m_g, self.m_time)
+
+    def collide(self):
+        selectCollision(self.m_configuration, self.m_problem, self.m_f, self.m_g, self.m_density, self.m_velocity,
+                        self.m_temperature, self.m_maskShockSensor, None, self.m_viscosity, self.getTimeStepSize(),
+                        self.m_stencil, False)
+
+    def run(self, n_steps=None):
+        n = self.m_configuration.getNumberOfTimeSteps() if n_steps is None else n_steps
+        self.collide()
+        self._configure_collision()
+        self.ctx.step(n)
+        self.ctx.synchronize()
+        self.m_i += n
+        self.m_time += n * self.getTimeStepSize()
+        rho, u, T, s = self.ctx.download_moments(want_T=True)
+        self.m_density[...], self.m_velocity[...], self.m_temperature[...], self.m_maskShockSensor[...] = rho, u, T, s
