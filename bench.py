@@ -34,8 +34,8 @@ UNIT = "MDoF*Q/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=32, help="cells per axis per GPU (32 = refinement 5)")
     ap.add_argument("--order", type=int, default=4)
@@ -67,6 +67,10 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:      # nvidia-smi needs a moment to start
+                time.sleep(0.05)
+            self.rows.clear()                                     # keep only samples taken under load
         except OSError:
             self.proc = None
 
@@ -113,7 +117,7 @@ def ncu_traffic(workload_key):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup, layers):
+def cpu_reference_run(args, steps, warmup, layers, target_s=12.0):
     """Reference-ordered CPU step (oracle port, OpenMP over rows/DoFs) on a z-slab sample of the workload."""
     from natrium_b200 import harness
     from natrium_b200.stencils import Stencil
@@ -140,6 +144,10 @@ def cpu_reference_run(args, steps, warmup, layers):
     stepper = cpu.ReferenceOrderStepper(ost, blocks, n, 2 * math.pi, dt)
     for _ in range(warmup):
         stepper.step(f)
+    if steps <= 0:                       # calibrate: about `target_s` seconds of CPU work
+        t0 = time.perf_counter()
+        stepper.step(f)
+        steps = int(max(3, min(2000, target_s / max(1e-4, time.perf_counter() - t0))))
     t0 = time.perf_counter()
     for _ in range(steps):
         stepper.step(f)
@@ -156,7 +164,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 40))
+    steps = max(1, min(args.steps, 400))
     base, ms = cpu_reference_run(args, steps, max(1, min(args.warmup, 3)), args.cpu_sample_layers)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": ms, "higher_is_better": True,
@@ -256,6 +264,8 @@ def run_ours(args):
     hf.numpy()[...] = ctx.download_populations(0)
     hrho = np.empty(n); hu = np.empty((D, n))
     e2e_steps = max(1, args.e2e_steps)
+    import ctypes
+    _dp = ctypes.POINTER(ctypes.c_double)
 
     def e2e_step():
         ctx.upload_populations_async(0, hf.data_ptr())
@@ -263,8 +273,6 @@ def run_ours(args):
         ctx.download_populations_async(0, hf.data_ptr())
         ctx.lib.nb200_download_moments(ctx._h, hrho.ctypes.data_as(_dp), hu.ctypes.data_as(_dp), None, None, n)
 
-    import ctypes
-    _dp = ctypes.POINTER(ctypes.c_double)
     e2e_step()
     barrier()
     ctx.timer_start()
@@ -297,7 +305,7 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_base, _ = cpu_reference_run(args, 10, 1, args.cpu_sample_layers)
+            cpu_base, _ = cpu_reference_run(args, 0, 1, args.cpu_sample_layers)
         except Exception as ex:    # the baseline is a reported number, never a reason to lose the bench line
             cpu_base = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
 

@@ -122,6 +122,10 @@ struct nb200_ctx {
 
 static const NbStencilOps* find_ops(int D, int Q);
 
+// Stamp for the constant block: process-wide and monotonic, so a new context that happens to reuse a freed
+// context's address can never be mistaken for it by the per-stencil units' upload cache.
+static uint64_t g_const_stamp = 1;
+
 static int fail(nb200_ctx* c, int code, const char* fmt, ...)
 {
     char buf[512];
@@ -404,7 +408,7 @@ extern "C" int nb200_set_stencil(nb200_ctx* c, int D, int Q, const double* e_sca
     c->stencil_set = true;
     c->collision_set = false;
     c->ops = find_ops(D, Q);
-    c->const_version++;
+    c->const_version = ++g_const_stamp;
     return NB200_OK;
 }
 
@@ -674,7 +678,7 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     h.prandtl_set = p->prandtl_set;
     h.sutherland_set = p->sutherland_set;
     c->collision_set = true;
-    c->const_version++;
+    c->const_version = ++g_const_stamp;
     return NB200_OK;
 }
 

@@ -1,0 +1,139 @@
+"""Host-side logic on CPU: the synthetic assembly (product harness) against the oracle's path-tracing
+assembly, the stencil tables against the oracle's and the reference sources, and the slab partition /
+ghost plan (single process simulation of the exchange)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from natrium_b200 import harness
+from natrium_b200.stencils import Stencil
+from oracle import assembly, stencils as ost
+
+REF = "/root/reference/src/library/natrium/stencils"
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D3Q19", "D3Q15", "D2Q25H", "D3Q45"])
+def test_stencil_tables(name):
+    s = Stencil(name, 1.7)
+    e, w, cs2, vm = ost.make(name, 1.7)
+    assert np.array_equal(s.getDirections(), e) and np.array_equal(s.getWeights(), w)
+    assert s.getSpeedOfSoundSquare() == cs2 and s.getMaxParticleVelocityMagnitude() == vm
+    assert abs(w.sum() - 1) < 1e-12
+    assert np.max(np.abs(w @ e)) < 1e-12                          # first moment vanishes
+    second = np.einsum("i,ia,ib->ab", w, e, e)
+    assert np.max(np.abs(second - cs2 * np.eye(e.shape[1]))) < 1e-10   # isotropy with cs2 = scaling^2/3
+    for i in range(s.getQ()):
+        j = s.getIndexOfOppositeDirection(i)
+        assert np.max(np.abs(e[i] + e[j])) < 1e-14
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference sources not mounted (GPU box)")
+def test_d3q45_table_against_reference_source():
+    """The 45 literal direction rows and weights, parsed straight from L/stencils/D3Q45.cpp."""
+    src = open(os.path.join(REF, "D3Q45.cpp")).read()
+    rows = re.findall(r"\{\s*(-?[0-9.]+)\s*,\s*(-?[0-9.]+)\s*,\s*(-?[0-9.]+)\s*\}", src)
+    raw = np.array([[float(a) for a in r] for r in rows])
+    assert raw.shape == (45, 3)
+    e, w, _, _ = ost.make("D3Q45", 2.0)
+    assert np.array_equal(e, 2.0 * raw / math.sqrt(3))
+    wsrc = re.search(r"vector<double> result \{(.*?)\};", src, flags=re.S).group(1)
+    wref = np.array([float(x) for x in re.findall(r"[0-9.]+", wsrc)])
+    assert np.array_equal(w, wref)
+
+
+def test_gll_points():
+    for p in range(1, 9):
+        a, b = harness.gauss_lobatto_points(p), assembly.gll_nodes(p)
+        assert np.max(np.abs(a - b)) < 2e-16
+    assert abs(harness.gauss_lobatto_points(4)[1] - (1 - math.sqrt(3 / 7)) / 2) < 1e-16
+
+
+CASES = [(2, 8, 4, "D2Q9", math.sqrt(3) / 0.05, 0.4, 1), (2, 4, 2, "D2Q25H", 1.0, 1.0, 1), (2, 6, 3, "D2Q9", 1.0, 0.4, 3),
+         (3, 3, 2, "D3Q19", math.sqrt(3) / 0.05, 0.4, 1), (3, 4, 2, "D3Q19", 1.0, 0.4, 2), (3, 2, 2, "D3Q45", 1.0, 0.4, 1),
+         (3, 4, 1, "D3Q15", 1.0, 0.4, 4)]
+
+
+def local_to_global(pb, part):
+    gid = part.owned_global_ids()
+    if len(part.ghost_planes):
+        gid = np.concatenate([gid, (part.ghost_planes[:, None] * pb.plane + np.arange(pb.plane)[None, :]).reshape(-1)])
+    return gid
+
+
+@pytest.mark.parametrize("dim,cells,p,name,scaling,cfl,nranks", CASES)
+def test_harness_assembly_equals_oracle(dim, cells, p, name, scaling, cfl, nranks):
+    """The vectorised product-side assembly reproduces the oracle's path-tracing restatement of
+    fillSparseObject entry by entry, for every rank of a slab partition."""
+    st = Stencil(name, scaling)
+    pb = harness.CartesianProblem(dim, cells, p)
+    dt = pb.timestep(st, cfl)
+    e, w, cs2, vm = ost.make(name, scaling)
+    mesh = assembly.CartesianMesh.uniform(dim, cells)
+    assert dt == assembly.calculate_timestep(mesh, p, vm, cfl)
+    blocks, dofs = assembly.assemble_semilagrangian(mesh, p, e, dt)
+    assert all(k[0] == k[1] for k in blocks)                 # periodic: diagonal blocks only
+    seen = np.zeros(pb.N, dtype=int)
+    for r in range(nranks):
+        part = harness.SlabPartition(pb, st, dt, r, nranks)
+        own, gid = part.owned_global_ids(), local_to_global(pb, part)
+        seen[own] += 1
+        for a in range(1, st.getQ()):
+            rp, col, val = harness.assemble_direction(pb, part, st, dt, a)
+            coo = sp.csr_matrix((val, col, rp), shape=(part.n_owned, part.n_owned + part.n_ghost)).tocoo()
+            mg = sp.coo_matrix((coo.data, (coo.row, gid[coo.col])), shape=(part.n_owned, pb.N)).tocsr()
+            ref = blocks[(a - 1, a - 1)][own]
+            assert mg.nnz == ref.nnz
+            d = mg - ref
+            assert d.nnz == 0 or np.max(np.abs(d.data)) <= 1e-15
+    assert np.all(seen == 1)                                  # every DoF owned exactly once
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_halo_plan_single_process(nranks):
+    """Simulate the exchange of nb200_set_halo's plan in numpy: after it, rank-local SpMVs equal the global one."""
+    st = Stencil("D3Q19", 1.0)
+    pb = harness.CartesianProblem(3, [2, 2, 4], 2)
+    dt = pb.timestep(st, 0.4)
+    parts = [harness.SlabPartition(pb, st, dt, r, nranks) for r in range(nranks)]
+    plans = [p.halo_plan() for p in parts]
+    rng = np.random.default_rng(0)
+    xg = rng.standard_normal(pb.N)
+    local = [np.concatenate([xg[p.owned_global_ids()], np.full(p.n_ghost, np.nan)]) for p in parts]
+    for r, (nbr, so, si, ro) in enumerate(plans):
+        assert ro[-1] == parts[r].n_ghost
+        for k, dst in enumerate(nbr):
+            nb2, so2, si2, ro2 = plans[dst]
+            k2 = list(nb2).index(r)                           # the matching segment on the receiver
+            payload = local[r][si[so[k]:so[k + 1]]]
+            assert len(payload) == ro2[k2 + 1] - ro2[k2]
+            local[dst][parts[dst].n_owned + ro2[k2]: parts[dst].n_owned + ro2[k2 + 1]] = payload
+    single = harness.SlabPartition(pb, st, dt, 0, 1)
+    for a in (1, 2, 7, 16):
+        rp, col, val = harness.assemble_direction(pb, single, st, dt, a)
+        yg = sp.csr_matrix((val, col, rp), shape=(pb.N, pb.N)) @ xg
+        for r, p in enumerate(parts):
+            assert not np.isnan(local[r]).any()
+            rp, col, val = harness.assemble_direction(pb, p, st, dt, a)
+            y = sp.csr_matrix((val, col, rp), shape=(p.n_owned, p.n_owned + p.n_ghost)) @ local[r]
+            assert np.max(np.abs(y - yg[p.owned_global_ids()])) <= 1e-14
+
+
+def test_equilibrium_init_against_oracle():
+    from oracle import fields
+    st = Stencil("D3Q19", 3.0)
+    e, w, cs2, _ = ost.make("D3Q19", 3.0)
+    rng = np.random.default_rng(1)
+    rho, u = 1 + 0.1 * rng.standard_normal(20), 0.2 * rng.standard_normal((3, 20))
+    assert np.max(np.abs(harness.equilibrium_distributions(st, rho, u) - fields.equilibrium_init(e, w, cs2, rho, u))) <= 1e-15
+    for name in ("D2Q25H", "D3Q45"):
+        st = Stencil(name, 1.3)
+        e, w, cs2, _ = ost.make(name, 1.3)
+        D = e.shape[1]
+        rho, u, T = 1 + 0.1 * rng.standard_normal(7), 0.2 * rng.standard_normal((D, 7)), 1 + 0.1 * rng.standard_normal(7)
+        f1, g1 = harness.quartic_equilibrium_distributions(st, rho, u, T, 1.4)
+        f2, g2 = fields.quartic_equilibrium_init(e, w, cs2, 1.3, rho, u, T, 1.4)
+        assert np.max(np.abs(f1 - f2) / np.abs(f2)) <= 1e-11 and np.max(np.abs(g1 - g2) / np.abs(g2)) <= 1e-11

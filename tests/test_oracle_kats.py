@@ -1,0 +1,143 @@
+"""Pins the CPU oracle against the reference's own known-answer / self-consistency tests
+(SURVEY.md section 4).  The reference ships no golden arrays, so these are the properties and
+cross-path identities its Boost.Test suite asserts, restated with the same inputs and tolerances.
+CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import assembly, cpu, fields
+from tests import common
+
+
+def synthetic_populations(Q, n):
+    """BGKStandard_test.cpp:373-380: f_i(j) = 1.5 + sin(1.5 i) + 0.001 + i/(i+1) + (0.5 cos j)^2 with integer i/(i+1) = 0."""
+    i = np.arange(Q, dtype=np.float64)[:, None]
+    j = np.arange(n, dtype=np.float64)[None, :]
+    return 1.5 + np.sin(1.5 * i) + 0.001 + (0.5 * np.cos(j)) ** 2 + 0 * i
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D3Q19", "D3Q15"])
+def test_collide_all_equals_collide_single_point(name, oracle_lib):
+    """BGKStandard_collideAllD2Q9/D3Q19/D3Q15_test (BGKStandard_test.cpp:358-590): the vectorised
+    collideAll equals the scalar legacy collideSinglePoint to 1e-10 % (= 1e-12 relative); tau = 0.9, dt = 0.1.
+    Here: collision_advanced BGK (unscaled e, 1/tau with tau = tau_legacy + 0.5) == legacy BGKStandard
+    (scaled e, prefactor -1/(tau_legacy + 0.5)), the oracle-internal cross-check of SURVEY 8(c)."""
+    st = oracle_lib.Stencil(name, 5.0)
+    n, dt, tau_legacy = 10, 0.1, 0.9
+    nu = tau_legacy * dt * st.cs2
+    f = synthetic_populations(st.Q, n)
+    got = f.copy()
+    _, _, rc = oracle_lib.collide_bgk(st, got, nu, dt)
+    assert rc == 0
+    for j in range(n):
+        ref = oracle_lib.legacy_collide_single_point(st, f[:, j], tau_legacy)
+        assert np.max(np.abs(got[:, j] - ref) / np.abs(ref)) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["D2Q9", "D3Q19", "D3Q15", "D2Q25H", "D3Q45"])
+def test_collision_invariants(name, oracle_lib):
+    """BGKStandardCollisionInvariants_test (:311-356): rho and rho*u conserved to 1e-15 (relative);
+    f_eq is a fixed point of the collision."""
+    st = oracle_lib.Stencil(name, 1.0)
+    f = synthetic_populations(st.Q, 50) * st.w[:, None]
+    before = f.copy()
+    oracle_lib.collide_bgk(st, f, 0.03, 0.1, equilibrium=1 if name == "D2Q25H" else 0)
+    assert np.max(np.abs(f.sum(0) - before.sum(0)) / before.sum(0)) <= 5e-15
+    assert np.max(np.abs(st.e.T @ f - st.e.T @ before)) <= 5e-15 * np.max(np.abs(before.sum(0))) * np.abs(st.e).max()
+    # fixed point
+    feq = np.stack([oracle_lib.equilibrium(st, 1.1, [0.05, -0.02, 0.01][:st.D], kind=0)]).T.copy()
+    fixed = feq.copy()
+    oracle_lib.collide_bgk(st, fixed, 0.03, 0.1, equilibrium=0)
+    if name != "D2Q25H" and name != "D3Q45":      # 2nd-order f_eq on lattices whose 2nd moments are exact
+        assert np.max(np.abs(fixed - feq)) <= 1e-15
+
+
+def test_equilibrium_moments_d2q9(oracle_lib):
+    """Equilibrium_test (Equilibrium_test.cpp:43-109): rho, u recovered from BGK f_eq; u=(0.1,0.2)."""
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    feq = oracle_lib.equilibrium(st, 1.0, [0.1, 0.2], kind=0)
+    assert abs(feq.sum() - 1.0) <= 1e-7
+    assert np.max(np.abs(st.e.T @ feq - [0.1, 0.2])) <= 1e-7
+
+
+def test_equilibrium_moments_d3q45_quartic(oracle_lib):
+    """Equilibrium_D3Q45_test (:161-213): quartic f_eq with T = 1.2, u = (0.1,0.2,0.3) recovers rho, u to 1e-5 %,
+    and the temperature through calculateTemperature with g = f_eq T (2 Cv - D)."""
+    st = oracle_lib.Stencil("D3Q45", 1.0)
+    u, T, rho, gamma = np.array([0.1, 0.2, 0.3]), 1.2, 1.0, 1.4
+    feq = oracle_lib.equilibrium(st, rho, u, T=T, kind=1)
+    assert abs(feq.sum() - rho) <= 1e-7
+    assert np.max(np.abs(st.e.T @ feq / feq.sum() - u)) <= 1e-7
+    f = feq[:, None].copy()
+    g = (feq * T * (2.0 / (gamma - 1.0) - 3))[:, None].copy()
+    r, v, Tout, _, rc = oracle_lib.collide_bgk_fg(st, f, g, 0.01, 0.1, equilibrium=1, gamma=gamma)
+    assert rc == 0 and abs(Tout[0] - T) <= 1e-7 and abs(r[0] - rho) <= 1e-7
+    assert np.max(np.abs(f[:, 0] - feq)) <= 1e-12        # equilibrium is a fixed point of relaxWithG
+
+
+def test_quartic_init_matches_collision_equilibrium(oracle_lib):
+    """CompressibleCFDSolver::calcQuarticEquilibrium (init, literal loop nest) == QuarticEquilibrium::polynomial."""
+    for name, D in (("D2Q25H", 2), ("D3Q45", 3)):
+        st = oracle_lib.Stencil(name, 1.3)
+        rho, T = np.array([1.07]), np.array([1.15])
+        u = np.array([[0.11], [-0.07], [0.05]])[:D] * 1.3
+        f, g = fields.quartic_equilibrium_init(st.e, st.w, st.cs2, st.scaling, rho, u, T, 1.4)
+        feq = oracle_lib.equilibrium(st, 1.07, u[:, 0] / 1.3, T=1.15, kind=1)
+        assert np.max(np.abs(f[:, 0] - feq) / np.abs(feq)) <= 1e-12
+
+
+def test_constant_streaming_and_row_structure():
+    """SemiLagrangian2D/3D_ConstantStreaming_test (SemiLagrangian_test.cpp:519-596): M*1 = 1;
+    2D p=3 ref 3 D2Q9 dt=0.1 / 3D p=1 ref 3 D3Q19 dt=0.1 on the unit-square/cube periodic test domain;
+    plus the nnz-per-row structure of SURVEY 8 ((p+1)^k)."""
+    from oracle import stencils
+    for dim, p, name in ((2, 3, "D2Q9"), (3, 1, "D3Q19")):
+        e, w, cs2, vm = stencils.make(name, 1.0)
+        mesh = assembly.CartesianMesh.uniform(dim, 8 if dim == 2 else 4, L=1.0)
+        blocks, dofs = assembly.assemble_semilagrangian(mesh, p, e, 0.1 if dim == 2 else 0.05)
+        ones = np.ones(dofs.N)
+        for k, m in blocks.items():
+            assert k[0] == k[1]
+            assert np.sum((cpu.spmv_csr(m, ones) - ones) ** 2) <= 1e-6
+    o = common.oracle_problem("c1_tgv2d_d2q9")
+    assert o["dofs"].N == 1089
+    nnz = sum(b.nnz for b in o["blocks"].values())
+    assert nnz == 120 * 1089                     # 4*5 + 4*25 per DoF
+    for (bi, _), m in o["blocks"].items():
+        k = np.count_nonzero(o["st"].e[bi + 1])
+        assert np.all(np.diff(m.indptr) == 5 ** k)
+
+
+def test_uniform_flow_stays_uniform(oracle_lib):
+    """CFDSolver_SteadyStreaming_test (CFDSolver_test.cpp:44-112): |rho-1|, |u-0.1| < 1e-5 after 100 steps."""
+    o = common.oracle_problem("tgv2d_small")
+    st, n = o["st"], o["dofs"].N
+    f = fields.equilibrium_init(st.e, st.w, st.cs2, np.ones(n), np.full((2, n), 0.1))
+    stepper = oracle_lib.ReferenceOrderStepper(st, o["blocks"], n, 1.0, o["dt"])
+    for _ in range(100):
+        assert stepper.step(f) == 0
+    assert np.max(np.abs(stepper.rho - 1)) < 1e-5 and np.max(np.abs(stepper.u - 0.1)) < 1e-5
+
+
+def test_config1_energy_decay(oracle_lib):
+    """Integration test #11 ConvergenceTestSemiLagrangianPeriodic (IntegrationTestCases.cpp:885-961) =
+    BASELINE config 1: E_kin(t)/E_kin(0) = exp(-4 nu t) within 1e-2 at t = 0.5."""
+    o = common.oracle_problem("c1_tgv2d_d2q9")
+    st, n, dt, nu = o["st"], o["dofs"].N, o["dt"], 1.0
+    f = o["f"].copy()
+    stepper = oracle_lib.ReferenceOrderStepper(st, o["blocks"], n, nu, dt)
+    r0, u0, _ = oracle_lib.collide_bgk(st, f, nu, dt)
+    E0 = 0.5 * (r0 * (u0 ** 2).sum(0)).sum()
+    steps = int(round(0.5 / dt))
+    for _ in range(steps):
+        stepper.step(f)
+    E = 0.5 * (stepper.rho * (stepper.u ** 2).sum(0)).sum()
+    assert abs(E / E0 - math.exp(-4 * nu * steps * dt)) < 1e-2
+
+
+def test_density_exception_code(oracle_lib):
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    f = np.zeros((9, 4))
+    assert oracle_lib.collide_bgk(st, f, 0.1, 0.1)[2] == -1      # CollisionException: rho < 1e-10
