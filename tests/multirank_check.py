@@ -1,0 +1,103 @@
+"""Multi-GPU parity worker (run under torchrun, one rank per GPU): slab-partitioned problem, NCCL ghost
+exchange inside nb200_step, result gathered on rank 0 and compared with the single-domain CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from natrium_b200 import Context, harness, _capi  # noqa: E402
+from natrium_b200.stencils import Stencil          # noqa: E402
+
+
+def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, with_g, steps=6):
+    st = Stencil(name, scaling)
+    pb = harness.CartesianProblem(dim, cells, p)
+    dt = pb.timestep(st, cfl)
+    part = harness.SlabPartition(pb, st, dt, rank, world)
+    ctx = Context(local, rank, world, uid)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+    ctx.set_layout(part.n_owned, part.n_ghost, with_g)
+    harness.upload_streaming_matrix(ctx, pb, part, st, dt)
+    ctx.set_halo(*part.halo_plan())
+    if with_g:
+        ctx.set_collision(nu, dt, equilibrium=_capi.QUARTIC_EQUILIBRIUM, with_g=True, gamma=1.4, prandtl=0.71, sutherland=True)
+    else:
+        ctx.set_collision(nu, dt)
+    x = part.owned_points()
+    if dim == 2:
+        rho, u = harness.taylor_green_2d(x)
+        rho = 1.0 + 0.05 * np.cos(x[:, 0]) * np.sin(x[:, 1])
+        u = 0.1 * u
+    else:
+        rho, u = harness.taylor_green_3d(x, st.getSpeedOfSound())
+    T = 1.0 + 0.02 * np.sin(x[:, 0]) * np.cos(x[:, -1])
+    if with_g:
+        f, g = harness.quartic_equilibrium_distributions(st, rho, u, T, 1.4)
+        ctx.upload_populations(1, g)
+    else:
+        f = harness.equilibrium_distributions(st, rho, u)
+    ctx.upload_populations(0, f)
+    ctx.step(steps)
+    ctx.synchronize()
+    cons = ctx.conserved()
+    got = [ctx.download_populations(0)] + ([ctx.download_populations(1)] if with_g else [])
+    ids = part.owned_global_ids()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ids, got, f, g if with_g else None))
+    ctx.close()
+    if rank != 0:
+        return True
+    # single-domain oracle on the assembled global state
+    from oracle import cpu
+    import scipy.sparse as sp
+    N = pb.N
+    F0, G0 = np.empty((st.getQ(), N)), np.empty((st.getQ(), N))
+    RES = [np.empty((st.getQ(), N)) for _ in got]
+    for ids_r, got_r, f_r, g_r in gathered:
+        F0[:, ids_r] = f_r
+        if with_g:
+            G0[:, ids_r] = g_r
+        for k, a in enumerate(got_r):
+            RES[k][:, ids_r] = a
+    single = harness.SlabPartition(pb, st, dt, 0, 1)
+    blocks = {}
+    for a in range(1, st.getQ()):
+        rp, col, val = harness.assemble_direction(pb, single, st, dt, a)
+        blocks[(a - 1, a - 1)] = sp.csr_matrix((val, col, rp), shape=(N, N))
+    ost = cpu.Stencil(name, scaling)
+    stepper = cpu.ReferenceOrderStepper(ost, blocks, N, nu, dt, equilibrium=1 if with_g else 0, with_g=with_g,
+                                        gamma=1.4, prandtl=0.71 if with_g else None, sutherland=with_g)
+    for _ in range(steps):
+        assert stepper.step(F0, G0 if with_g else None) == 0
+    err = float(np.max(np.abs(RES[0] - F0) / np.abs(F0)))
+    if with_g:
+        err = max(err, float(np.max(np.abs(RES[1] - G0) / np.abs(G0))))
+    mass = F0.sum()
+    ok = err <= 1e-11 and abs(cons[0] - mass) <= 1e-12 * mass
+    print(f"multirank {name} world={world}: max rel err after {steps} steps = {err:.3e}, mass {cons[0]:.15g} vs {mass:.15g} -> {'OK' if ok else 'FAIL'}", flush=True)
+    return ok
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    box = [Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ok = run_case(rank, world, local, box[0], "D3Q19", 3, [3, 3, 2 * world], 2, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False)
+    box = [Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ok = run_case(rank, world, local, box[0], "D2Q25H", 2, [5, 3 * world], 2, 1.0, 0.01, 1.0, True) and ok
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+if __name__ == "__main__":
+    main()
