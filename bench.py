@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-layers", type=int, default=8, help="z cell layers of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--format", default="dict", choices=["dict", "ell"], help="device format of the streaming matrix")
+    ap.add_argument("--dof-order", default="cell", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     return ap.parse_args()
 
 
@@ -219,6 +222,10 @@ def run_ours(args):
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     part = harness.SlabPartition(pb, st, dt, rank, world)
     ctx.set_layout(part.n_owned, part.n_ghost, False)
+    from natrium_b200 import _capi
+    ctx.set_matrix_format(_capi.FORMAT_DICT if args.format == "dict" else _capi.FORMAT_ELL, args.dedup_tol if args.format == "dict" else 0.0)
+    if args.dof_order == "cell":
+        ctx.set_dof_order(part.cell_blocked_order())
     t0 = time.perf_counter()
     nnz = harness.upload_streaming_matrix(ctx, pb, part, st, dt)
     t_asm = time.perf_counter() - t0
@@ -296,11 +303,11 @@ def run_ours(args):
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     info = ctx.matrix_info()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(f"{args.stencil}_p{args.order}_{args.cells}"),
+                "traffic": ncu_traffic(f"{args.stencil}_p{args.order}_{args.cells}_{args.format}"),
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": bpd, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel": "k_stream_collide_f<3,19,BGK>" if args.stencil == "D3Q19" else "k_stream_collide_f",
+                "kernel": f"k_stream_collide_f<{D},{Q},BGK,{args.format}>",
                 "kernel_ms": kern_ms, "frac_of_nominal_8000": achieved / 8000.0,
-                "device_format_bytes": info["device_bytes"], "nnz": nnz}
+                "device_format_bytes": info["device_bytes"], "nnz": nnz, "matrix_format": ctx.matrix_format_info(), "dof_order": args.dof_order}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -89,6 +89,15 @@ int nb200_set_stencil(nb200_ctx *ctx, int D, int Q, const double *e_scaled, cons
  * with_g allocates the second distribution (CompressibleCFDSolver::m_g). */
 int nb200_set_layout(nb200_ctx *ctx, int64_t n_owned, int64_t n_ghost, int with_g);
 
+/* Optional locality hint, right after nb200_set_layout: the library stores owned DoF order[k] at internal
+ * position k (populations, moments and matrix rows; ghosts stay behind the owned range).  Every other call keeps
+ * speaking the caller's numbering -- uploads, downloads, CSR blocks and the halo plan are translated inside.
+ * The natural order is the one SemiLagrangian::fillSparseObject itself walks: for each locally owned cell in
+ * active-cell (p4est Morton) order, cell->get_dof_indices(), first visit wins
+ * (L/advection/SemiLagrangian.cpp:201-223).  DoFs of one cell then sit next to each other, a warp reads one
+ * source cell, and the gathered support values stay in L1. */
+int nb200_set_dof_order(nb200_ctx *ctx, int64_t n_owned, const int32_t *order);
+
 /* One block (bi,bj) of getSystemMatrix() (distributed_sparse_block_matrix, (Q-1)x(Q-1) blocks,
  * SemiLagrangian.cpp:101,116-134) as local CSR: exactly what
  * block(bi,bj).trilinos_matrix().ExtractMyRowView gives row by row (idiom in
@@ -98,6 +107,21 @@ int nb200_upload_block_csr(nb200_ctx *ctx, int bi, int bj, int64_t n_rows, const
 
 /* Builds the device streaming format from the uploaded blocks (after reassemble()). */
 int nb200_finalize_matrix(nb200_ctx *ctx);
+
+/* Device representation of getSystemMatrix().  Call before the first nb200_upload_block_csr.
+ *   NB200_FORMAT_ELL   warp-sliced ELL, 12 B per stored entry, values bit-identical to the upload.
+ *   NB200_FORMAT_DICT  (default) dictionary format: each row = (column-list id, weight-pattern id); rows that
+ *                      read the same source cell share a list, rows whose values agree entry by entry to within
+ *                      value_dedup_tol share a pattern.  value_dedup_tol = 0 keeps every value bit-identical;
+ *                      the default 1e-14 is four orders below the 1e-10 below which the reference's own
+ *                      assembly drops entries (L/advection/SemiLagrangian.cpp:483) and bounds the per-row
+ *                      perturbation by K*1e-14*max|f| (K = row length <= (p+1)^dim).
+ * The matrix the reference assembles on a regular mesh has only O((p+1)^dim) distinct rows per direction up
+ * to round-off, which is what the dictionary exploits; on an unstructured mesh it degenerates to ELL. */
+enum nb200_matrix_format { NB200_FORMAT_ELL = 0, NB200_FORMAT_DICT = 1 };
+int nb200_set_matrix_format(nb200_ctx *ctx, int format, double value_dedup_tol);
+/* out = { format, #weight patterns, #column lists, pool bytes, row-descriptor bytes, #row-length classes } */
+int nb200_matrix_format_info(const nb200_ctx *ctx, int64_t out[6], double *value_dedup_tol);
 
 /* Ghost plan derived from the column map / IndexSets: for neighbour k, owned local indices
  * send_idx[send_off[k]..send_off[k+1]) go to rank nbr_rank[k]; ghost slots

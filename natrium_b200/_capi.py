@@ -22,6 +22,7 @@ NB200_ERR_NO_DEVICE = -6
 
 BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = 0, 1, 2
 BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = 0, 1
+FORMAT_ELL, FORMAT_DICT = 0, 1
 
 
 class CollisionParams(C.Structure):
@@ -51,8 +52,11 @@ SIGNATURES = {
     "nb200_last_error": (C.c_char_p, [_vp]),
     "nb200_set_stencil": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double]),
     "nb200_set_layout": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int]),
+    "nb200_set_dof_order": (C.c_int, [_vp, C.c_int64, _i32p]),
     "nb200_upload_block_csr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _i64p, _i32p, _dp]),
     "nb200_finalize_matrix": (C.c_int, [_vp]),
+    "nb200_set_matrix_format": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "nb200_matrix_format_info": (C.c_int, [_vp, _i64p, _dp]),
     "nb200_set_halo": (C.c_int, [_vp, C.c_int, _i32p, _i64p, _i32p, _i64p]),
     "nb200_upload_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
     "nb200_download_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
@@ -159,6 +163,10 @@ class Context:
         self._check(self.lib.nb200_set_layout(self._h, n_owned, n_ghost, 1 if with_g else 0))
         self.n_owned, self.n_ghost, self.with_g = int(n_owned), int(n_ghost), bool(with_g)
 
+    def set_dof_order(self, order):
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        self._check(self.lib.nb200_set_dof_order(self._h, len(order), order.ctypes.data_as(_i32p)))
+
     def upload_block_csr(self, bi, bj, rowptr, col, val):
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
         col = np.ascontiguousarray(col, dtype=np.int32)
@@ -168,6 +176,16 @@ class Context:
 
     def finalize_matrix(self):
         self._check(self.lib.nb200_finalize_matrix(self._h))
+
+    def set_matrix_format(self, fmt=FORMAT_DICT, value_dedup_tol=1e-14):
+        self._check(self.lib.nb200_set_matrix_format(self._h, fmt, value_dedup_tol))
+
+    def matrix_format_info(self):
+        out = (C.c_int64 * 6)()
+        tol = C.c_double()
+        self._check(self.lib.nb200_matrix_format_info(self._h, out, C.byref(tol)))
+        return dict(format="dict" if out[0] == FORMAT_DICT else "ell", patterns=out[1], lists=out[2], pool_bytes=out[3],
+                    descriptor_bytes=out[4], classes=out[5], value_dedup_tol=tol.value)
 
     def set_halo(self, nbr_rank, send_off, send_idx, recv_off):
         nbr = np.ascontiguousarray(nbr_rank, dtype=np.int32)

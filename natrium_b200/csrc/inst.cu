@@ -41,15 +41,29 @@ int fused(const NbLaunch& L)
     const unsigned grid = grid_for(L.A.n_slices * 32, 128);
     if (!L.with_g) {
 #if NB_FUSE_F
-        if (L.eq == NB_EQ_BGK) k_stream_collide_f<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag);
-        else k_stream_collide_f<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag);
+#define NB_LAUNCH_F(EQ, FMT) k_stream_collide_f<D, Q, EQ, FMT><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag)
+        if (L.fmt == NB_FMT_DICT) { if (L.eq == NB_EQ_BGK) NB_LAUNCH_F(NB_EQ_BGK, NB_FMT_DICT); else NB_LAUNCH_F(NB_EQ_QUARTIC, NB_FMT_DICT); }
+        else { if (L.eq == NB_EQ_BGK) NB_LAUNCH_F(NB_EQ_BGK, NB_FMT_ELL); else NB_LAUNCH_F(NB_EQ_QUARTIC, NB_FMT_ELL); }
+#undef NB_LAUNCH_F
 #else
         return -1;
 #endif
     } else {
 #if NB_WITH_G && NB_FUSE_G
-        if (L.eq == NB_EQ_BGK) k_stream_collide_fg<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag);
-        else k_stream_collide_fg<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag);
+        const size_t smem_fg = (size_t)2 * Q * 128 * sizeof(double);
+#define NB_LAUNCH_FG(EQ, FMT)                                                                                              \
+    do {                                                                                                                   \
+        static bool attr_set = false;                                                                                      \
+        if (!attr_set) {                                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_fg<D, Q, EQ, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fg); \
+            if (e != cudaSuccess) return (int)e;                                                                           \
+            attr_set = true;                                                                                               \
+        }                                                                                                                  \
+        k_stream_collide_fg<D, Q, EQ, FMT><<<grid, 128, smem_fg, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
+    } while (0)
+        if (L.fmt == NB_FMT_DICT) { if (L.eq == NB_EQ_BGK) NB_LAUNCH_FG(NB_EQ_BGK, NB_FMT_DICT); else NB_LAUNCH_FG(NB_EQ_QUARTIC, NB_FMT_DICT); }
+        else { if (L.eq == NB_EQ_BGK) NB_LAUNCH_FG(NB_EQ_BGK, NB_FMT_ELL); else NB_LAUNCH_FG(NB_EQ_QUARTIC, NB_FMT_ELL); }
+#undef NB_LAUNCH_FG
 #else
         return -1;
 #endif

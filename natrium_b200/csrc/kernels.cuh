@@ -9,24 +9,40 @@
 // kernels: hot path
 // ---------------------------------------------------------------------------------------------
 // Fused stream + collide, f only.  x: current populations (owned + ghosts), y: next.
-template <int D, int Q, int EQ>
-__global__ void __launch_bounds__(128)
+// Two phases per thread (= one DoF): (1) a compact, not unrolled loop over the Q-1 rows of the DoF that
+// parks each streamed value in this thread's column of a shared-memory tile -- few live registers, so many
+// warps are resident while the gathers are in flight; (2) the collision on the Q values read back from the
+// tile.  No barrier: a thread only ever touches its own column.
+#ifndef NB_FUSED_OCC_F
+#define NB_FUSED_OCC_F 5
+#endif
+#ifndef NB_FUSED_OCC_FG
+#define NB_FUSED_OCC_FG 2
+#endif
+template <int D, int Q, int EQ, int FMT>
+__global__ void __launch_bounds__(128, NB_FUSED_OCC_F)
 k_stream_collide_f(StreamArgs A, const double* __restrict__ x, double* __restrict__ y,
                    double* __restrict__ rho_out, double* __restrict__ u_out, int* __restrict__ flag)
 {
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    __shared__ double tile[Q][128];
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + tid;
     const int64_t slice = row >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = tid & 31;
     if (slice >= A.n_slices) return;
     const bool active = row < A.n_owned;
-    double f[Q];
-    f[0] = active ? x[row] : 0.0;
-#pragma unroll
+    if (FMT == NB_FMT_DICT && !active) return;
+    tile[0][tid] = active ? x[row] : 0.0;
+#pragma unroll 1
     for (int a = 1; a < Q; a++) {
-        double dummy;
-        nb_row_dot<1>(A, a - 1, slice, lane, x, nullptr, f[a], dummy);
+        double r, dummy;
+        nb_row_dot<FMT, 1>(A, a - 1, row, slice, lane, x, nullptr, r, dummy);
+        tile[a][tid] = r;
     }
     if (!active) return;
+    double f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
     double rho, u[3];
     nb_collide_bgk<D, Q, EQ>(f, rho, u, nullptr);
     if (rho < 1e-10) *flag = 1;
@@ -38,24 +54,39 @@ k_stream_collide_f(StreamArgs A, const double* __restrict__ x, double* __restric
 }
 
 // Fused stream + collide for f and g (one pass over the matrix for both distributions).
-template <int D, int Q, int EQ>
-__global__ void __launch_bounds__(128)
+template <int D, int Q, int EQ, int FMT>
+__global__ void __launch_bounds__(128, NB_FUSED_OCC_FG)
 k_stream_collide_fg(StreamArgs A, const double* __restrict__ xf, const double* __restrict__ xg,
                     double* __restrict__ yf, double* __restrict__ yg, double* __restrict__ rho_out,
                     double* __restrict__ u_out, double* __restrict__ T_out, double* __restrict__ s_out,
                     int* __restrict__ flag)
 {
-    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    extern __shared__ double tile_fg[];        // [2][Q][128]
+    double (*tf)[128] = reinterpret_cast<double (*)[128]>(tile_fg);
+    double (*tg)[128] = reinterpret_cast<double (*)[128]>(tile_fg + Q * 128);
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + tid;
     const int64_t slice = row >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = tid & 31;
     if (slice >= A.n_slices) return;
     const bool active = row < A.n_owned;
-    double f[Q], g[Q];
-    f[0] = active ? xf[row] : 0.0;
-    g[0] = active ? xg[row] : 0.0;
-#pragma unroll
-    for (int a = 1; a < Q; a++) nb_row_dot<2>(A, a - 1, slice, lane, xf, xg, f[a], g[a]);
+    if (FMT == NB_FMT_DICT && !active) return;
+    tf[0][tid] = active ? xf[row] : 0.0;
+    tg[0][tid] = active ? xg[row] : 0.0;
+#pragma unroll 1
+    for (int a = 1; a < Q; a++) {
+        double r0, r1;
+        nb_row_dot<FMT, 2>(A, a - 1, row, slice, lane, xf, xg, r0, r1);
+        tf[a][tid] = r0;
+        tg[a][tid] = r1;
+    }
     if (!active) return;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        f[q] = tf[q][tid];
+        g[q] = tg[q][tid];
+    }
     double rho, u[3], T, sensor;
     nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, nullptr);
     if (rho < 1e-10) *flag = 1;

@@ -15,6 +15,7 @@ struct NbLaunch {
     double* rho; double* u; double* T; double* sensor;
     int* flag;
     int eq;        // NB_EQ_BGK / NB_EQ_QUARTIC
+    int fmt;       // NB_FMT_ELL / NB_FMT_DICT
     int with_g;
     int in_init;
     // constant-block ownership: the unit re-uploads when (owner, version) changed

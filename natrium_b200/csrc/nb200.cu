@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -25,6 +26,7 @@
 #include "../../include/natrium_b200.h"
 #include "nbconst.h"
 #include "launch.h"
+#include "dict_build.h"
 
 // ---------------------------------------------------------------------------------------------
 // NCCL, bound at run time (dlopen) so that a single-GPU user needs no NCCL at all and a
@@ -104,6 +106,20 @@ struct nb200_ctx {
     int64_t* d_slice_off = nullptr;   // [(Q-1)][n_slices+1]
     double* ell_val = nullptr;
     int32_t* ell_idx = nullptr;
+    // internal DoF order (nb200_set_dof_order): position k holds user DoF order[k]; perm = inverse
+    bool has_order = false;
+    std::vector<int32_t> order, perm;
+    int32_t *d_order = nullptr, *d_perm = nullptr;
+    double* d_stage = nullptr;               // [Q][n_owned] staging for permuted host transfers
+    // dictionary format (NB_FMT_DICT)
+    int fmt = NB_FMT_DICT;
+    double dedup_tol = 1e-14;
+    std::vector<nbdict::DirBuild> dirs;      // host staging between upload_block_csr and finalize_matrix
+    int2* d_desc = nullptr;
+    NbDirClass* d_cls = nullptr;
+    int64_t desc_stride = 0;
+    std::vector<void*> pools;                // device pools owned by the format
+    int64_t dict_patterns = 0, dict_lists = 0, dict_pool_bytes = 0, dict_classes = 0;
     // collision
     const NbStencilOps* ops = nullptr;
     uint64_t const_version = 1;
@@ -211,8 +227,19 @@ __global__ void k_ell_pad(int64_t n_rows, int64_t n_slices, const int64_t* __res
     }
 }
 
+// dictionary pools: host layout [entry][K] -> device layout [K][stride] (k-major)
+template <typename T>
+__global__ void k_pool_transpose(int64_t n, int K, int64_t stride, const T* __restrict__ in, T* __restrict__ out)
+{
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n * K) return;
+    const int64_t p = t / K;
+    const int k = (int)(t - p * K);
+    out[(int64_t)k * stride + p] = in[t];
+}
+
 // Stream only: y_alpha = sum_beta M_{alpha beta} x_beta, y_0 = x_0.  grid.y = Q (direction).
-template <int NRHS>
+template <int FMT, int NRHS>
 __global__ void __launch_bounds__(128)
 k_stream(StreamArgs A, const double* __restrict__ x0, const double* __restrict__ x1,
          double* __restrict__ y0, double* __restrict__ y1)
@@ -223,6 +250,7 @@ k_stream(StreamArgs A, const double* __restrict__ x0, const double* __restrict__
     const int q = blockIdx.y;
     if (slice >= A.n_slices) return;
     const bool active = row < A.n_owned;
+    if (FMT == NB_FMT_DICT && !active) return;
     double r0 = 0.0, r1 = 0.0;
     if (q == 0) {
         if (active) {
@@ -230,11 +258,22 @@ k_stream(StreamArgs A, const double* __restrict__ x0, const double* __restrict__
             if (NRHS == 2) r1 = x1[row];
         }
     } else {
-        nb_row_dot<NRHS>(A, q - 1, slice, lane, x0, x1, r0, r1);
+        nb_row_dot<FMT, NRHS>(A, q - 1, row, slice, lane, x0, x1, r0, r1);
     }
     if (!active) return;
     y0[(int64_t)q * A.stride + row] = r0;
     if (NRHS == 2) y1[(int64_t)q * A.stride + row] = r1;
+}
+
+// internal <-> user DoF order.  rows: number of arrays (populations / velocity components).
+// to_internal: dst[r*dst_stride + k] = src[r*src_stride + order[k]];  to_user: dst[r*dst_stride + i] = src[r*src_stride + perm[i]]
+__global__ void k_permute_rows(int64_t n, int rows, const int32_t* __restrict__ map, const double* __restrict__ src,
+                               int64_t src_stride, double* __restrict__ dst, int64_t dst_stride)
+{
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (k >= n || r >= rows) return;
+    dst[(int64_t)r * dst_stride + k] = src[(int64_t)r * src_stride + map[k]];
 }
 
 // halo pack / unpack: buffer layout [neighbour segment][population][entry]
@@ -316,12 +355,18 @@ static void free_blocks(nb200_ctx* c)
 {
     for (auto& b : c->blocks) { cudaFree(b.rowptr); cudaFree(b.col); cudaFree(b.val); }
     c->blocks.clear();
+    c->dirs.clear();
+    c->dirs.shrink_to_fit();
 }
 
 static void free_matrix(nb200_ctx* c)
 {
     cudaFree(c->d_slice_off); cudaFree(c->ell_val); cudaFree(c->ell_idx);
     c->d_slice_off = nullptr; c->ell_val = nullptr; c->ell_idx = nullptr;
+    cudaFree(c->d_desc); cudaFree(c->d_cls);
+    c->d_desc = nullptr; c->d_cls = nullptr;
+    for (void* p : c->pools) cudaFree(p);
+    c->pools.clear();
     c->matrix_ready = false;
 }
 
@@ -335,6 +380,7 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) cudaFree(c->pop[w][b]);
     cudaFree(c->rho); cudaFree(c->u); cudaFree(c->T); cudaFree(c->sensor);
     cudaFree(c->d_flag); cudaFree(c->d_partial);
+    cudaFree(c->d_order); cudaFree(c->d_perm); cudaFree(c->d_stage);
     cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
     cudaFree(c->d_seg_send); cudaFree(c->d_seg_recv); cudaFree(c->d_send_off); cudaFree(c->d_recv_off);
     if (c->comm) g_nccl.CommDestroy(c->comm);
@@ -442,6 +488,77 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
     c->cur[0] = c->cur[1] = 0;
     free_blocks(c);
     free_matrix(c);
+    cudaFree(c->d_order); cudaFree(c->d_perm); cudaFree(c->d_stage);
+    c->d_order = c->d_perm = nullptr; c->d_stage = nullptr;
+    c->has_order = false;
+    c->order.clear(); c->perm.clear();
+    return NB200_OK;
+}
+
+extern "C" int nb200_set_dof_order(nb200_ctx* c, int64_t n, const int32_t* order)
+{
+    if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "set_dof_order: call set_layout first");
+    if (n != c->n_owned || (n > 0 && !order)) return fail(c, NB200_ERR_ARG, "set_dof_order: n=%lld != n_owned=%lld", (long long)n, (long long)c->n_owned);
+    if (!c->blocks.empty() || c->matrix_ready || c->n_nbr) return fail(c, NB200_ERR_ARG, "set_dof_order: call right after set_layout (before matrix / halo uploads)");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    std::vector<int32_t> perm((size_t)n, -1);
+    for (int64_t k = 0; k < n; k++) {
+        if (order[k] < 0 || order[k] >= n || perm[(size_t)order[k]] >= 0) return fail(c, NB200_ERR_ARG, "set_dof_order: not a permutation of [0, n_owned)");
+        perm[(size_t)order[k]] = (int32_t)k;
+    }
+    c->order.assign(order, order + n);
+    c->perm.swap(perm);
+    cudaFree(c->d_order); cudaFree(c->d_perm);
+    c->d_order = c->d_perm = nullptr;
+    if (n > 0) {
+        CUDA_TRY(c, cudaMalloc(&c->d_order, (size_t)n * 4));
+        CUDA_TRY(c, cudaMalloc(&c->d_perm, (size_t)n * 4));
+        CUDA_TRY(c, cudaMemcpy(c->d_order, c->order.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->d_perm, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    }
+    c->has_order = n > 0;
+    return NB200_OK;
+}
+
+// staging buffer for permuted transfers: rows x n_owned doubles
+static int need_stage(nb200_ctx* c)
+{
+    if (c->d_stage) return NB200_OK;
+    const size_t rows = (size_t)std::max(c->Q, 3);
+    CUDA_TRY(c, cudaMalloc(&c->d_stage, rows * (size_t)std::max<int64_t>(1, c->n_owned) * sizeof(double)));
+    return NB200_OK;
+}
+
+// host (user order, contiguous rows of n) -> device array (internal order, row stride dst_stride)
+static int copy_rows_in(nb200_ctx* c, const double* host, int rows, double* dev, int64_t dev_stride)
+{
+    const int64_t n = c->n_owned;
+    if (n == 0 || rows == 0) return NB200_OK;
+    if (!c->has_order) {
+        CUDA_TRY(c, cudaMemcpy2DAsync(dev, (size_t)dev_stride * 8, host, (size_t)n * 8, (size_t)n * 8, rows, cudaMemcpyHostToDevice, c->stream));
+        return NB200_OK;
+    }
+    int rc = need_stage(c);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_stage, host, (size_t)rows * n * 8, cudaMemcpyHostToDevice, c->stream));
+    k_permute_rows<<<dim3(grid_for(n, 256), rows), 256, 0, c->stream>>>(n, rows, c->d_order, c->d_stage, n, dev, dev_stride);
+    c->launches++;
+    return NB200_OK;
+}
+
+static int copy_rows_out(nb200_ctx* c, double* host, int rows, const double* dev, int64_t dev_stride)
+{
+    const int64_t n = c->n_owned;
+    if (n == 0 || rows == 0) return NB200_OK;
+    if (!c->has_order) {
+        CUDA_TRY(c, cudaMemcpy2DAsync(host, (size_t)n * 8, dev, (size_t)dev_stride * 8, (size_t)n * 8, rows, cudaMemcpyDeviceToHost, c->stream));
+        return NB200_OK;
+    }
+    int rc = need_stage(c);
+    if (rc) return rc;
+    k_permute_rows<<<dim3(grid_for(n, 256), rows), 256, 0, c->stream>>>(n, rows, c->d_perm, dev, dev_stride, c->d_stage, n);
+    c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(host, c->d_stage, (size_t)rows * n * 8, cudaMemcpyDeviceToHost, c->stream));
     return NB200_OK;
 }
 
@@ -455,6 +572,56 @@ extern "C" int nb200_upload_block_csr(nb200_ctx* c, int bi, int bj, int64_t n_ro
     const int64_t nnz = rowptr[n_rows] - rowptr[0];
     if (rowptr[0] != 0 || nnz < 0 || (nnz > 0 && (!col || !val))) return fail(c, NB200_ERR_ARG, "upload_block_csr: malformed CSR");
     for (auto& b : c->blocks) if (b.bi == bi && b.bj == bj) return fail(c, NB200_ERR_ARG, "block (%d,%d) uploaded twice", bi, bj);
+    for (int64_t i = 0; i < n_rows; i++) if (rowptr[i + 1] < rowptr[i]) return fail(c, NB200_ERR_ARG, "upload_block_csr: rowptr not monotone");
+    for (int64_t k = 0; k < nnz; k++)
+        if (col[k] < 0 || col[k] >= c->n_owned + c->n_ghost) return fail(c, NB200_ERR_ARG, "upload_block_csr: column %d outside owned+ghost range", (int)col[k]);
+    // internal DoF order: row k of the device matrix is user row order[k]; owned columns map through perm
+    std::vector<int64_t> p_rowptr;
+    std::vector<int32_t> p_col;
+    std::vector<double> p_val;
+    if (c->has_order) {
+        p_rowptr.resize((size_t)n_rows + 1);
+        p_rowptr[0] = 0;
+        for (int64_t k = 0; k < n_rows; k++) {
+            const int64_t i = c->order[(size_t)k];
+            p_rowptr[(size_t)k + 1] = p_rowptr[(size_t)k] + (rowptr[i + 1] - rowptr[i]);
+        }
+        p_col.resize((size_t)std::max<int64_t>(1, nnz));
+        p_val.resize((size_t)std::max<int64_t>(1, nnz));
+        unsigned nt = std::thread::hardware_concurrency();
+        nt = nt == 0 ? 4 : (nt > 32 ? 32 : nt);
+        if (n_rows < 20000) nt = 1;
+        auto work = [&](int64_t lo, int64_t hi) {
+            for (int64_t k = lo; k < hi; k++) {
+                const int64_t i = c->order[(size_t)k];
+                int64_t o = p_rowptr[(size_t)k];
+                for (int64_t j = rowptr[i]; j < rowptr[i + 1]; j++, o++) {
+                    p_col[(size_t)o] = col[j] < c->n_owned ? c->perm[(size_t)col[j]] : col[j];
+                    p_val[(size_t)o] = val[j];
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work, n_rows * t / nt, n_rows * (t + 1) / nt);
+        work(0, n_rows / nt);
+        for (auto& t : th) t.join();
+        rowptr = p_rowptr.data();
+        col = p_col.data();
+        val = p_val.data();
+    }
+    if (c->fmt == NB_FMT_DICT) {
+        if (c->dirs.empty()) {
+            c->dirs.resize((size_t)(c->Q - 1));
+            for (auto& d : c->dirs) d.init(n_rows);
+        }
+        const char* msg = "";
+        if (!nbdict::add_block(c->dirs[(size_t)bi], n_rows, rowptr, col, val, (int64_t)(bj + 1) * c->stride, c->dedup_tol,
+                               NB_MAX_CLS - 1, (int64_t)NB_PAT_MASK, &msg))
+            return fail(c, NB200_ERR_UNSUPPORTED, "upload_block_csr: %s; select NB200_FORMAT_ELL", msg);
+        c->blocks.push_back(CsrBlock{bi, bj, n_rows, nnz, nullptr, nullptr, nullptr});   // bookkeeping only
+        c->matrix_ready = false;
+        return NB200_OK;
+    }
     CsrBlock b{bi, bj, n_rows, nnz, nullptr, nullptr, nullptr};
     CUDA_TRY(c, cudaMalloc(&b.rowptr, (size_t)(n_rows + 1) * sizeof(int64_t)));
     CUDA_TRY(c, cudaMalloc(&b.col, (size_t)std::max<int64_t>(1, nnz) * sizeof(int32_t)));
@@ -469,6 +636,87 @@ extern "C" int nb200_upload_block_csr(nb200_ctx* c, int bi, int bj, int64_t n_ro
     return NB200_OK;
 }
 
+// Builds the device pools of the dictionary format from the host staging (dict_build.h).
+static int finalize_dict(nb200_ctx* c)
+{
+    const int nb = c->Q - 1;
+    const int64_t n = c->n_owned;
+    if (c->dirs.empty()) {
+        c->dirs.resize((size_t)nb);
+        for (auto& d : c->dirs) d.init(n);
+    }
+    c->desc_stride = std::max<int64_t>(32, c->n_slices * 32);
+    std::vector<NbDirClass> hcls((size_t)nb * NB_MAX_CLS);
+    memset(hcls.data(), 0, hcls.size() * sizeof(NbDirClass));
+    std::vector<int2> hdesc((size_t)nb * c->desc_stride, make_int2(0, 0));
+    void* dummy = nullptr;
+    CUDA_TRY(c, cudaMalloc(&dummy, 256));
+    CUDA_TRY(c, cudaMemsetAsync(dummy, 0, 256, c->stream));
+    c->pools.push_back(dummy);
+    c->dict_patterns = c->dict_lists = c->dict_pool_bytes = c->dict_classes = 0;
+    c->nnz_total = 0;
+    for (int a = 0; a < nb; a++) {
+        nbdict::DirBuild& d = c->dirs[(size_t)a];
+        c->nnz_total += d.nnz;
+        const int ncls = (int)d.cls.size();
+        const int empty_cls = ncls;       // K = 0 class for rows without entries
+        int64_t w_bytes = 0;
+        for (int ci = 0; ci < ncls; ci++) w_bytes += d.cls[(size_t)ci].n_pats() * d.cls[(size_t)ci].K * 8 + d.cls[(size_t)ci].n_lists() * d.cls[(size_t)ci].K * 4;
+        const int streamed = w_bytes > ((int64_t)48 << 20) ? 1 : 0;
+        for (int ci = 0; ci <= ncls; ci++) {
+            NbDirClass& H = hcls[(size_t)a * NB_MAX_CLS + ci];
+            if (ci == empty_cls) {
+                H.W = (const double*)dummy; H.L = (const int32_t*)dummy; H.K = 0; H.P = 32; H.NL = 32; H.streamed = 0;
+                continue;
+            }
+            nbdict::ClassBuild& B = d.cls[(size_t)ci];
+            const int K = B.K;
+            const int64_t P = ((B.n_pats() + 31) / 32) * 32, NL = ((int64_t)K + 3) / 4 * 4;   // NL: list pitch
+            double *dW = nullptr, *sW = nullptr;
+            int32_t* dL = nullptr;
+            CUDA_TRY(c, cudaMalloc(&dW, (size_t)K * P * 8));
+            c->pools.push_back(dW);
+            const size_t l_bytes = (size_t)std::max<int64_t>(1, B.n_lists()) * NL * 4;
+            CUDA_TRY(c, cudaMalloc(&dL, l_bytes));
+            c->pools.push_back(dL);
+            CUDA_TRY(c, cudaMemsetAsync(dW, 0, (size_t)K * P * 8, c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(dL, 0, l_bytes, c->stream));
+            CUDA_TRY(c, cudaMalloc(&sW, B.pats.size() * 8));
+            CUDA_TRY(c, cudaMemcpyAsync(sW, B.pats.data(), B.pats.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            if (B.n_lists())   // list-major as built, rows padded to the pitch
+                CUDA_TRY(c, cudaMemcpy2DAsync(dL, (size_t)NL * 4, B.lists.data(), (size_t)K * 4, (size_t)K * 4, (size_t)B.n_lists(), cudaMemcpyHostToDevice, c->stream));
+            k_pool_transpose<double><<<grid_for(B.n_pats() * K, 256), 256, 0, c->stream>>>(B.n_pats(), K, P, sW, dW);
+            c->launches += 1;
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            CUDA_TRY(c, cudaGetLastError());
+            cudaFree(sW);
+            H.W = dW; H.L = dL; H.K = K; H.P = P; H.NL = NL; H.streamed = streamed;
+            c->dict_patterns += B.n_pats();
+            c->dict_lists += B.n_lists();
+            c->dict_pool_bytes += (int64_t)K * P * 8 + (int64_t)l_bytes;
+            c->dict_classes++;
+            // the host copy of this class is not needed any more
+            std::vector<double>().swap(B.pats);
+            std::vector<int32_t>().swap(B.lists);
+        }
+        int2* hd = hdesc.data() + (size_t)a * c->desc_stride;
+        for (int64_t i = 0; i < n; i++) {
+            const int ci = d.row_cls[(size_t)i];
+            if (ci < 0) hd[i] = make_int2(0, (int)((unsigned)empty_cls << NB_PAT_BITS));
+            else hd[i] = make_int2(d.row_lst[(size_t)i], (int)(((unsigned)ci << NB_PAT_BITS) | (unsigned)d.row_pat[(size_t)i]));
+        }
+        for (int64_t i = n; i < c->desc_stride; i++) hd[i] = make_int2(0, (int)((unsigned)empty_cls << NB_PAT_BITS));
+    }
+    CUDA_TRY(c, cudaMalloc(&c->d_desc, hdesc.size() * sizeof(int2)));
+    CUDA_TRY(c, cudaMemcpy(c->d_desc, hdesc.data(), hdesc.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMalloc(&c->d_cls, hcls.size() * sizeof(NbDirClass)));
+    CUDA_TRY(c, cudaMemcpy(c->d_cls, hcls.data(), hcls.size() * sizeof(NbDirClass), cudaMemcpyHostToDevice));
+    c->ell_entries = c->nnz_total;
+    free_blocks(c);
+    c->matrix_ready = true;
+    return NB200_OK;
+}
+
 extern "C" int nb200_finalize_matrix(nb200_ctx* c)
 {
     if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "finalize_matrix: call set_layout first");
@@ -478,6 +726,7 @@ extern "C" int nb200_finalize_matrix(nb200_ctx* c)
     const int64_t n = c->n_owned;
     const int64_t n_slices = (n + 31) / 32;
     c->n_slices = n_slices;
+    if (c->fmt == NB_FMT_DICT) return finalize_dict(c);
     std::sort(c->blocks.begin(), c->blocks.end(), [](const CsrBlock& a, const CsrBlock& b) {
         return a.bi != b.bi ? a.bi < b.bi : a.bj < b.bj;
     });
@@ -555,8 +804,10 @@ extern "C" int nb200_set_halo(nb200_ctx* c, int n_nbr, const int32_t* nbr_rank, 
     for (int64_t k = 0; k < c->n_send; k++)
         if (send_idx[k] < 0 || send_idx[k] >= c->n_owned) return fail(c, NB200_ERR_ARG, "set_halo: send index out of owned range");
     if (c->n_send) {
+        std::vector<int32_t> si(send_idx, send_idx + c->n_send);
+        if (c->has_order) for (auto& v : si) v = c->perm[(size_t)v];
         CUDA_TRY(c, cudaMalloc(&c->d_send_idx, (size_t)c->n_send * sizeof(int32_t)));
-        CUDA_TRY(c, cudaMemcpy(c->d_send_idx, send_idx, (size_t)c->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->d_send_idx, si.data(), (size_t)c->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     {   // entry -> neighbour segment lookup for the pack / unpack kernels
         std::vector<int64_t> tmp((size_t)std::max<int64_t>(1, c->n_send), 0);
@@ -593,7 +844,8 @@ extern "C" int nb200_upload_population(nb200_ctx* c, int which, int q, const dou
     if (rc) return rc;
     if (q < 0 || q >= c->Q || !host) return fail(c, NB200_ERR_ARG, "upload_population: bad q/host");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaMemcpyAsync(c->pop[which][c->cur[which]] + (int64_t)q * c->stride, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    rc = copy_rows_in(c, host, 1, c->pop[which][c->cur[which]] + (int64_t)q * c->stride, c->stride);
+    if (rc) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
 }
@@ -604,7 +856,8 @@ extern "C" int nb200_download_population(nb200_ctx* c, int which, int q, double*
     if (rc) return rc;
     if (q < 0 || q >= c->Q || !host) return fail(c, NB200_ERR_ARG, "download_population: bad q/host");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaMemcpyAsync(host, c->pop[which][c->cur[which]] + (int64_t)q * c->stride, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    rc = copy_rows_out(c, host, 1, c->pop[which][c->cur[which]] + (int64_t)q * c->stride, c->stride);
+    if (rc) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
 }
@@ -617,8 +870,8 @@ static int copy_all(nb200_ctx* c, int which, double* host, int64_t n, bool up, b
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (n > 0) {
         double* dev = c->pop[which][c->cur[which]];
-        if (up) CUDA_TRY(c, cudaMemcpy2DAsync(dev, (size_t)c->stride * sizeof(double), host, (size_t)n * sizeof(double), (size_t)n * sizeof(double), c->Q, cudaMemcpyHostToDevice, c->stream));
-        else CUDA_TRY(c, cudaMemcpy2DAsync(host, (size_t)n * sizeof(double), dev, (size_t)c->stride * sizeof(double), (size_t)n * sizeof(double), c->Q, cudaMemcpyDeviceToHost, c->stream));
+        rc = up ? copy_rows_in(c, host, c->Q, dev, c->stride) : copy_rows_out(c, host, c->Q, dev, c->stride);
+        if (rc) return rc;
     }
     if (sync) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
@@ -633,7 +886,8 @@ extern "C" int nb200_upload_velocity(nb200_ctx* c, const double* u, int64_t n)
 {
     if (!c || !c->stride || n != c->n_owned || !u) return fail(c, NB200_ERR_ARG, "upload_velocity: bad argument");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    CUDA_TRY(c, cudaMemcpyAsync(c->u, u, (size_t)n * c->D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    int rc = copy_rows_in(c, u, c->D, c->u, n);
+    if (rc) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
 }
@@ -730,6 +984,7 @@ static StreamArgs stream_args(nb200_ctx* c)
 {
     StreamArgs A;
     A.ell_val = c->ell_val; A.ell_idx = c->ell_idx; A.slice_off = c->d_slice_off;
+    A.desc = c->d_desc; A.cls = c->d_cls; A.desc_stride = c->desc_stride;
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
     return A;
 }
@@ -750,6 +1005,7 @@ static NbLaunch make_launch(nb200_ctx* c)
     L.rho = c->rho; L.u = c->u; L.T = c->T; L.sensor = c->sensor; L.flag = c->d_flag;
     L.eq = c->cp.equilibrium == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
+    L.fmt = c->fmt;
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;
     L.partial = c->d_partial; L.n_partial_blocks = c->n_partial_blocks;
     L.out = c->d_partial ? c->d_partial + (size_t)c->n_partial_blocks * 5 : nullptr;
@@ -793,11 +1049,13 @@ static int launch_stream(nb200_ctx* c, bool do_f, bool do_g)
     const StreamArgs A = stream_args(c);
     dim3 grid(grid_for(c->n_slices * 32, 128), (unsigned)c->Q);
     if (do_f && do_g) {
-        k_stream<2><<<grid, 128, 0, c->stream>>>(A, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
+        if (c->fmt == NB_FMT_DICT) k_stream<NB_FMT_DICT, 2><<<grid, 128, 0, c->stream>>>(A, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
+        else k_stream<NB_FMT_ELL, 2><<<grid, 128, 0, c->stream>>>(A, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
         c->cur[0] ^= 1; c->cur[1] ^= 1;
     } else {
         const int w = do_f ? 0 : 1;
-        k_stream<1><<<grid, 128, 0, c->stream>>>(A, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
+        if (c->fmt == NB_FMT_DICT) k_stream<NB_FMT_DICT, 1><<<grid, 128, 0, c->stream>>>(A, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
+        else k_stream<NB_FMT_ELL, 1><<<grid, 128, 0, c->stream>>>(A, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
         c->cur[w] ^= 1;
     }
     c->launches++;
@@ -843,7 +1101,12 @@ extern "C" int nb200_collide(nb200_ctx* c)
 // Register budget decides where fusing pays: the f+g epilogue for Q=45 needs > 255 registers,
 // so that configuration runs stream(f,g in one matrix pass) + collide as two kernels (2 % more
 // traffic: 16*Q bytes per distribution against 67 kB of matrix per DoF).
-static bool use_fused(const nb200_ctx* c) { return c->ops->fused != nullptr && c->Q <= 25; }
+static bool use_fused(const nb200_ctx* c)
+{
+    static const char* env = getenv("NB200_FUSE");   // experiments only: NB200_FUSE=0 forces stream + collide
+    if (env && env[0] == '0') return false;
+    return c->ops->fused != nullptr && c->Q <= 25;
+}
 
 extern "C" int nb200_step(nb200_ctx* c, int n_steps)
 {
@@ -873,11 +1136,14 @@ extern "C" int nb200_download_moments(nb200_ctx* c, double* rho, double* u, doub
 {
     if (!c || !c->stride || n != c->n_owned) return fail(c, NB200_ERR_ARG, "download_moments: bad argument");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    const size_t nb = (size_t)n * sizeof(double);
-    if (rho) CUDA_TRY(c, cudaMemcpyAsync(rho, c->rho, nb, cudaMemcpyDeviceToHost, c->stream));
-    if (u) CUDA_TRY(c, cudaMemcpyAsync(u, c->u, nb * c->D, cudaMemcpyDeviceToHost, c->stream));
-    if (T) CUDA_TRY(c, cudaMemcpyAsync(T, c->T, nb, cudaMemcpyDeviceToHost, c->stream));
-    if (sensor) CUDA_TRY(c, cudaMemcpyAsync(sensor, c->sensor, nb, cudaMemcpyDeviceToHost, c->stream));
+    // one array at a time: the permuted path shares a single staging buffer, so fence between arrays
+    struct { double* host; const double* dev; int rows; } parts[4] = {{rho, c->rho, 1}, {u, c->u, c->D}, {T, c->T, 1}, {sensor, c->sensor, 1}};
+    for (auto& pt : parts) {
+        if (!pt.host) continue;
+        int rc = copy_rows_out(c, pt.host, pt.rows, pt.dev, n);
+        if (rc) return rc;
+        if (c->has_order) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
 }
@@ -945,7 +1211,34 @@ extern "C" int nb200_matrix_info(const nb200_ctx* c, int64_t* nnz, int64_t* devi
     if (!c || !c->matrix_ready) return NB200_ERR_ARG;
     if (nnz) *nnz = c->nnz_total;
     if (padded_entries) *padded_entries = c->ell_entries;
-    if (device_bytes) *device_bytes = c->ell_entries * 12 + (int64_t)(c->Q - 1) * (c->n_slices + 1) * 8;
+    if (device_bytes) {
+        if (c->fmt == NB_FMT_DICT) *device_bytes = c->dict_pool_bytes + (int64_t)(c->Q - 1) * c->desc_stride * 8;
+        else *device_bytes = c->ell_entries * 12 + (int64_t)(c->Q - 1) * (c->n_slices + 1) * 8;
+    }
+    return NB200_OK;
+}
+
+extern "C" int nb200_set_matrix_format(nb200_ctx* c, int format, double value_dedup_tol)
+{
+    if (!c) return NB200_ERR_ARG;
+    if (format != NB200_FORMAT_ELL && format != NB200_FORMAT_DICT) return fail(c, NB200_ERR_ARG, "set_matrix_format: unknown format %d", format);
+    if (!(value_dedup_tol >= 0.0) || value_dedup_tol > 1e-10) return fail(c, NB200_ERR_ARG, "set_matrix_format: tolerance must be in [0, 1e-10]");
+    if (!c->blocks.empty()) return fail(c, NB200_ERR_ARG, "set_matrix_format: call before the first upload_block_csr");
+    c->fmt = format == NB200_FORMAT_DICT ? NB_FMT_DICT : NB_FMT_ELL;
+    c->dedup_tol = value_dedup_tol;
+    return NB200_OK;
+}
+
+extern "C" int nb200_matrix_format_info(const nb200_ctx* c, int64_t out[6], double* value_dedup_tol)
+{
+    if (!c || !c->matrix_ready || !out) return NB200_ERR_ARG;
+    out[0] = c->fmt == NB_FMT_DICT ? NB200_FORMAT_DICT : NB200_FORMAT_ELL;
+    out[1] = c->fmt == NB_FMT_DICT ? c->dict_patterns : 0;
+    out[2] = c->fmt == NB_FMT_DICT ? c->dict_lists : 0;
+    out[3] = c->fmt == NB_FMT_DICT ? c->dict_pool_bytes : c->ell_entries * 12;
+    out[4] = c->fmt == NB_FMT_DICT ? (int64_t)(c->Q - 1) * c->desc_stride * 8 : (int64_t)(c->Q - 1) * (c->n_slices + 1) * 8;
+    out[5] = c->fmt == NB_FMT_DICT ? c->dict_classes : 0;
+    if (value_dedup_tol) *value_dedup_tol = c->dedup_tol;
     return NB200_OK;
 }
 

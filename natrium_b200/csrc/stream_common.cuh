@@ -1,12 +1,42 @@
-// stream_common.cuh -- warp-sliced ELL row product shared by all streaming kernels.
+// stream_common.cuh -- the two device formats of the streaming matrix and their row products.
+//
+//   NB_FMT_ELL   warp-sliced ELL: 8 B value + 4 B index per stored entry, streamed from HBM.
+//   NB_FMT_DICT  dictionary format: every row is a (column-list id, weight-pattern id) pair; lists
+//                (list-major) and patterns (k-major) live in pools, one pool per row length K ("class").  Rows whose
+//                departure point lies in the same source cell share a column list; rows with the
+//                same position relative to their cell share a weight pattern (up to the dedup
+//                tolerance), so on a regular mesh the matrix shrinks from 12 B/nnz to 8 B/row and the
+//                kernel is bound by the populations, not by the matrix.  Without any sharing the
+//                pools degenerate to a column-major ELL, so the format is always valid.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
+enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1 };
+
+#define NB_CLS_BITS 6
+#define NB_MAX_CLS (1 << NB_CLS_BITS)           // row-length classes per direction
+#define NB_PAT_BITS (32 - NB_CLS_BITS)
+#define NB_PAT_MASK ((1u << NB_PAT_BITS) - 1u)
+
+// one row-length class of one direction
+struct NbDirClass {
+    const double* __restrict__ W;     // [K][P]  weight patterns, k-major (lanes of a warp hold different patterns)
+    const int32_t* __restrict__ L;    // [n_lists][NL] column lists (flat population index), list-major, 16-byte aligned rows
+    int32_t K;
+    int32_t streamed;                 // pools too large to stay cached: read with evict-first
+    int64_t P, NL;                    // P: padded pattern count (k-major pitch); NL: list pitch = K rounded up to 4
+};
+
 struct StreamArgs {
+    // NB_FMT_ELL
     const double* __restrict__ ell_val;
     const int32_t* __restrict__ ell_idx;
     const int64_t* __restrict__ slice_off;   // [(Q-1)][n_slices+1]
+    // NB_FMT_DICT
+    const int2* __restrict__ desc;           // [(Q-1)][desc_stride]: x = list id, y = class << 26 | pattern id
+    const NbDirClass* __restrict__ cls;      // [(Q-1)][NB_MAX_CLS]
+    int64_t desc_stride;
     int64_t n_slices;
     int64_t n_owned;
     int64_t stride;
@@ -14,9 +44,9 @@ struct StreamArgs {
 
 // one ELL row dot product for 1 or 2 right-hand sides (f and g share the matrix pass)
 template <int NRHS>
-__device__ __forceinline__ void nb_row_dot(const StreamArgs& A, int alpha_m1, int64_t slice, int lane,
-                                           const double* __restrict__ x0, const double* __restrict__ x1,
-                                           double& y0, double& y1)
+__device__ __forceinline__ void nb_row_dot_ell(const StreamArgs& A, int alpha_m1, int64_t slice, int lane,
+                                               const double* __restrict__ x0, const double* __restrict__ x1,
+                                               double& y0, double& y1)
 {
     const int64_t* so = A.slice_off + (int64_t)alpha_m1 * (A.n_slices + 1) + slice;
     const int64_t off = __ldg(so);
@@ -51,3 +81,81 @@ __device__ __forceinline__ void nb_row_dot(const StreamArgs& A, int alpha_m1, in
     y1 = a1;
 }
 
+// Dictionary row product, one row per lane.  The column list of a row is contiguous (list-major pool,
+// padded to a multiple of 4 entries) and is read with 16-byte loads; lanes whose rows read the same
+// source cell read the same addresses (one L1 wavefront).  Weight patterns are k-major: lanes hold
+// different (neighbouring) pattern ids, so one k is one or two adjacent lines.  With a cell-blocked DoF
+// order all three streams (list, weights, gathered support values) are L1/L2 hits.
+// Summation order per row is k = 0..K-1, exactly as stored (and as the CSR reference loop).
+template <int NRHS, bool STREAMED>
+__device__ __forceinline__ void nb_dict_accumulate(const double* __restrict__ W, const int32_t* __restrict__ L,
+                                                   int K, int64_t P, const double* __restrict__ x0,
+                                                   const double* __restrict__ x1, double& a0, double& a1)
+{
+    const int4* __restrict__ L4 = reinterpret_cast<const int4*>(L);
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+        const int4 i0 = STREAMED ? __ldcs(L4 + (k >> 2)) : __ldg(L4 + (k >> 2));
+        const int4 i1 = STREAMED ? __ldcs(L4 + (k >> 2) + 1) : __ldg(L4 + (k >> 2) + 1);
+        const int32_t ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        double vv[8], xa[8], xb[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            xa[j] = __ldg(x0 + ii[j]);
+            if (NRHS == 2) xb[j] = __ldg(x1 + ii[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            a0 += vv[j] * xa[j];
+            if (NRHS == 2) a1 += vv[j] * xb[j];
+        }
+    }
+    for (; k + 4 <= K; k += 4) {
+        const int4 i0 = STREAMED ? __ldcs(L4 + (k >> 2)) : __ldg(L4 + (k >> 2));
+        const int32_t ii[4] = {i0.x, i0.y, i0.z, i0.w};
+        double vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            a0 += vv[j] * __ldg(x0 + ii[j]);
+            if (NRHS == 2) a1 += vv[j] * __ldg(x1 + ii[j]);
+        }
+    }
+    for (; k < K; k++) {
+        const int32_t ii = __ldg(L + k);
+        const double vv = __ldg(W + (int64_t)k * P);
+        a0 += vv * __ldg(x0 + ii);
+        if (NRHS == 2) a1 += vv * __ldg(x1 + ii);
+    }
+}
+
+template <int NRHS>
+__device__ __forceinline__ void nb_row_dot_dict(const StreamArgs& A, int alpha_m1, int64_t row,
+                                                const double* __restrict__ x0, const double* __restrict__ x1,
+                                                double& y0, double& y1)
+{
+    const int2 d = __ldcs(A.desc + (int64_t)alpha_m1 * A.desc_stride + row);
+    const unsigned cw = (unsigned)d.y;
+    const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + (cw >> NB_PAT_BITS);
+    const int K = C->K;
+    const double* __restrict__ W = C->W + (cw & NB_PAT_MASK);
+    const int32_t* __restrict__ L = C->L + (int64_t)d.x * C->NL;     // NL = list pitch (K rounded up to 4)
+    const int64_t P = C->P;
+    double a0 = 0.0, a1 = 0.0;
+    if (C->streamed) nb_dict_accumulate<NRHS, true>(W, L, K, P, x0, x1, a0, a1);
+    else nb_dict_accumulate<NRHS, false>(W, L, K, P, x0, x1, a0, a1);
+    y0 = a0;
+    y1 = a1;
+}
+
+template <int FMT, int NRHS>
+__device__ __forceinline__ void nb_row_dot(const StreamArgs& A, int alpha_m1, int64_t row, int64_t slice, int lane,
+                                           const double* __restrict__ x0, const double* __restrict__ x1,
+                                           double& y0, double& y1)
+{
+    if (FMT == NB_FMT_ELL) nb_row_dot_ell<NRHS>(A, alpha_m1, slice, lane, x0, x1, y0, y1);
+    else nb_row_dot_dict<NRHS>(A, alpha_m1, row, x0, x1, y0, y1);
+}

@@ -196,6 +196,33 @@ class SlabPartition:
     def owned_points(self):
         return self.pb.points_of_planes(self.owned_planes)
 
+    def cell_blocked_order(self):
+        """Owned local DoF indices in the order SemiLagrangian::fillSparseObject visits them
+        (SemiLagrangian.cpp:201-223): cell by cell (lexicographic, x fastest), cell->get_dof_indices(),
+        first visit wins.  Input for nb200_set_dof_order."""
+        pb = self.pb
+        p, dim = pb.p, pb.dim
+        loc = np.arange(p + 1)
+        last = pb.axes[-1]
+        own_cells = [c for c in range(last.n) if np.any(self.plane_owner[c * p + loc] == self.rank)]
+        gz = (np.asarray(own_cells, dtype=np.int64)[:, None] * p + loc[None, :])          # (ncz, p+1) planes
+        zbase = np.where(self.plane_owner[gz] == self.rank, self.base[gz], -1)
+        gx = (np.arange(pb.axes[0].n, dtype=np.int64)[:, None] * p + loc[None, :])        # (ncx, p+1)
+        if dim == 2:
+            ids = zbase[:, None, :, None] + gx[None, :, None, :]                         # (cz, cx, lz, lx)
+            ok = np.broadcast_to(zbase[:, None, :, None] >= 0, ids.shape)
+        else:
+            ndx = pb.nd[0]
+            gy = (np.arange(pb.axes[1].n, dtype=np.int64)[:, None] * p + loc[None, :])
+            ids = (zbase[:, None, None, :, None, None] + gy[None, :, None, None, :, None] * ndx
+                   + gx[None, None, :, None, None, :])                                    # (cz, cy, cx, lz, ly, lx)
+            ok = np.broadcast_to(zbase[:, None, None, :, None, None] >= 0, ids.shape)
+        flat = ids.reshape(-1)[ok.reshape(-1)]
+        uniq, first = np.unique(flat, return_index=True)
+        order = uniq[np.argsort(first, kind="stable")]
+        assert len(order) == self.n_owned
+        return order.astype(np.int32)
+
     def owned_global_ids(self):
         return (self.owned_planes[:, None] * self.pb.plane + np.arange(self.pb.plane)[None, :]).reshape(-1)
 

@@ -183,6 +183,7 @@ class CFDSolver:
         self.m_advectionOperator.setDeltaT(dt)
         part = self.m_advectionOperator.getPartition()
         self.ctx.set_layout(part.n_owned, part.n_ghost, with_g)
+        self.ctx.set_dof_order(part.cell_blocked_order())     # cell-by-cell, the order fillSparseObject walks
         self.m_advectionOperator.reassemble()
         self.m_f = DistributionFunctions(self.ctx, 0)
         self.m_time, self.m_i = 0.0, 0

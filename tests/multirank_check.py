@@ -22,6 +22,7 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
     ctx = Context(local, rank, world, uid)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     ctx.set_layout(part.n_owned, part.n_ghost, with_g)
+    ctx.set_dof_order(part.cell_blocked_order())      # internal order: halo indices are translated inside
     harness.upload_streaming_matrix(ctx, pb, part, st, dt)
     ctx.set_halo(*part.halo_plan())
     if with_g:

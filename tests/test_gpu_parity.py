@@ -16,13 +16,24 @@ TOL_STEP = 1e-12      # north_star: 1e-12 relative per step
 TOL_CONS = 1e-13      # conserved sums vs oracle
 
 
-def make_ctx(case, with_matrix=True):
-    from natrium_b200 import Context, harness
+# device formats of the streaming matrix: library default (dictionary, value tolerance 1e-14), bit-faithful
+# dictionary (tolerance 0) and the generic warp-sliced ELL
+# (format, value tolerance, cell-blocked internal DoF order)
+FORMATS = [None, ("dict", 1e-14, True), ("dict", 0.0, False), ("ell", 0.0, False), ("ell", 0.0, True)]
+FORMAT_IDS = ["dict-default", "dict-cellorder", "dict-exact", "ell", "ell-cellorder"]
+
+
+def make_ctx(case, with_matrix=True, fmt=None):
+    from natrium_b200 import Context, harness, _capi
     c, st, pb, dt = common.product_problem(case)
     ctx = Context(0)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     part = harness.SlabPartition(pb, st, dt)
     ctx.set_layout(part.n_owned, part.n_ghost, bool(c.get("with_g")))
+    if fmt is not None:
+        ctx.set_matrix_format(_capi.FORMAT_DICT if fmt[0] == "dict" else _capi.FORMAT_ELL, fmt[1])
+        if fmt[2]:
+            ctx.set_dof_order(part.cell_blocked_order())
     if with_matrix:
         harness.upload_streaming_matrix(ctx, pb, part, st, dt)
     return ctx, c, st, pb, dt, part
@@ -37,11 +48,12 @@ def set_collision(ctx, c, dt, **kw):
         ctx.set_collision(c["nu"], dt, equilibrium=kw.get("equilibrium", _capi.BGK_EQUILIBRIUM))
 
 
+@pytest.mark.parametrize("fmt", FORMATS, ids=FORMAT_IDS)
 @pytest.mark.parametrize("case", ["c1_tgv2d_d2q9", "tgv3d_d3q19_small", "tgv3d_d3q15", "tgv2d_d2q25", "tgv3d_d3q45"])
-def test_stream_matches_oracle(case, oracle_lib):
+def test_stream_matches_oracle(case, fmt, oracle_lib):
     """nb200_stream == vmult (CFDSolver.cpp:671-672): f.FStream = M f_old.FStream, f0 untouched."""
     o = common.oracle_problem(case)
-    ctx, c, st, pb, dt, part = make_ctx(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=fmt)
     assert dt == o["dt"]
     ctx.upload_populations(0, o["f"])
     ctx.stream(0)
@@ -128,6 +140,8 @@ def test_collide_fg_matches_oracle(stencil, eq, prandtl, sutherland, oracle_lib)
     ctx = Context(0)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     ctx.set_layout(n, 0, True)
+    if sutherland:
+        ctx.set_dof_order(rng.permutation(n))          # internal DoF order must be invisible to the caller
     ctx.set_collision(nu, dt, equilibrium=eq, with_g=True, gamma=gamma, prandtl=prandtl, sutherland=sutherland)
     ctx.upload_populations(0, f)
     ctx.upload_populations(1, g)
@@ -146,11 +160,12 @@ def test_collide_fg_matches_oracle(stencil, eq, prandtl, sutherland, oracle_lib)
     ctx.close()
 
 
+@pytest.mark.parametrize("fmt", FORMATS, ids=FORMAT_IDS)
 @pytest.mark.parametrize("case", ["c1_tgv2d_d2q9", "tgv3d_d3q19_small", "tgv3d_d3q15", "tgv2d_d2q25", "tgv3d_d3q45"])
-def test_fused_step_matches_oracle_per_step(case, oracle_lib):
+def test_fused_step_matches_oracle_per_step(case, fmt, oracle_lib):
     """10 steps of nb200_step(1) vs the reference-ordered CPU step from the same state each step."""
     o = common.oracle_problem(case)
-    ctx, c, st, pb, dt, part = make_ctx(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=fmt)
     with_g = bool(c.get("with_g"))
     set_collision(ctx, c, dt)
     stepper = oracle_lib.ReferenceOrderStepper(o["st"], o["blocks"], o["dofs"].N, c["nu"], dt,
@@ -199,12 +214,13 @@ def test_unfused_equals_fused():
     ctx.close()
 
 
-def test_conserved_moments_1000_steps(oracle_lib):
+@pytest.mark.parametrize("fmt", FORMATS, ids=FORMAT_IDS)
+def test_conserved_moments_1000_steps(fmt, oracle_lib):
     """Config 1 (TGV2D, D2Q9, p=4, 8x8 cells): sums of rho, rho*u, energy vs the oracle at steps 1, 10, 100, 1000,
     and the physics bound of integration test #11 (E_kin(t)/E_kin(0) = exp(-4 nu t))."""
     case = "c1_tgv2d_d2q9"
     o = common.oracle_problem(case)
-    ctx, c, st, pb, dt, part = make_ctx(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=fmt)
     set_collision(ctx, c, dt)
     stepper = oracle_lib.ReferenceOrderStepper(o["st"], o["blocks"], o["dofs"].N, c["nu"], dt)
     f = o["f"].copy()
@@ -253,7 +269,8 @@ def test_uniform_flow_stays_uniform():
     ctx.close()
 
 
-def test_in_initialization_collide(oracle_lib):
+@pytest.mark.parametrize("ordered", [False, True])
+def test_in_initialization_collide(ordered, oracle_lib):
     """inInitializationProcedure: velocities are an input (CollisionOperator.h:79-91)."""
     from natrium_b200 import Context, Stencil
     st, ost = Stencil("D2Q9", 1.0), oracle_lib.Stencil("D2Q9", 1.0)
@@ -263,6 +280,10 @@ def test_in_initialization_collide(oracle_lib):
     ctx = Context(0)
     ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
     ctx.set_layout(n, 0, False)
+    if ordered:
+        ctx.set_dof_order(np.random.default_rng(1).permutation(n))
+        with pytest.raises(Exception):
+            ctx.set_dof_order(np.zeros(n, dtype=np.int32))     # not a permutation
     ctx.set_collision(0.03, 0.1, in_init=True)
     ctx.upload_populations(0, f)
     ctx.upload_velocity(u0)
@@ -300,22 +321,30 @@ def test_error_behaviour():
     ctx.close()
 
 
-def test_ragged_and_offdiagonal_blocks(oracle_lib):
+@pytest.mark.parametrize("fmt", FORMATS, ids=FORMAT_IDS)
+def test_ragged_and_offdiagonal_blocks(fmt, oracle_lib):
     """Generic CSR input: ragged rows, empty rows, off-diagonal (wall-bounce) blocks, duplicates-free;
-    n not a multiple of the slice size."""
+    n not a multiple of the slice size.  Block (5,5) has more distinct row lengths than the dictionary
+    format has exact classes (padded power-of-two classes take over)."""
     import scipy.sparse as sp
-    from natrium_b200 import Context, Stencil
+    from natrium_b200 import Context, Stencil, _capi
     st = Stencil("D2Q9", 1.0)
     n = 1000 + 7
     rng = np.random.default_rng(3)
     blocks = {}
-    for (bi, bj, dens) in [(0, 0, 0.01), (0, 2, 0.002), (1, 1, 0.02), (3, 1, 0.001), (4, 4, 0.0), (7, 7, 0.05), (7, 0, 0.01)]:
+    for (bi, bj, dens) in [(0, 0, 0.01), (0, 2, 0.002), (1, 1, 0.02), (3, 1, 0.001), (4, 4, 0.0), (7, 7, 0.05), (7, 0, 0.01),
+                           (5, 5, 0.15)]:
         m = sp.random(n, n, density=dens, random_state=rng, format="csr", dtype=np.float64)
         m.sort_indices()
         blocks[(bi, bj)] = m
+    assert len(set(np.diff(blocks[(5, 5)].indptr).tolist())) > 50
     ctx = Context(0)
     ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
     ctx.set_layout(n, 0, False)
+    if fmt is not None:
+        ctx.set_matrix_format(_capi.FORMAT_DICT if fmt[0] == "dict" else _capi.FORMAT_ELL, fmt[1])
+        if fmt[2]:
+            ctx.set_dof_order(rng.permutation(n))
     for (bi, bj), m in blocks.items():
         ctx.upload_block_csr(bi, bj, m.indptr, m.indices, m.data)
     ctx.finalize_matrix()
