@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cpu-sample-layers", type=int, default=8, help="z cell layers of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="dict", choices=["dict", "ell"], help="device format of the streaming matrix")
-    ap.add_argument("--dof-order", default="cell", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--dof-order", default="none", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     return ap.parse_args()
 

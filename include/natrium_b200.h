@@ -146,6 +146,10 @@ int nb200_download_populations_async(nb200_ctx *ctx, int which, double *pinned_h
 /* Initial macroscopic velocity for in_init collisions (u_raw is an input then). u: [D][n_owned]. */
 int nb200_upload_velocity(nb200_ctx *ctx, const double *u, int64_t n);
 
+/* Macroscopic density m_density (n_owned doubles).  Only MRTEntropic reads it: its guard looks at the density
+ * stored by the previous call (L/collision/MRTEntropic.cpp:229-232).  A new layout starts with densities = 1. */
+int nb200_upload_density(nb200_ctx *ctx, const double *rho, int64_t n);
+
 /* ---- per-step operators ------------------------------------------------------------------ */
 
 int nb200_set_collision(nb200_ctx *ctx, const nb200_collision_params *p);

@@ -65,6 +65,7 @@ SIGNATURES = {
     "nb200_upload_populations_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "nb200_download_populations_async": (C.c_int, [_vp, C.c_int, _vp, C.c_int64]),
     "nb200_upload_velocity": (C.c_int, [_vp, _dp, C.c_int64]),
+    "nb200_upload_density": (C.c_int, [_vp, _dp, C.c_int64]),
     "nb200_set_collision": (C.c_int, [_vp, C.POINTER(CollisionParams)]),
     "nb200_update_ghosted": (C.c_int, [_vp]),
     "nb200_stream": (C.c_int, [_vp, C.c_int]),
@@ -225,6 +226,10 @@ class Context:
     def upload_velocity(self, u):
         u = _as_f64(u)
         self._check(self.lib.nb200_upload_velocity(self._h, _dptr(u), u.shape[1]))
+
+    def upload_density(self, rho):
+        rho = _as_f64(rho)
+        self._check(self.lib.nb200_upload_density(self._h, _dptr(rho), rho.shape[0]))
 
     # ---- operators
     def set_collision(self, viscosity, dt, scheme=BGK_STANDARD, equilibrium=BGK_EQUILIBRIUM, with_g=False,

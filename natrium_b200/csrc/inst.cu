@@ -13,6 +13,18 @@
 #define NB_FUSE_F 1
 #endif
 
+// entropic kernels exist where the reference has them: KBCStandard D2Q9 / D3Q15, MRTEntropic D3Q19
+#if (NB_D == 2 && NB_Q == 9) || (NB_D == 3 && NB_Q == 15)
+#define NB_IF_KBC(stmt) stmt
+#else
+#define NB_IF_KBC(stmt) return -1
+#endif
+#if (NB_D == 3 && NB_Q == 19)
+#define NB_IF_MRTE(stmt) stmt
+#else
+#define NB_IF_MRTE(stmt) return -1
+#endif
+
 namespace {
 
 constexpr int D = NB_D;
@@ -26,6 +38,10 @@ int bind(const NbLaunch& L)
     if (s_owner != L.owner || s_version != L.version) {
         cudaError_t e = cudaMemcpyToSymbolAsync(cP, L.hc, sizeof(NbConst), 0, cudaMemcpyHostToDevice, L.stream);
         if (e != cudaSuccess) return (int)e;
+        if (D == 3 && Q == 19 && L.mrt) {
+            e = cudaMemcpyToSymbolAsync(cM, L.mrt, sizeof(NbMrtTables), 0, cudaMemcpyHostToDevice, L.stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         s_owner = L.owner;
         s_version = L.version;
     }
@@ -42,8 +58,17 @@ int fused(const NbLaunch& L)
     if (!L.with_g) {
 #if NB_FUSE_F
 #define NB_LAUNCH_F(EQ, FMT) k_stream_collide_f<D, Q, EQ, FMT><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag)
-        if (L.fmt == NB_FMT_DICT) { if (L.eq == NB_EQ_BGK) NB_LAUNCH_F(NB_EQ_BGK, NB_FMT_DICT); else NB_LAUNCH_F(NB_EQ_QUARTIC, NB_FMT_DICT); }
-        else { if (L.eq == NB_EQ_BGK) NB_LAUNCH_F(NB_EQ_BGK, NB_FMT_ELL); else NB_LAUNCH_F(NB_EQ_QUARTIC, NB_FMT_ELL); }
+#define NB_LAUNCH_F_KIND(FMT)                                                                    \
+    do {                                                                                         \
+        if (L.eq == NB_EQ_BGK) NB_LAUNCH_F(NB_EQ_BGK, FMT);                                      \
+        else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_F(NB_EQ_QUARTIC, FMT);                         \
+        else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_F(NB_KIND_KBC, FMT)); }              \
+        else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_F(NB_KIND_MRT_ENTROPIC, FMT)); } \
+        else return -1;                                                                          \
+    } while (0)
+        if (L.fmt == NB_FMT_DICT) NB_LAUNCH_F_KIND(NB_FMT_DICT);
+        else NB_LAUNCH_F_KIND(NB_FMT_ELL);
+#undef NB_LAUNCH_F_KIND
 #undef NB_LAUNCH_F
 #else
         return -1;
@@ -78,8 +103,13 @@ int collide(const NbLaunch& L)
     const int64_t n = L.A.n_owned;
     const unsigned grid = grid_for(n, 128);
     if (!L.with_g) {
-        if (L.eq == NB_EQ_BGK) k_collide_f<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);
-        else k_collide_f<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);
+#define NB_LAUNCH_C(EQ) k_collide_f<D, Q, EQ><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag)
+        if (L.eq == NB_EQ_BGK) NB_LAUNCH_C(NB_EQ_BGK);
+        else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_C(NB_EQ_QUARTIC);
+        else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_C(NB_KIND_KBC)); }
+        else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_C(NB_KIND_MRT_ENTROPIC)); }
+        else return -1;
+#undef NB_LAUNCH_C
     } else {
 #if NB_WITH_G
         if (L.eq == NB_EQ_BGK) k_collide_fg<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);

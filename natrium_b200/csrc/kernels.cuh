@@ -4,6 +4,7 @@
 #pragma once
 #include "stream_common.cuh"
 #include "collide.cuh"
+#include "entropic.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // kernels: hot path
@@ -43,14 +44,13 @@ k_stream_collide_f(StreamArgs A, const double* __restrict__ x, double* __restric
     double f[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
-    double rho, u[3];
-    nb_collide_bgk<D, Q, EQ>(f, rho, u, nullptr);
-    if (rho < 1e-10) *flag = 1;
+    double rho, v[3] = {0.0, 0.0, 0.0};
+    if (nb_collide_f<D, Q, EQ>(f, rho, v, false, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
 #pragma unroll
     for (int q = 0; q < Q; q++) y[(int64_t)q * A.stride + row] = f[q];
     rho_out[row] = rho;
 #pragma unroll
-    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = v[j];
 }
 
 // Fused stream + collide for f and g (one pass over the matrix for both distributions).
@@ -113,19 +113,18 @@ k_collide_f(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __rest
     double f[Q];
 #pragma unroll
     for (int q = 0; q < Q; q++) f[q] = fbuf[(int64_t)q * stride + row];
-    double rho, u[3], uo[3];
+    double rho, v[3] = {0.0, 0.0, 0.0};
     if (in_init) {
 #pragma unroll
-        for (int j = 0; j < D; j++) uo[j] = u_out[(int64_t)j * n + row];
+        for (int j = 0; j < D; j++) v[j] = u_out[(int64_t)j * n + row];
     }
-    nb_collide_bgk<D, Q, EQ>(f, rho, u, in_init ? uo : nullptr);
-    if (rho < 1e-10) *flag = 1;
+    if (nb_collide_f<D, Q, EQ>(f, rho, v, in_init != 0, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
 #pragma unroll
     for (int q = 0; q < Q; q++) fbuf[(int64_t)q * stride + row] = f[q];
     rho_out[row] = rho;
     if (!in_init) {
 #pragma unroll
-        for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = u[j] * cP.scaling;
+        for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = v[j];
     }
 }
 

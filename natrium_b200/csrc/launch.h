@@ -6,6 +6,7 @@
 #include "stream_common.cuh"
 
 struct NbConst;
+struct NbMrtHost;
 
 struct NbLaunch {
     cudaStream_t stream;
@@ -20,6 +21,7 @@ struct NbLaunch {
     int in_init;
     // constant-block ownership: the unit re-uploads when (owner, version) changed
     const NbConst* hc; const void* owner; uint64_t version;
+    const NbMrtHost* mrt;   // MRTEntropic tables (D3Q19 unit only)
     // conserved sums
     double* partial; int n_partial_blocks; double* out;
 };

@@ -125,6 +125,8 @@ struct nb200_ctx {
     uint64_t const_version = 1;
     nb200_collision_params cp;
     bool collision_set = false;
+    int kind = NB_EQ_BGK;                    // kernel template selector (NB_EQ_* / NB_KIND_*)
+    NbMrtHost mrt;                           // MRTEntropic D3Q19 tables
     // halo
     int n_nbr = 0;
     std::vector<int32_t> nbr_rank;
@@ -479,7 +481,10 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
     CUDA_TRY(c, cudaMalloc(&c->u, nb * 3));
     CUDA_TRY(c, cudaMalloc(&c->T, nb));
     CUDA_TRY(c, cudaMalloc(&c->sensor, nb));
-    CUDA_TRY(c, cudaMemsetAsync(c->rho, 0, nb, c->stream));
+    {   // densities start at 1 like a freshly constructed solver (only MRTEntropic's stale-density guard reads them)
+        std::vector<double> ones((size_t)std::max<int64_t>(1, n_owned), 1.0);
+        CUDA_TRY(c, cudaMemcpy(c->rho, ones.data(), nb, cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(c, cudaMemsetAsync(c->u, 0, nb * 3, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->T, 0, nb, c->stream));
     CUDA_TRY(c, cudaMemsetAsync(c->sensor, 0, nb, c->stream));
@@ -892,15 +897,72 @@ extern "C" int nb200_upload_velocity(nb200_ctx* c, const double* u, int64_t n)
     return NB200_OK;
 }
 
+extern "C" int nb200_upload_density(nb200_ctx* c, const double* rho, int64_t n)
+{
+    if (!c || !c->stride || n != c->n_owned || !rho) return fail(c, NB200_ERR_ARG, "upload_density: bad argument");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    int rc = copy_rows_in(c, rho, 1, c->rho, n);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return NB200_OK;
+}
+
 // ---- collision setup ------------------------------------------------------------------------
+
+// d'Humieres D3Q19 moment basis in the direction order MRTEntropic.cpp:172-198 assumes
+// (+-x, +-y, +-z, xy-, xz-, yz-diagonals), and its inverse M^-1 = M^T diag(1/|row|^2) (rows are orthogonal).
+static void fill_mrt_entropic_tables(NbMrtHost& t)
+{
+    static const int cx[19] = {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, 1, -1, 0, 0, 0, 0};
+    static const int cy[19] = {0, 0, 0, 1, -1, 0, 0, 1, 1, -1, -1, 0, 0, 0, 0, 1, -1, 1, -1};
+    static const int cz[19] = {0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, 1, -1, -1, 1, 1, -1, -1};
+    for (int q = 0; q < 19; q++) {
+        const double x = cx[q], y = cy[q], z = cz[q], c2 = x * x + y * y + z * z;
+        double* col[19];
+        for (int p = 0; p < 19; p++) col[p] = &t.tm[p][q];
+        *col[0] = 1;
+        *col[1] = 19 * c2 - 30;
+        *col[2] = (21 * c2 * c2 - 53 * c2 + 24) / 2;
+        *col[3] = x;  *col[4] = (5 * c2 - 9) * x;
+        *col[5] = y;  *col[6] = (5 * c2 - 9) * y;
+        *col[7] = z;  *col[8] = (5 * c2 - 9) * z;
+        *col[9] = 3 * x * x - c2;  *col[10] = (3 * c2 - 5) * (3 * x * x - c2);
+        *col[11] = y * y - z * z;  *col[12] = (3 * c2 - 5) * (y * y - z * z);
+        *col[13] = x * y;  *col[14] = y * z;  *col[15] = x * z;
+        *col[16] = (y * y - z * z) * x;  *col[17] = (z * z - x * x) * y;  *col[18] = (x * x - y * y) * z;
+    }
+    for (int p = 0; p < 19; p++) {
+        double n2 = 0;
+        for (int q = 0; q < 19; q++) n2 += t.tm[p][q] * t.tm[p][q];
+        for (int q = 0; q < 19; q++) t.invm[q][p] = t.tm[p][q] / n2;
+    }
+}
 
 extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p)
 {
     if (!c || !p || !c->stencil_set) return fail(c, NB200_ERR_ARG, "set_collision: call set_stencil first");
     if (p->viscosity <= 0 || p->dt <= 0) return fail(c, NB200_ERR_ARG, "set_collision: viscosity and dt must be positive");
-    if (p->scheme != NB200_BGK_STANDARD) return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- scheme %d", p->scheme);
+    if (p->scheme != NB200_BGK_STANDARD && p->scheme != NB200_KBC_STANDARD && p->scheme != NB200_MRT_ENTROPIC)
+        return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- scheme %d", p->scheme);
     if (p->equilibrium != NB200_BGK_EQUILIBRIUM && p->equilibrium != NB200_QUARTIC_EQUILIBRIUM) return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- equilibrium %d", p->equilibrium);
     if (!c->ops) return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- D%dQ%d", c->D, c->Q);
+    if (p->scheme != NB200_BGK_STANDARD) {
+        // legacy entropic family: KBCStandard::collideAll (D2Q9, D3Q15; KBCStandard.cpp:70-85 throws otherwise),
+        // MRTEntropic::collideAll (D3Q19; the D2Q9 branch of MRTEntropic.cpp:39-165 is not on the path)
+        const bool kbc = p->scheme == NB200_KBC_STANDARD;
+        const bool ok = !p->with_g && (kbc ? ((c->D == 2 && c->Q == 9) || (c->D == 3 && c->Q == 15)) : (c->D == 3 && c->Q == 19));
+        if (!ok) return fail(c, NB200_ERR_UNSUPPORTED, kbc ? "KBC_Standard only implemented for D2Q9 and D3Q15" : "MRT_ENTROPIC only implemented for D3Q19 (f only)");
+        c->cp = *p;
+        NbConst& h = c->hc;
+        const double cs2s = h.cs2 * h.scaling * h.scaling;
+        h.tau = p->viscosity / (p->dt * cs2s) + 0.5;
+        h.tau_legacy = p->viscosity / (p->dt * cs2s);     // CollisionModel::calculateRelaxationParameter
+        c->kind = kbc ? NB_KIND_KBC : NB_KIND_MRT_ENTROPIC;
+        if (!kbc) fill_mrt_entropic_tables(c->mrt);
+        c->collision_set = true;
+        c->const_version = ++g_const_stamp;
+        return NB200_OK;
+    }
     // The dispatch table of selectCollision (CollisionSelection.h:85-91,141-149,179-202,251), restricted to
     // the stencils on the path.  Anything else throws "Collision model not implemented yet" there.
     int eq = p->equilibrium;
@@ -926,6 +988,8 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     NbConst& h = c->hc;
     const double cs2_scaled = h.cs2 * h.scaling * h.scaling;
     h.tau = p->viscosity / (p->dt * cs2_scaled) + 0.5;     // calculateTauFromNu
+    h.tau_legacy = p->viscosity / (p->dt * cs2_scaled);
+    c->kind = eq == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK;
     h.gamma = p->gamma;
     h.Cv = p->with_g ? 1. / (p->gamma - 1.0) : 0.0;
     h.prandtl = p->prandtl_set ? p->prandtl : (p->prandtl != 0.0 ? p->prandtl : 1.0);
@@ -1003,7 +1067,8 @@ static NbLaunch make_launch(nb200_ctx* c)
     L.stream = c->stream;
     L.A = stream_args(c);
     L.rho = c->rho; L.u = c->u; L.T = c->T; L.sensor = c->sensor; L.flag = c->d_flag;
-    L.eq = c->cp.equilibrium == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK;
+    L.eq = c->kind;
+    L.mrt = c->kind == NB_KIND_MRT_ENTROPIC ? &c->mrt : nullptr;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
     L.fmt = c->fmt;
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;

@@ -17,10 +17,19 @@ struct NbConst {
     double cs2;        // unscaled speed of sound squared
     double scaling;
     double tau;
+    double tau_legacy;   // nu/(dt*cs2_scaled): relaxation parameter of the legacy CollisionModel family
     double gamma, Cv, prandtl;
     int prandtl_set, sutherland_set;
     int D, Q;
 };
 
 
-enum { NB_EQ_BGK = 0, NB_EQ_QUARTIC = 1 };
+// collision kind = template parameter of the kernels: the two equilibria of the collision_advanced BGK
+// scheme, and the legacy entropic models
+enum { NB_EQ_BGK = 0, NB_EQ_QUARTIC = 1, NB_KIND_KBC = 2, NB_KIND_MRT_ENTROPIC = 3 };
+
+// MRTEntropic D3Q19 moment matrix and inverse (host copy, uploaded to the D3Q19 unit)
+struct NbMrtHost {
+    double tm[19][19];
+    double invm[19][19];
+};

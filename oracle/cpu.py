@@ -102,6 +102,35 @@ def collide_bgk_fg(st, f, g, viscosity, dt, equilibrium=1, gamma=1.4, prandtl=No
     return rho, u, T, mss, rc
 
 
+def collide_entropic(st, f, viscosity, dt, scheme, in_init=False, u_init=None, rho_prev=None, n=None):
+    """Legacy entropic collideAll in place.  scheme: "KBC_STANDARD" (D2Q9, D3Q15; KBCStandard.cpp:88-1028) or
+    "MRT_ENTROPIC" (D3Q19; MRTEntropic.cpp:167-305).  tau is the legacy nu/(dt cs2).  Returns (rho, u_scaled, status)."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    tau = viscosity / (dt * st.cs2)
+    rho = np.ones(n) if rho_prev is None else np.ascontiguousarray(rho_prev, dtype=np.float64).copy()
+    u = np.zeros((st.D, n)) if u_init is None else np.ascontiguousarray(u_init, dtype=np.float64)
+    L = lib()
+    if scheme == "KBC_STANDARD" and (st.D, Q) == (2, 9):
+        rc = L.orc_collide_kbc_d2q9(C.c_int64(n), C.c_int64(stride), _d(f), _d(rho), _d(u), C.c_double(st.scaling),
+                                    C.c_double(tau), C.c_int(1 if in_init else 0))
+    elif scheme == "KBC_STANDARD" and (st.D, Q) == (3, 15):
+        rc = L.orc_collide_kbc_d3q15(C.c_int64(n), C.c_int64(stride), _d(f), _d(rho), _d(u), C.c_double(st.scaling),
+                                     C.c_double(st.cs2), C.c_double(tau), C.c_int(1 if in_init else 0))
+    elif scheme == "MRT_ENTROPIC" and (st.D, Q) == (3, 19):
+        rc = L.orc_collide_mrt_entropic_d3q19(C.c_int64(n), C.c_int64(stride), _d(f), _d(rho), _d(u),
+                                              C.c_double(st.scaling), C.c_double(tau), C.c_int(1 if in_init else 0))
+    else:
+        raise ValueError(f"{scheme} is not implemented for D{st.D}Q{Q} in the reference")
+    return rho, u, rc
+
+
+def mrt_entropic_tables():
+    tm, invm = np.zeros((19, 19)), np.zeros((19, 19))
+    lib().orc_mrt_entropic_tables(_d(tm), _d(invm))
+    return tm, invm
+
+
 def equilibrium(st, rho, u_unscaled, T=1.0, kind=0):
     feq = np.zeros(st.Q)
     uu = np.zeros(3)

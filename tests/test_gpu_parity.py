@@ -393,3 +393,79 @@ def test_host_mirror_solver(oracle_lib):
     solver.run(5)
     assert rel_err(solver.getF().to_host(), f) <= 1e-11
     solver.ctx.close()
+
+
+# ---- entropic family ------------------------------------------------------------------------------------
+ENTROPIC = [("D2Q9", "KBC_STANDARD"), ("D3Q15", "KBC_STANDARD"), ("D3Q19", "MRT_ENTROPIC")]
+
+
+@pytest.mark.parametrize("in_init", [False, True])
+@pytest.mark.parametrize("stencil,scheme", ENTROPIC)
+def test_collide_entropic_matches_oracle(stencil, scheme, in_init, oracle_lib):
+    """CollisionModel::collideAll of the legacy entropic models (KBCStandard.cpp:88-1028, MRTEntropic.cpp:167-305)
+    on the BGKStandard_test population, tau_legacy = 0.9, dt = 0.1, scaled stencil."""
+    from natrium_b200 import Context, Stencil, _capi
+    scaling = 2.5
+    st, ost = Stencil(stencil, scaling), oracle_lib.Stencil(stencil, scaling)
+    n, dt = 1000, 0.1
+    nu = 0.9 * dt * st.getSpeedOfSoundSquare()
+    f = synthetic_populations(st.getQ(), n) * st.getWeights()[:, None]
+    u0 = 0.05 * scaling * np.vstack([np.sin(np.arange(n) + d) for d in range(st.getD())])
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+    ctx.set_layout(n, 0, False)
+    ctx.set_dof_order(np.random.default_rng(5).permutation(n))
+    ctx.set_collision(nu, dt, scheme=getattr(_capi, scheme), in_init=in_init)
+    ctx.upload_populations(0, f)
+    if in_init:
+        ctx.upload_velocity(u0)
+    ctx.collide()
+    ctx.synchronize()
+    got = ctx.download_populations(0)
+    rho, u = ctx.download_moments()
+    ref = f.copy()
+    rrho, ru, rc = oracle_lib.collide_entropic(ost, ref, nu, dt, scheme, in_init=in_init, u_init=u0.copy() if in_init else None)
+    assert rc == 0
+    assert rel_err(got, ref) <= TOL_STEP
+    assert rel_err(rho, rrho) <= 1e-14
+    assert np.max(np.abs(u - ru)) <= 1e-13 * max(1.0, np.max(np.abs(ru)))
+    if stencil != "D3Q15":      # KBCStandard D3Q15 mixes unscaled u^2 with the scaled cs2 (:749-750): mass drifts for scaling != 1
+        assert np.max(np.abs(got.sum(axis=0) - f.sum(axis=0))) <= 1e-13 * np.max(f.sum(axis=0))
+    ctx.close()
+
+
+@pytest.mark.parametrize("case,scheme", [("c1_tgv2d_d2q9", "KBC_STANDARD"), ("tgv3d_d3q15", "KBC_STANDARD"),
+                                         ("tgv3d_d3q19_small", "MRT_ENTROPIC")])
+def test_fused_entropic_step_matches_oracle(case, scheme, oracle_lib):
+    """nb200_step with an entropic collision == oracle stream (CSR vmult) followed by the oracle's collideAll, per step."""
+    from natrium_b200 import _capi
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=("dict", 1e-14, True))
+    ctx.set_collision(c["nu"], dt, scheme=getattr(_capi, scheme))
+    f = o["f"].copy()
+    ctx.upload_populations(0, f)
+    rho_prev = None
+    for s in range(5):
+        ctx.step(1)
+        ctx.synchronize()
+        f = oracle_lib.stream(o["blocks"], f)
+        rho_prev, _, rc = oracle_lib.collide_entropic(o["st"], f, c["nu"], dt, scheme, rho_prev=rho_prev)
+        assert rc == 0
+        got = ctx.download_populations(0)
+        assert rel_err(got, f) <= TOL_STEP, (case, s, rel_err(got, f))
+        ctx.upload_populations(0, f)
+    assert rel_err(ctx.download_moments()[0], rho_prev) <= 1e-13
+    ctx.close()
+
+
+def test_entropic_dispatch_errors():
+    """KBC_Standard only for D2Q9/D3Q15, MRT_ENTROPIC only for D3Q19: CollisionException otherwise."""
+    from natrium_b200 import CollisionException, Context, Stencil, _capi
+    for name, scheme in [("D3Q19", _capi.KBC_STANDARD), ("D3Q15", _capi.MRT_ENTROPIC), ("D2Q9", _capi.MRT_ENTROPIC)]:
+        st = Stencil(name, 1.0)
+        ctx = Context(0)
+        ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+        ctx.set_layout(8, 0, False)
+        with pytest.raises(CollisionException):
+            ctx.set_collision(0.1, 0.1, scheme=scheme)
+        ctx.close()

@@ -141,3 +141,88 @@ def test_density_exception_code(oracle_lib):
     st = oracle_lib.Stencil("D2Q9", 1.0)
     f = np.zeros((9, 4))
     assert oracle_lib.collide_bgk(st, f, 0.1, 0.1)[2] == -1      # CollisionException: rho < 1e-10
+
+
+# ---- entropic family (legacy CollisionModel interface) -------------------------------------------------
+def test_kbc_d2q9_mass_equals_bgk(oracle_lib):
+    """KBCStandard_collideAll_test (KBCStandard_test.cpp:36-108): f_i = 0.1 i + 0.1, tau = 0.9, dt = 0.1; the sum of
+    the populations after the entropic collision equals the one after BGK to 1e-5.  (The reference test instantiates
+    KBCCentral; the model on the hot path is KBCStandard, same property.)"""
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    n, dt, tau = 9, 0.1, 0.9
+    nu = tau * dt * st.cs2
+    f = (0.1 * np.arange(9)[:, None] + 0.1) * np.ones((9, n))
+    kbc, bgk = f.copy(), f.copy()
+    _, _, rc = oracle_lib.collide_entropic(st, kbc, nu, dt, "KBC_STANDARD")
+    assert rc == 0
+    oracle_lib.collide_bgk(st, bgk, nu, dt)
+    assert np.max(np.abs(kbc.sum(0) - bgk.sum(0))) <= 1e-5
+    assert np.max(np.abs(kbc.sum(0) - f.sum(0))) <= 1e-14 * f.sum(0).max()
+    assert np.max(np.abs(kbc - bgk)) > 1e-3          # and it is not simply BGK
+
+
+def test_kbc_d3q15_mass_equals_bgk(oracle_lib):
+    """KBCStandard_collideAllD3Q15_test (KBCStandard_test.cpp:111-189), same inputs: synthetic populations, tau 0.9."""
+    st = oracle_lib.Stencil("D3Q15", 1.0)
+    n, dt, tau = 27, 0.1, 0.9
+    nu = tau * dt * st.cs2
+    f = synthetic_populations(15, n)
+    kbc, bgk = f.copy(), f.copy()
+    rho, u, rc = oracle_lib.collide_entropic(st, kbc, nu, dt, "KBC_STANDARD")
+    assert rc == 0
+    oracle_lib.collide_bgk(st, bgk, nu, dt)
+    assert np.max(np.abs(kbc.sum(0) - bgk.sum(0))) <= 1e-5
+    assert np.max(np.abs(rho - f.sum(0))) <= 1e-14 * rho.max()
+    # momentum is a collision invariant too (scaling 1, where the reference's u^2 quirk is harmless)
+    assert np.max(np.abs(st.e.T @ kbc - st.e.T @ f)) <= 1e-13 * f.sum(0).max()
+
+
+def test_kbc_equilibrium_is_fixed_point(oracle_lib):
+    """The product-form entropic equilibrium (KBCStandard.cpp:250-271) is reproduced by the collision (gamma = 2 branch
+    for sum_h < 1e-16, :430-433) and carries the prescribed rho, u."""
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    rho0, u0 = 1.07, np.array([0.04, -0.03])
+    r3 = math.sqrt(3.0)
+    w = st.w
+    feq = np.empty(9)
+    for i in range(9):
+        val = w[i] * rho0
+        for p in range(2):
+            v = u0[p] * r3
+            val *= 2 - math.sqrt(1 + v * v)
+            val *= ((2 * v / r3 + math.sqrt(1 + v * v)) / (1 - v / r3)) ** st.e[i, p]
+        feq[i] = val                                   # KBCStandard::getEquilibriumDistribution, :26-62
+    f = np.repeat(feq[:, None], 4, axis=1).copy()
+    rho, u, rc = oracle_lib.collide_entropic(st, f, 0.01, 0.1, "KBC_STANDARD")
+    assert rc == 0
+    assert np.max(np.abs(f - feq[:, None])) <= 1e-15
+    assert np.max(np.abs(rho - rho0)) <= 1e-15 and np.max(np.abs(u - u0[:, None])) <= 1e-15
+
+
+def test_mrt_entropic_d3q19_invariants_and_tables(oracle_lib):
+    """MRTEntropic::collideAllD3Q19 (MRTEntropic.cpp:167-305): invm is the inverse of tm; density and the momentum
+    moments m3, m5, m7 (as the reference defines them through tm) are untouched; the density guard looks at the density
+    of the previous call."""
+    tm, invm = oracle_lib.mrt_entropic_tables()
+    assert np.max(np.abs(invm @ tm - np.eye(19))) <= 1e-15
+    st = oracle_lib.Stencil("D3Q19", 1.0)
+    f = synthetic_populations(19, 30) * st.w[:, None]
+    g = f.copy()
+    rho, u, rc = oracle_lib.collide_entropic(st, g, 0.02, 0.1, "MRT_ENTROPIC")
+    assert rc == 0
+    for row in (0, 3, 5, 7):
+        assert np.max(np.abs(tm[row] @ g - tm[row] @ f)) <= 1e-14 * np.abs(f).sum(0).max()
+    assert np.max(np.abs(rho - f.sum(0))) <= 1e-15 * rho.max()
+    assert np.max(np.abs(u[0] - (tm[3] @ f) / rho)) <= 1e-15
+    g = f.copy()
+    _, _, rc = oracle_lib.collide_entropic(st, g, 0.02, 0.1, "MRT_ENTROPIC", rho_prev=np.zeros(30))
+    assert rc == 1 and np.array_equal(g, f)
+
+
+def test_entropic_dispatch_matches_reference(oracle_lib):
+    """KBCStandard::collideAll throws for anything but D2Q9 / D3Q15 (KBCStandard.cpp:70-85); MRTEntropic for
+    anything but D2Q9 / D3Q19 (MRTEntropic.cpp:27-36; only D3Q19 is on the path)."""
+    with pytest.raises(ValueError):
+        oracle_lib.collide_entropic(oracle_lib.Stencil("D3Q19", 1.0), np.ones((19, 4)), 0.1, 0.1, "KBC_STANDARD")
+    with pytest.raises(ValueError):
+        oracle_lib.collide_entropic(oracle_lib.Stencil("D3Q15", 1.0), np.ones((15, 4)), 0.1, 0.1, "MRT_ENTROPIC")
