@@ -43,8 +43,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-layers", type=int, default=8, help="z cell layers of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--format", default="dict", choices=["dict", "ell"], help="device format of the streaming matrix")
-    ap.add_argument("--dof-order", default="none", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--format", default="dict", choices=["dict", "dict-unstaged", "ell"], help="device format of the streaming matrix")
+    ap.add_argument("--dof-order", default="cell", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     return ap.parse_args()
 
@@ -223,7 +223,8 @@ def run_ours(args):
     part = harness.SlabPartition(pb, st, dt, rank, world)
     ctx.set_layout(part.n_owned, part.n_ghost, False)
     from natrium_b200 import _capi
-    ctx.set_matrix_format(_capi.FORMAT_DICT if args.format == "dict" else _capi.FORMAT_ELL, args.dedup_tol if args.format == "dict" else 0.0)
+    fmt_code = {"dict": _capi.FORMAT_DICT, "dict-unstaged": _capi.FORMAT_DICT_UNSTAGED, "ell": _capi.FORMAT_ELL}[args.format]
+    ctx.set_matrix_format(fmt_code, args.dedup_tol if args.format != "ell" else 0.0)
     if args.dof_order == "cell":
         ctx.set_dof_order(part.cell_blocked_order())
     t0 = time.perf_counter()

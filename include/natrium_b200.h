@@ -117,11 +117,19 @@ int nb200_finalize_matrix(nb200_ctx *ctx);
  *                      assembly drops entries (L/advection/SemiLagrangian.cpp:483) and bounds the per-row
  *                      perturbation by K*1e-14*max|f| (K = row length <= (p+1)^dim).
  * The matrix the reference assembles on a regular mesh has only O((p+1)^dim) distinct rows per direction up
- * to round-off, which is what the dictionary exploits; on an unstructured mesh it degenerates to ELL. */
-enum nb200_matrix_format { NB200_FORMAT_ELL = 0, NB200_FORMAT_DICT = 1 };
+ * to round-off, which is what the dictionary exploits; on an unstructured mesh it degenerates to ELL.
+ *   NB200_FORMAT_DICT_UNSTAGED  the same dictionary, but every row walks its own column list in global memory.
+ *                      NB200_FORMAT_DICT drives the dictionary CTA by CTA instead: the distinct column lists of
+ *                      128 consecutive rows are copied to shared memory once per pass and shared by the rows
+ *                      ("staged"); it falls back to the unstaged kernels by itself when the rows of a CTA share
+ *                      too little for the staged values of one direction to fit (see nb200_staging_info). */
+enum nb200_matrix_format { NB200_FORMAT_ELL = 0, NB200_FORMAT_DICT = 1, NB200_FORMAT_DICT_UNSTAGED = 2 };
 int nb200_set_matrix_format(nb200_ctx *ctx, int format, double value_dedup_tol);
 /* out = { format, #weight patterns, #column lists, pool bytes, row-descriptor bytes, #row-length classes } */
 int nb200_matrix_format_info(const nb200_ctx *ctx, int64_t out[6], double *value_dedup_tol);
+/* out = { 1 if the staged kernels are in use, staged support values per step (all CTAs, all passes), #passes,
+ *         largest pass (values), pass capacity (values) } */
+int nb200_staging_info(const nb200_ctx *ctx, int64_t out[5]);
 
 /* Ghost plan derived from the column map / IndexSets: for neighbour k, owned local indices
  * send_idx[send_off[k]..send_off[k+1]) go to rank nbr_rank[k]; ghost slots

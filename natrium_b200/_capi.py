@@ -22,7 +22,7 @@ NB200_ERR_NO_DEVICE = -6
 
 BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = 0, 1, 2
 BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = 0, 1
-FORMAT_ELL, FORMAT_DICT = 0, 1
+FORMAT_ELL, FORMAT_DICT, FORMAT_DICT_UNSTAGED = 0, 1, 2
 
 
 class CollisionParams(C.Structure):
@@ -57,6 +57,7 @@ SIGNATURES = {
     "nb200_finalize_matrix": (C.c_int, [_vp]),
     "nb200_set_matrix_format": (C.c_int, [_vp, C.c_int, C.c_double]),
     "nb200_matrix_format_info": (C.c_int, [_vp, _i64p, _dp]),
+    "nb200_staging_info": (C.c_int, [_vp, _i64p]),
     "nb200_set_halo": (C.c_int, [_vp, C.c_int, _i32p, _i64p, _i32p, _i64p]),
     "nb200_upload_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
     "nb200_download_population": (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int64]),
@@ -185,8 +186,11 @@ class Context:
         out = (C.c_int64 * 6)()
         tol = C.c_double()
         self._check(self.lib.nb200_matrix_format_info(self._h, out, C.byref(tol)))
+        st = (C.c_int64 * 5)()
+        self._check(self.lib.nb200_staging_info(self._h, st))
         return dict(format="dict" if out[0] == FORMAT_DICT else "ell", patterns=out[1], lists=out[2], pool_bytes=out[3],
-                    descriptor_bytes=out[4], classes=out[5], value_dedup_tol=tol.value)
+                    descriptor_bytes=out[4], classes=out[5], value_dedup_tol=tol.value, staged=bool(st[0]),
+                    staged_values=st[1], staging_passes=st[2], largest_pass=st[3], pass_capacity=st[4])
 
     def set_halo(self, nbr_rank, send_off, send_idx, recv_off):
         nbr = np.ascontiguousarray(nbr_rank, dtype=np.int32)

@@ -14,7 +14,10 @@
 //   f+g relax (Prandtl fix, Sutherland, sensor)   CollisionSchemes.h:43-118, Aux...h:420-515
 // Unlike the reference, the Hermite tensors are reduced once on the host to their 10+15
 // unique symmetric components and kept in constant memory (the reference recomputes the
-// full tensors per DoF, CollisionOperator.h:68-69).
+// full tensors per DoF, CollisionOperator.h:68-69).  Divisions by run-time constants (cs2, tau,
+// weights, 6 cs2^3, 24 cs2^4) are multiplications by reciprocals rounded once on the host: each
+// differs from the reference's division by at most one ulp of the term, far inside the 1e-12
+// per-step parity bound, and removes ~60 fp64 divisions per DoF from the D3Q19 epilogue.
 #pragma once
 #include <cstdint>
 
@@ -60,9 +63,9 @@ __device__ __forceinline__ void nb_feq_bgk(double rho, const double (&u)[3], dou
 {
     const double cs2 = cP.cs2;
     if (D == 2 && Q == 9) {
-        const double prefactor = 1. / cs2;
+        const double prefactor = cP.inv_cs2;
         const double scalar_product = u[0] * u[0] + u[1] * u[1];
-        const double uSquareTerm = -scalar_product / (2 * cs2);
+        const double uSquareTerm = -scalar_product * cP.half_inv_cs2;
         double weighting = 4. / 9. * rho;
         double mixedTerm;
         feq[0] = weighting * (1 + uSquareTerm);
@@ -82,14 +85,15 @@ __device__ __forceinline__ void nb_feq_bgk(double rho, const double (&u)[3], dou
         feq[8] = weighting * (1 - mixedTerm * (1 - 0.5 * mixedTerm) + uSquareTerm);
         return;
     }
+    const double inv_cs2 = cP.inv_cs2, half_inv_cs2 = cP.half_inv_cs2;
     double uu_term = 0.0;
 #pragma unroll
-    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) / (2.0 * cs2);
+    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) * half_inv_cs2;
 #pragma unroll
     for (int i = 0; i < Q; i++) {
         double ue_term = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) / cs2;
+        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) * inv_cs2;
         feq[i] = cP.w[i] * rho * (1 + ue_term * (1 + 0.5 * (ue_term)) + uu_term);
     }
 }
@@ -99,9 +103,10 @@ template <int D, int Q>
 __device__ __forceinline__ void nb_feq_quartic(double rho, const double (&u)[3], double T, double (&feq)[Q])
 {
     const double cs2 = cP.cs2;
+    const double inv_cs2 = cP.inv_cs2, half_inv_cs2 = cP.half_inv_cs2;
     double uu_term = 0.0;
 #pragma unroll
-    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) / (2.0 * cs2);
+    for (int j = 0; j < D; j++) uu_term += -(u[j] * u[j]) * half_inv_cs2;
     const double T1 = cs2 * (T - 1);
     const double a_xxx = u[0] * u[0] * u[0] + T1 * (u[0] + u[0] + u[0]);
     const double a_xxy = u[0] * u[0] * u[1] + T1 * (u[1]);
@@ -133,30 +138,30 @@ __device__ __forceinline__ void nb_feq_quartic(double rho, const double (&u)[3],
         a_xyyz = u[0] * u[1] * u[1] * u[2] + T1 * (u[0] * u[2]);
         a_xxyz = u[0] * u[0] * u[1] * u[2] + T1 * (u[1] * u[2]);
     }
-    const double c3 = 6. * cs2 * cs2 * cs2;
-    const double c4 = 24. * cs2 * cs2 * cs2 * cs2;
+    const double inv_c3 = cP.inv_c3;     // 1 / (6 cs2^3)
+    const double inv_c4 = cP.inv_c4;     // 1 / (24 cs2^4)
 #pragma unroll
     for (int i = 0; i < Q; i++) {
         const double w = cP.w[i];
         double ue_term = 0.0;
 #pragma unroll
-        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) / cs2;
+        for (int j = 0; j < D; j++) ue_term += (u[j] * cP.e[i][j]) * inv_cs2;
         double fe = w * rho * (1 + ue_term * (1 + 0.5 * (ue_term)) + uu_term);
         // (T-1) trace term: the reference's alp/bet double loop only has diagonal contributions
 #pragma unroll
         for (int a = 0; a < D; a++)
-            fe += rho * w / (2.0 * cs2) * ((T - 1) * cP.e[i][a] * cP.e[i][a] - cs2 * (T - 1));
+            fe += rho * w * half_inv_cs2 * ((T - 1) * cP.e[i][a] * cP.e[i][a] - cs2 * (T - 1));
         const double* H3 = cP.H3[i];
         const double* H4 = cP.H4[i];
-        fe += w * rho / c3 * (a_xxx * H3[0] + 3 * (a_xxy * H3[1] + a_xyy * H3[2]) + a_yyy * H3[3]);
+        fe += w * rho * inv_c3 * (a_xxx * H3[0] + 3 * (a_xxy * H3[1] + a_xyy * H3[2]) + a_yyy * H3[3]);
         if (D == 3)
-            fe += w * rho / c3
+            fe += w * rho * inv_c3
                 * (a_zzz * H3[4] + 3 * (a_xxz * H3[5] + a_xzz * H3[6] + a_yzz * H3[7] + a_yyz * H3[8])
                    + 6.0 * a_xyz * H3[9]);
-        fe += w * rho / c4
+        fe += w * rho * inv_c4
             * (H4[0] * a_xxxx + H4[1] * a_yyyy + 6.0 * H4[4] * a_xxyy + 4.0 * H4[3] * a_xyyy + 4.0 * H4[2] * a_xxxy);
         if (D == 3)
-            fe += w * rho / c4
+            fe += w * rho * inv_c4
                 * (H4[5] * a_zzzz + 4.0 * (H4[6] * a_xzzz + H4[9] * a_yzzz + H4[8] * a_xxxz + H4[11] * a_yyyz)
                    + 6.0 * (H4[7] * a_xxzz + H4[10] * a_yyzz)
                    + 12.0 * (H4[12] * a_xxyz + H4[13] * a_xyyz + H4[14] * a_xyzz));
@@ -178,9 +183,9 @@ __device__ __forceinline__ void nb_collide_bgk(double (&f)[Q], double& rho, doub
     double feq[Q];
     if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, feq);
     else nb_feq_quartic<D, Q>(rho, u, 1.0, feq);
-    const double tau = cP.tau;
+    const double omega = cP.inv_tau;
 #pragma unroll
-    for (int p = 0; p < Q; ++p) f[p] -= 1. / tau * (f[p] - feq[p]);
+    for (int p = 0; p < Q; ++p) f[p] -= omega * (f[p] - feq[p]);
 }
 
 // collideAll body, f + g (relaxWithG).  Writes T and the Knudsen-estimate sensor.
@@ -198,7 +203,7 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
         double sum = 0.0;
 #pragma unroll
         for (int a = 0; a < D; a++) sum += (cP.e[i][a] - u[a]) * (cP.e[i][a] - u[a]);
-        Tacc += sum * f[i] / cs2 + g[i];
+        Tacc += sum * f[i] * cP.inv_cs2 + g[i];
     }
     const double C_v = cP.Cv;
     T = Tacc * 0.5 / (rho * C_v);
@@ -225,7 +230,7 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
     for (int i = 0; i < Q; i++) {
         const double fneq = f[i] - feq[i];
         const double gneq = g[i] - feq[i] * gfac;
-        knudsen += fabs(f[i] - feq[i]) / cP.w[i];
+        knudsen += fabs(f[i] - feq[i]) * cP.inv_w[i];
         if (cP.prandtl_set) {
             double c[3];
 #pragma unroll
@@ -249,7 +254,8 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
     const double visc_omega = 1. / visc_tau;
     const double prandtl_omega = 1. / prandtl_tau;
     const double prandtl_diff = visc_omega - prandtl_omega;
-    const double cs6 = 6.0 * cs2 * cs2 * cs2;
+    const double inv_cs6 = cP.inv_c3;
+    const double inv_T = 1.0 / T;
 #pragma unroll
     for (int i = 0; i < Q; i++) {
         double fStar = 0.0, gStar = 0.0;
@@ -261,9 +267,9 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
 #pragma unroll
                     for (int c = 0; c < D; c++)
                         fStar += cP.w[i] * (Qn[a][b][c] * (cP.e[i][a] * cP.e[i][b] * cP.e[i][c]
-                                                            - 3 * cs2 * cP.e[i][c] * (a == b ? 1.0 : 0.0))) / cs6;
+                                                            - 3 * cs2 * cP.e[i][c] * (a == b ? 1.0 : 0.0))) * inv_cs6;
 #pragma unroll
-            for (int a = 0; a < D; a++) gStar += cP.w[i] * (qg[a] * cP.e[i][a]) / T;
+            for (int a = 0; a < D; a++) gStar += cP.w[i] * (qg[a] * cP.e[i][a]) * inv_T;
         }
         const double fneq = f[i] - feq[i];
         const double gneq = g[i] - feq[i] * gfac;

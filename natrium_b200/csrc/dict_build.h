@@ -15,7 +15,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace nbdict {
@@ -222,6 +224,140 @@ static bool add_block(DirBuild& d, int64_t n_rows, const int64_t* rowptr, const 
         d.row_pat[(size_t)i] = pid;
         d.row_cls[(size_t)i] = (int8_t)ci;
     }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NB_FMT_STAGED tables (see stream_common.cuh).  Input: the finished dictionary (row -> class, list, pattern for
+// every direction, lists still on the host).  For every CTA (cta_rows consecutive rows) and direction the distinct
+// column lists of its rows are appended to stage_col in first-occurrence order; directions are packed into passes
+// of at most `cap` staged values.  Returns false when a single direction of some CTA needs more than `cap` values
+// (the caller then keeps the plain dictionary kernel).
+// ---------------------------------------------------------------------------------------------
+struct StagePassHost {
+    int64_t begin;
+    int32_t count;
+    int16_t a0, a1;
+};
+
+struct StagingBuild {
+    std::vector<int32_t> stage_col;
+    std::vector<StagePassHost> passes;
+    std::vector<int32_t> cta_ptr;          // [n_cta + 1]
+    std::vector<int32_t> sdesc_x;          // [n_dirs][desc_stride]  offset | class << 16
+    int64_t max_pass_count = 0;
+};
+
+static bool build_staging(const std::vector<DirBuild>& dirs, int64_t n_rows, int64_t desc_stride, int cta_rows, int cap,
+                          int empty_cls, StagingBuild& out)
+{
+    const int nd = (int)dirs.size();
+    const int64_t n_cta = (n_rows + cta_rows - 1) / cta_rows;
+    out.cta_ptr.assign((size_t)n_cta + 1, 0);
+    out.sdesc_x.assign((size_t)nd * desc_stride, (int32_t)((uint32_t)empty_cls << 16));
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt == 0 ? 4 : (nt > 32 ? 32 : nt);
+    if (n_cta < 64) nt = 1;
+    // each worker builds the passes / stage_col of a contiguous range of CTAs; stitched together afterwards
+    struct Part { std::vector<int32_t> col; std::vector<StagePassHost> passes; std::vector<int32_t> n_pass; bool ok = true; int64_t max_count = 0; };
+    std::vector<Part> parts(nt);
+    auto work = [&](unsigned t) {
+        Part& P = parts[t];
+        const int64_t b0 = n_cta * t / nt, b1 = n_cta * (t + 1) / nt;
+        // scratch: open-addressing table over (class, list) of one CTA and direction
+        const int TS = 1024;                      // > 2 * cta_rows
+        std::vector<int64_t> key(TS, (int64_t)-1);
+        std::vector<int32_t> val(TS);
+        std::vector<int> used;
+        for (int64_t b = b0; b < b1; b++) {
+            const int64_t r0 = b * cta_rows, r1 = std::min<int64_t>(n_rows, r0 + cta_rows);
+            StagePassHost cur{(int64_t)P.col.size(), 0, 0, 0};
+            int np = 0;
+            for (int a = 0; a < nd; a++) {
+                const DirBuild& d = dirs[(size_t)a];
+                // distinct lists of this (CTA, direction), first-occurrence order
+                for (int u : used) key[(size_t)u] = -1;
+                used.clear();
+                int32_t need = 0;
+                std::vector<std::pair<int, int32_t>> order;   // (class, list) in staging order
+                for (int64_t r = r0; r < r1; r++) {
+                    const int ci = d.row_cls[(size_t)r];
+                    if (ci < 0) continue;
+                    const int64_t kk = ((int64_t)ci << 32) | (uint32_t)d.row_lst[(size_t)r];
+                    size_t h = (size_t)(mix64(0x9e3779b97f4a7c15ull, (uint64_t)kk)) & (TS - 1);
+                    while (key[h] >= 0 && key[h] != kk) h = (h + 1) & (TS - 1);
+                    if (key[h] < 0) {
+                        key[h] = kk;
+                        val[h] = need;
+                        used.push_back((int)h);
+                        order.emplace_back(ci, d.row_lst[(size_t)r]);
+                        need += d.cls[(size_t)ci].K;
+                    }
+                }
+                if (need > cap) { P.ok = false; return; }
+                if (cur.count + need > cap) {       // close the pass before this direction
+                    cur.a1 = (int16_t)a;
+                    P.passes.push_back(cur);
+                    P.max_count = std::max<int64_t>(P.max_count, cur.count);
+                    np++;
+                    cur = StagePassHost{(int64_t)P.col.size(), 0, (int16_t)a, (int16_t)a};
+                }
+                const int32_t base = cur.count;
+                for (auto& cl : order) {
+                    const ClassBuild& C = d.cls[(size_t)cl.first];
+                    const int32_t* L = C.lists.data() + (size_t)cl.second * C.K;
+                    P.col.insert(P.col.end(), L, L + C.K);
+                }
+                int32_t* sx = out.sdesc_x.data() + (size_t)a * desc_stride;
+                for (int64_t r = r0; r < r1; r++) {
+                    const int ci = d.row_cls[(size_t)r];
+                    if (ci < 0) continue;
+                    const int64_t kk = ((int64_t)ci << 32) | (uint32_t)d.row_lst[(size_t)r];
+                    size_t h = (size_t)(mix64(0x9e3779b97f4a7c15ull, (uint64_t)kk)) & (TS - 1);
+                    while (key[h] != kk) h = (h + 1) & (TS - 1);
+                    sx[r] = (int32_t)(((uint32_t)ci << 16) | (uint32_t)(base + val[h]));
+                }
+                cur.count += need;
+            }
+            cur.a1 = (int16_t)nd;
+            P.passes.push_back(cur);
+            P.max_count = std::max<int64_t>(P.max_count, cur.count);
+            np++;
+            P.n_pass.push_back(np);
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (auto& P : parts) if (!P.ok) return false;
+    size_t tot_col = 0, tot_pass = 0;
+    for (auto& P : parts) { tot_col += P.col.size(); tot_pass += P.passes.size(); }
+    if (tot_pass >= (size_t)INT32_MAX) return false;
+    out.stage_col.resize(tot_col);
+    out.passes.resize(tot_pass);
+    size_t oc = 0, op = 0;
+    int64_t b = 0;
+    for (auto& P : parts) {
+        memcpy(out.stage_col.data() + oc, P.col.data(), P.col.size() * sizeof(int32_t));
+        for (size_t i = 0; i < P.passes.size(); i++) {
+            out.passes[op + i] = P.passes[i];
+            out.passes[op + i].begin += (int64_t)oc;
+        }
+        size_t pp = op;
+        for (int npass : P.n_pass) {
+            out.cta_ptr[(size_t)b] = (int32_t)pp;
+            pp += (size_t)npass;
+            b++;
+        }
+        oc += P.col.size();
+        op += P.passes.size();
+        out.max_pass_count = std::max(out.max_pass_count, P.max_count);
+        std::vector<int32_t>().swap(P.col);
+    }
+    out.cta_ptr[(size_t)n_cta] = (int32_t)op;
     return true;
 }
 

@@ -66,7 +66,26 @@ int fused(const NbLaunch& L)
         else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_F(NB_KIND_MRT_ENTROPIC, FMT)); } \
         else return -1;                                                                          \
     } while (0)
-        if (L.fmt == NB_FMT_DICT) NB_LAUNCH_F_KIND(NB_FMT_DICT);
+        if (L.fmt == NB_FMT_STAGED) {
+            const size_t smem_st = (size_t)(Q * NB_CTA_ROWS + NB_STAGE_CAP) * sizeof(double);
+#define NB_LAUNCH_FS(EQ)                                                                                                    \
+    do {                                                                                                                   \
+        static bool attr_set = false;                                                                                      \
+        if (!attr_set) {                                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_f_staged<D, Q, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st); \
+            if (e != cudaSuccess) return (int)e;                                                                           \
+            attr_set = true;                                                                                               \
+        }                                                                                                                  \
+        k_stream_collide_f_staged<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_st, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag); \
+    } while (0)
+            if (L.eq == NB_EQ_BGK) NB_LAUNCH_FS(NB_EQ_BGK);
+            else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_FS(NB_EQ_QUARTIC);
+            else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_FS(NB_KIND_KBC)); }
+            else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_FS(NB_KIND_MRT_ENTROPIC)); }
+            else return -1;
+#undef NB_LAUNCH_FS
+        }
+        else if (L.fmt == NB_FMT_DICT) NB_LAUNCH_F_KIND(NB_FMT_DICT);
         else NB_LAUNCH_F_KIND(NB_FMT_ELL);
 #undef NB_LAUNCH_F_KIND
 #undef NB_LAUNCH_F
@@ -86,7 +105,22 @@ int fused(const NbLaunch& L)
         }                                                                                                                  \
         k_stream_collide_fg<D, Q, EQ, FMT><<<grid, 128, smem_fg, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
     } while (0)
-        if (L.fmt == NB_FMT_DICT) { if (L.eq == NB_EQ_BGK) NB_LAUNCH_FG(NB_EQ_BGK, NB_FMT_DICT); else NB_LAUNCH_FG(NB_EQ_QUARTIC, NB_FMT_DICT); }
+        if (L.fmt == NB_FMT_STAGED) {
+            const size_t smem_st = (size_t)(2 * Q * NB_CTA_ROWS + 2 * NB_STAGE_CAP_FG) * sizeof(double);
+#define NB_LAUNCH_FGS(EQ)                                                                                                   \
+    do {                                                                                                                   \
+        static bool attr_set = false;                                                                                      \
+        if (!attr_set) {                                                                                                   \
+            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_fg_staged<D, Q, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st); \
+            if (e != cudaSuccess) return (int)e;                                                                           \
+            attr_set = true;                                                                                               \
+        }                                                                                                                  \
+        k_stream_collide_fg_staged<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_st, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
+    } while (0)
+            if (L.eq == NB_EQ_BGK) NB_LAUNCH_FGS(NB_EQ_BGK); else NB_LAUNCH_FGS(NB_EQ_QUARTIC);
+#undef NB_LAUNCH_FGS
+        }
+        else if (L.fmt == NB_FMT_DICT) { if (L.eq == NB_EQ_BGK) NB_LAUNCH_FG(NB_EQ_BGK, NB_FMT_DICT); else NB_LAUNCH_FG(NB_EQ_QUARTIC, NB_FMT_DICT); }
         else { if (L.eq == NB_EQ_BGK) NB_LAUNCH_FG(NB_EQ_BGK, NB_FMT_ELL); else NB_LAUNCH_FG(NB_EQ_QUARTIC, NB_FMT_ELL); }
 #undef NB_LAUNCH_FG
 #else

@@ -102,6 +102,151 @@ k_stream_collide_fg(StreamArgs A, const double* __restrict__ xf, const double* _
     for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
 }
 
+// ---------------------------------------------------------------------------------------------
+// NB_FMT_STAGED variants: the CTA stages the support values of a pass in shared memory, then every thread
+// (= one DoF) takes its rows from there.  Dynamic shared memory: [tile(s)][staged values].
+// The descriptors of a pass's directions are parked in the tile slots their results will overwrite.
+// ---------------------------------------------------------------------------------------------
+#ifndef NB_STAGED_OCC_F
+#define NB_STAGED_OCC_F 4
+#endif
+__device__ __forceinline__ int2 nb_empty_desc(const StreamArgs& A, int alpha_m1)
+{
+    // class NB_MAX_CLS-1 of every direction is reserved by the builder as the K = 0 class
+    (void)A; (void)alpha_m1;
+    return make_int2((int)((unsigned)(NB_MAX_CLS - 1) << 16), 0);
+}
+
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(NB_CTA_ROWS, NB_STAGED_OCC_F)
+k_stream_collide_f_staged(StreamArgs A, const double* __restrict__ x, double* __restrict__ y,
+                          double* __restrict__ rho_out, double* __restrict__ u_out, int* __restrict__ flag)
+{
+    extern __shared__ double smem_staged[];
+    double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_staged);   // [Q][128]
+    double* xs = smem_staged + Q * NB_CTA_ROWS;                                              // [NB_STAGE_CAP]
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const bool active = row < A.n_owned;
+    tile[0][tid] = active ? x[row] : 0.0;
+    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    for (int p = p0; p < p1; p++) {
+        const NbStagePass ps = A.stage_pass[p];
+        if (p > p0) __syncthreads();          // the previous pass's rows are done with xs
+        for (int a = ps.a0; a < ps.a1; a++) {
+            const int2 d = active ? __ldcs(A.sdesc + (int64_t)a * A.desc_stride + row) : nb_empty_desc(A, a);
+            reinterpret_cast<int2*>(&tile[a + 1][tid])[0] = d;
+        }
+        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
+        int e = tid;
+        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
+            int32_t c4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
+            double v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) v4[j] = __ldg(x + c4[j]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) xs[e + j * NB_CTA_ROWS] = v4[j];
+        }
+        for (; e < ps.count; e += NB_CTA_ROWS) xs[e] = __ldg(x + __ldcs(sc + e));
+        __syncthreads();
+#pragma unroll 1
+        for (int a = ps.a0; a < ps.a1; a++) {
+            const int2 d = reinterpret_cast<const int2*>(&tile[a + 1][tid])[0];
+            double r, dummy;
+            nb_row_dot_staged<1>(A, a, d, xs, xs, r, dummy);
+            tile[a + 1][tid] = r;
+        }
+    }
+    if (!active) return;
+    double f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
+    double rho, v[3] = {0.0, 0.0, 0.0};
+    if (nb_collide_f<D, Q, EQ>(f, rho, v, false, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) y[(int64_t)q * A.stride + row] = f[q];
+    rho_out[row] = rho;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = v[j];
+}
+
+// f + g: one pass over the matrix for both distributions; [tile f][tile g][xs f][xs g]
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(NB_CTA_ROWS, NB_FUSED_OCC_FG)
+k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const double* __restrict__ xg,
+                           double* __restrict__ yf, double* __restrict__ yg, double* __restrict__ rho_out,
+                           double* __restrict__ u_out, double* __restrict__ T_out, double* __restrict__ s_out,
+                           int* __restrict__ flag)
+{
+    extern __shared__ double smem_staged[];
+    double (*tf)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_staged);
+    double (*tg)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_staged + Q * NB_CTA_ROWS);
+    double* xsf = smem_staged + 2 * Q * NB_CTA_ROWS;
+    double* xsg = xsf + NB_STAGE_CAP_FG;
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const bool active = row < A.n_owned;
+    tf[0][tid] = active ? xf[row] : 0.0;
+    tg[0][tid] = active ? xg[row] : 0.0;
+    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    for (int p = p0; p < p1; p++) {
+        const NbStagePass ps = A.stage_pass[p];
+        if (p > p0) __syncthreads();
+        for (int a = ps.a0; a < ps.a1; a++) {
+            const int2 d = active ? __ldcs(A.sdesc + (int64_t)a * A.desc_stride + row) : nb_empty_desc(A, a);
+            reinterpret_cast<int2*>(&tf[a + 1][tid])[0] = d;
+        }
+        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
+        int e = tid;
+        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
+            int32_t c4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
+            double v4[4], w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v4[j] = __ldg(xf + c4[j]); w4[j] = __ldg(xg + c4[j]); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { xsf[e + j * NB_CTA_ROWS] = v4[j]; xsg[e + j * NB_CTA_ROWS] = w4[j]; }
+        }
+        for (; e < ps.count; e += NB_CTA_ROWS) {
+            const int32_t cc = __ldcs(sc + e);
+            xsf[e] = __ldg(xf + cc);
+            xsg[e] = __ldg(xg + cc);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int a = ps.a0; a < ps.a1; a++) {
+            const int2 d = reinterpret_cast<const int2*>(&tf[a + 1][tid])[0];
+            double r0, r1;
+            nb_row_dot_staged<2>(A, a, d, xsf, xsg, r0, r1);
+            tf[a + 1][tid] = r0;
+            tg[a + 1][tid] = r1;
+        }
+    }
+    if (!active) return;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        f[q] = tf[q][tid];
+        g[q] = tg[q][tid];
+    }
+    double rho, u[3], T, sensor;
+    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, nullptr);
+    if (rho < 1e-10) *flag = 1;
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        yf[(int64_t)q * A.stride + row] = f[q];
+        yg[(int64_t)q * A.stride + row] = g[q];
+    }
+    rho_out[row] = rho;
+    T_out[row] = T;
+    s_out[row] = sensor;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
+}
+
 // Stand-alone collide (in place), f only.
 template <int D, int Q, int EQ>
 __global__ void __launch_bounds__(128)

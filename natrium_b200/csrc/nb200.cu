@@ -120,6 +120,14 @@ struct nb200_ctx {
     int64_t desc_stride = 0;
     std::vector<void*> pools;                // device pools owned by the format
     int64_t dict_patterns = 0, dict_lists = 0, dict_pool_bytes = 0, dict_classes = 0;
+    // staged driving tables of the dictionary format (NB_FMT_STAGED kernels)
+    bool staged = false, want_staged = true;
+    int2* d_sdesc = nullptr;
+    int32_t* d_stage_col = nullptr;
+    NbStagePass* d_stage_pass = nullptr;
+    int32_t* d_stage_cta = nullptr;
+    int64_t stage_values = 0, stage_passes = 0, stage_max_pass = 0;
+    int stage_cap = 0;
     // collision
     const NbStencilOps* ops = nullptr;
     uint64_t const_version = 1;
@@ -267,6 +275,61 @@ k_stream(StreamArgs A, const double* __restrict__ x0, const double* __restrict__
     if (NRHS == 2) y1[(int64_t)q * A.stride + row] = r1;
 }
 
+// Stream only, staged dictionary format: one CTA = NB_CTA_ROWS rows, all directions, pass by pass.
+template <int NRHS>
+__global__ void __launch_bounds__(NB_CTA_ROWS)
+k_stream_staged(StreamArgs A, int Q, const double* __restrict__ x0, const double* __restrict__ x1,
+                double* __restrict__ y0, double* __restrict__ y1)
+{
+    extern __shared__ double xs_all[];
+    const int cap = NRHS == 2 ? NB_STAGE_CAP_FG : NB_STAGE_CAP;
+    double* xs0 = xs_all;
+    double* xs1 = xs_all + (NRHS == 2 ? cap : 0);
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const bool active = row < A.n_owned;
+    if (active) {
+        y0[row] = x0[row];
+        if (NRHS == 2) y1[row] = x1[row];
+    }
+    const int2 empty = make_int2((int)((unsigned)(NB_MAX_CLS - 1) << 16), 0);
+    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    for (int p = p0; p < p1; p++) {
+        const NbStagePass ps = A.stage_pass[p];
+        if (p > p0) __syncthreads();
+        int2 dn = active ? __ldcs(A.sdesc + (int64_t)ps.a0 * A.desc_stride + row) : empty;
+        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
+        int e = tid;
+        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
+            int32_t c4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
+            double v4[4], w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v4[j] = __ldg(x0 + c4[j]); if (NRHS == 2) w4[j] = __ldg(x1 + c4[j]); }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { xs0[e + j * NB_CTA_ROWS] = v4[j]; if (NRHS == 2) xs1[e + j * NB_CTA_ROWS] = w4[j]; }
+        }
+        for (; e < ps.count; e += NB_CTA_ROWS) {
+            const int32_t cc = __ldcs(sc + e);
+            xs0[e] = __ldg(x0 + cc);
+            if (NRHS == 2) xs1[e] = __ldg(x1 + cc);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int a = ps.a0; a < ps.a1; a++) {
+            const int2 d = dn;
+            if (a + 1 < ps.a1 && active) dn = __ldcs(A.sdesc + (int64_t)(a + 1) * A.desc_stride + row);
+            double r0, r1;
+            nb_row_dot_staged<NRHS>(A, a, d, xs0, xs1, r0, r1);
+            if (active) {
+                y0[(int64_t)(a + 1) * A.stride + row] = r0;
+                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + row] = r1;
+            }
+        }
+    }
+}
+
 // internal <-> user DoF order.  rows: number of arrays (populations / velocity components).
 // to_internal: dst[r*dst_stride + k] = src[r*src_stride + order[k]];  to_user: dst[r*dst_stride + i] = src[r*src_stride + perm[i]]
 __global__ void k_permute_rows(int64_t n, int rows, const int32_t* __restrict__ map, const double* __restrict__ src,
@@ -369,6 +432,10 @@ static void free_matrix(nb200_ctx* c)
     c->d_desc = nullptr; c->d_cls = nullptr;
     for (void* p : c->pools) cudaFree(p);
     c->pools.clear();
+    cudaFree(c->d_sdesc); cudaFree(c->d_stage_col); cudaFree(c->d_stage_pass); cudaFree(c->d_stage_cta);
+    c->d_sdesc = nullptr; c->d_stage_col = nullptr; c->d_stage_pass = nullptr; c->d_stage_cta = nullptr;
+    c->staged = false;
+    c->stage_values = c->stage_passes = c->stage_max_pass = 0;
     c->matrix_ready = false;
 }
 
@@ -420,6 +487,10 @@ extern "C" int nb200_set_stencil(nb200_ctx* c, int D, int Q, const double* e_sca
     memset(&h, 0, sizeof(h));
     h.D = D; h.Q = Q; h.scaling = scaling;
     h.cs2 = cs2_scaled / (scaling * scaling);
+    h.inv_cs2 = 1.0 / h.cs2;
+    h.half_inv_cs2 = 1.0 / (2.0 * h.cs2);
+    h.inv_c3 = 1.0 / (6. * h.cs2 * h.cs2 * h.cs2);
+    h.inv_c4 = 1.0 / (24. * h.cs2 * h.cs2 * h.cs2 * h.cs2);
     for (int i = 0; i < Q; i++) {
         for (int j = 0; j < D; j++) { h.es[i][j] = e_scaled[i * D + j]; h.e[i][j] = e_scaled[i * D + j] / scaling; }
         h.w[i] = w[i];
@@ -660,6 +731,15 @@ static int finalize_dict(nb200_ctx* c)
     c->pools.push_back(dummy);
     c->dict_patterns = c->dict_lists = c->dict_pool_bytes = c->dict_classes = 0;
     c->nnz_total = 0;
+    // staged driving tables (needs the host lists, so before the pools are released below)
+    nbdict::StagingBuild SB;
+    bool staged_ok = false;
+    {
+        static const char* env = getenv("NB200_STAGED");     // experiments only: NB200_STAGED=0 keeps the plain dictionary kernels
+        const bool want = c->want_staged && !(env && env[0] == '0') && n > 0;
+        c->stage_cap = c->with_g ? NB_STAGE_CAP_FG : NB_STAGE_CAP;
+        if (want) staged_ok = nbdict::build_staging(c->dirs, n, c->desc_stride, NB_CTA_ROWS, c->stage_cap, NB_MAX_CLS - 1, SB);
+    }
     for (int a = 0; a < nb; a++) {
         nbdict::DirBuild& d = c->dirs[(size_t)a];
         c->nnz_total += d.nnz;
@@ -672,6 +752,7 @@ static int finalize_dict(nb200_ctx* c)
             NbDirClass& H = hcls[(size_t)a * NB_MAX_CLS + ci];
             if (ci == empty_cls) {
                 H.W = (const double*)dummy; H.L = (const int32_t*)dummy; H.K = 0; H.P = 32; H.NL = 32; H.streamed = 0;
+                hcls[(size_t)a * NB_MAX_CLS + NB_MAX_CLS - 1] = H;     // the staged kernels' fixed K = 0 class
                 continue;
             }
             nbdict::ClassBuild& B = d.cls[(size_t)ci];
@@ -717,6 +798,25 @@ static int finalize_dict(nb200_ctx* c)
     CUDA_TRY(c, cudaMalloc(&c->d_cls, hcls.size() * sizeof(NbDirClass)));
     CUDA_TRY(c, cudaMemcpy(c->d_cls, hcls.data(), hcls.size() * sizeof(NbDirClass), cudaMemcpyHostToDevice));
     c->ell_entries = c->nnz_total;
+    if (staged_ok) {
+        // staged descriptors: x = offset | class << 16 (from the builder), y = pattern id (as in the plain descriptor)
+        std::vector<int2> hs(hdesc.size());
+        for (size_t i = 0; i < hs.size(); i++) hs[i] = make_int2(SB.sdesc_x[i], (int)((unsigned)hdesc[i].y & NB_PAT_MASK));
+        CUDA_TRY(c, cudaMalloc(&c->d_sdesc, hs.size() * sizeof(int2)));
+        CUDA_TRY(c, cudaMemcpy(c->d_sdesc, hs.data(), hs.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMalloc(&c->d_stage_col, std::max<size_t>(4, SB.stage_col.size() * sizeof(int32_t))));
+        if (!SB.stage_col.empty())
+            CUDA_TRY(c, cudaMemcpy(c->d_stage_col, SB.stage_col.data(), SB.stage_col.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        static_assert(sizeof(NbStagePass) == sizeof(nbdict::StagePassHost), "pass record layout");
+        CUDA_TRY(c, cudaMalloc(&c->d_stage_pass, SB.passes.size() * sizeof(NbStagePass)));
+        CUDA_TRY(c, cudaMemcpy(c->d_stage_pass, SB.passes.data(), SB.passes.size() * sizeof(NbStagePass), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMalloc(&c->d_stage_cta, SB.cta_ptr.size() * sizeof(int32_t)));
+        CUDA_TRY(c, cudaMemcpy(c->d_stage_cta, SB.cta_ptr.data(), SB.cta_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->staged = true;
+        c->stage_values = (int64_t)SB.stage_col.size();
+        c->stage_passes = (int64_t)SB.passes.size();
+        c->stage_max_pass = SB.max_pass_count;
+    }
     free_blocks(c);
     c->matrix_ready = true;
     return NB200_OK;
@@ -956,6 +1056,7 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
         NbConst& h = c->hc;
         const double cs2s = h.cs2 * h.scaling * h.scaling;
         h.tau = p->viscosity / (p->dt * cs2s) + 0.5;
+        h.inv_tau = 1.0 / h.tau;
         h.tau_legacy = p->viscosity / (p->dt * cs2s);     // CollisionModel::calculateRelaxationParameter
         c->kind = kbc ? NB_KIND_KBC : NB_KIND_MRT_ENTROPIC;
         if (!kbc) fill_mrt_entropic_tables(c->mrt);
@@ -988,6 +1089,7 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     NbConst& h = c->hc;
     const double cs2_scaled = h.cs2 * h.scaling * h.scaling;
     h.tau = p->viscosity / (p->dt * cs2_scaled) + 0.5;     // calculateTauFromNu
+    h.inv_tau = 1.0 / h.tau;
     h.tau_legacy = p->viscosity / (p->dt * cs2_scaled);
     c->kind = eq == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK;
     h.gamma = p->gamma;
@@ -1049,6 +1151,7 @@ static StreamArgs stream_args(nb200_ctx* c)
     StreamArgs A;
     A.ell_val = c->ell_val; A.ell_idx = c->ell_idx; A.slice_off = c->d_slice_off;
     A.desc = c->d_desc; A.cls = c->d_cls; A.desc_stride = c->desc_stride;
+    A.sdesc = c->d_sdesc; A.stage_col = c->d_stage_col; A.stage_pass = c->d_stage_pass; A.stage_cta = c->d_stage_cta;
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
     return A;
 }
@@ -1070,7 +1173,7 @@ static NbLaunch make_launch(nb200_ctx* c)
     L.eq = c->kind;
     L.mrt = c->kind == NB_KIND_MRT_ENTROPIC ? &c->mrt : nullptr;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
-    L.fmt = c->fmt;
+    L.fmt = (c->fmt == NB_FMT_DICT && c->staged) ? NB_FMT_STAGED : c->fmt;
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;
     L.partial = c->d_partial; L.n_partial_blocks = c->n_partial_blocks;
     L.out = c->d_partial ? c->d_partial + (size_t)c->n_partial_blocks * 5 : nullptr;
@@ -1113,6 +1216,27 @@ static int launch_stream(nb200_ctx* c, bool do_f, bool do_g)
 {
     const StreamArgs A = stream_args(c);
     dim3 grid(grid_for(c->n_slices * 32, 128), (unsigned)c->Q);
+    // the staged tables are sized for two distributions when the layout has g (NB_STAGE_CAP_FG), which a
+    // single-distribution pass can use as well
+    if (c->fmt == NB_FMT_DICT && c->staged) {
+        const unsigned g1 = grid_for(c->n_owned, NB_CTA_ROWS);
+        if (do_f && do_g) {
+            static bool attr2 = false;
+            const size_t sm = (size_t)2 * NB_STAGE_CAP_FG * sizeof(double);
+            if (!attr2) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr2 = true; }
+            k_stream_staged<2><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
+            c->cur[0] ^= 1; c->cur[1] ^= 1;
+        } else {
+            const int w = do_f ? 0 : 1;
+            static bool attr1 = false;
+            const size_t sm = (size_t)NB_STAGE_CAP * sizeof(double);
+            if (!attr1) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr1 = true; }
+            k_stream_staged<1><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
+            c->cur[w] ^= 1;
+        }
+        c->launches++;
+        return NB200_OK;
+    }
     if (do_f && do_g) {
         if (c->fmt == NB_FMT_DICT) k_stream<NB_FMT_DICT, 2><<<grid, 128, 0, c->stream>>>(A, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
         else k_stream<NB_FMT_ELL, 2><<<grid, 128, 0, c->stream>>>(A, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
@@ -1277,7 +1401,7 @@ extern "C" int nb200_matrix_info(const nb200_ctx* c, int64_t* nnz, int64_t* devi
     if (nnz) *nnz = c->nnz_total;
     if (padded_entries) *padded_entries = c->ell_entries;
     if (device_bytes) {
-        if (c->fmt == NB_FMT_DICT) *device_bytes = c->dict_pool_bytes + (int64_t)(c->Q - 1) * c->desc_stride * 8;
+        if (c->fmt == NB_FMT_DICT) *device_bytes = c->dict_pool_bytes + (int64_t)(c->Q - 1) * c->desc_stride * 8 * (c->staged ? 2 : 1) + c->stage_values * 4 + c->stage_passes * 16;
         else *device_bytes = c->ell_entries * 12 + (int64_t)(c->Q - 1) * (c->n_slices + 1) * 8;
     }
     return NB200_OK;
@@ -1286,10 +1410,11 @@ extern "C" int nb200_matrix_info(const nb200_ctx* c, int64_t* nnz, int64_t* devi
 extern "C" int nb200_set_matrix_format(nb200_ctx* c, int format, double value_dedup_tol)
 {
     if (!c) return NB200_ERR_ARG;
-    if (format != NB200_FORMAT_ELL && format != NB200_FORMAT_DICT) return fail(c, NB200_ERR_ARG, "set_matrix_format: unknown format %d", format);
+    if (format != NB200_FORMAT_ELL && format != NB200_FORMAT_DICT && format != NB200_FORMAT_DICT_UNSTAGED) return fail(c, NB200_ERR_ARG, "set_matrix_format: unknown format %d", format);
     if (!(value_dedup_tol >= 0.0) || value_dedup_tol > 1e-10) return fail(c, NB200_ERR_ARG, "set_matrix_format: tolerance must be in [0, 1e-10]");
     if (!c->blocks.empty()) return fail(c, NB200_ERR_ARG, "set_matrix_format: call before the first upload_block_csr");
-    c->fmt = format == NB200_FORMAT_DICT ? NB_FMT_DICT : NB_FMT_ELL;
+    c->fmt = format == NB200_FORMAT_ELL ? NB_FMT_ELL : NB_FMT_DICT;
+    c->want_staged = format == NB200_FORMAT_DICT;
     c->dedup_tol = value_dedup_tol;
     return NB200_OK;
 }
@@ -1304,6 +1429,17 @@ extern "C" int nb200_matrix_format_info(const nb200_ctx* c, int64_t out[6], doub
     out[4] = c->fmt == NB_FMT_DICT ? (int64_t)(c->Q - 1) * c->desc_stride * 8 : (int64_t)(c->Q - 1) * (c->n_slices + 1) * 8;
     out[5] = c->fmt == NB_FMT_DICT ? c->dict_classes : 0;
     if (value_dedup_tol) *value_dedup_tol = c->dedup_tol;
+    return NB200_OK;
+}
+
+extern "C" int nb200_staging_info(const nb200_ctx* c, int64_t out[5])
+{
+    if (!c || !c->matrix_ready || !out) return NB200_ERR_ARG;
+    out[0] = c->staged ? 1 : 0;
+    out[1] = c->stage_values;
+    out[2] = c->stage_passes;
+    out[3] = c->stage_max_pass;
+    out[4] = c->stage_cap;
     return NB200_OK;
 }
 

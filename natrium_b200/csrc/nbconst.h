@@ -15,6 +15,9 @@ struct NbConst {
     double H3[NB_MAXQ][10];
     double H4[NB_MAXQ][15];
     double cs2;        // unscaled speed of sound squared
+    double inv_cs2, half_inv_cs2;   // 1/cs2, 1/(2 cs2)
+    double inv_c3, inv_c4;          // 1/(6 cs2^3), 1/(24 cs2^4)
+    double inv_tau;                 // 1/tau
     double scaling;
     double tau;
     double tau_legacy;   // nu/(dt*cs2_scaled): relaxation parameter of the legacy CollisionModel family

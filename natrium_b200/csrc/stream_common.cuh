@@ -12,7 +12,19 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1 };
+//   NB_FMT_STAGED  the dictionary format driven CTA by CTA: for every block of NB_CTA_ROWS rows the builder
+//                lists, pass by pass, the distinct column lists those rows read (stage_col: one flat population
+//                index per staged support value).  The CTA copies them into shared memory with independent,
+//                coalesced loads, then every row takes its K support values from there (xs[off + k]) and its
+//                weights from the pattern pool.  A pass covers a range of directions whose staged values fit
+//                NB_STAGE_CAP doubles.  Rows that read the same source cell share the staged copy, so the
+//                gather traffic per CTA drops from rows x K to lists x K loads and the dependent
+//                descriptor -> list -> value chain of NB_FMT_DICT disappears from the inner loop.
+enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
+
+#define NB_CTA_ROWS 128
+#define NB_STAGE_CAP 4096          // doubles per pass and distribution (f only)
+#define NB_STAGE_CAP_FG 2048       // doubles per pass and distribution when f and g are staged together
 
 #define NB_CLS_BITS 6
 #define NB_MAX_CLS (1 << NB_CLS_BITS)           // row-length classes per direction
@@ -28,6 +40,13 @@ struct NbDirClass {
     int64_t P, NL;                    // P: padded pattern count (k-major pitch); NL: list pitch = K rounded up to 4
 };
 
+// one staging pass of one CTA: directions [a0, a1), `count` staged values starting at stage_col[begin]
+struct NbStagePass {
+    int64_t begin;
+    int32_t count;
+    int16_t a0, a1;
+};
+
 struct StreamArgs {
     // NB_FMT_ELL
     const double* __restrict__ ell_val;
@@ -37,6 +56,11 @@ struct StreamArgs {
     const int2* __restrict__ desc;           // [(Q-1)][desc_stride]: x = list id, y = class << 26 | pattern id
     const NbDirClass* __restrict__ cls;      // [(Q-1)][NB_MAX_CLS]
     int64_t desc_stride;
+    // NB_FMT_STAGED (shares cls / desc_stride with NB_FMT_DICT)
+    const int2* __restrict__ sdesc;          // [(Q-1)][desc_stride]: x = offset into the pass's staged values | class << 16, y = pattern id
+    const int32_t* __restrict__ stage_col;   // flat population index of every staged support value, pass after pass
+    const struct NbStagePass* __restrict__ stage_pass;
+    const int32_t* __restrict__ stage_cta;   // [n_cta + 1] first pass of every CTA
     int64_t n_slices;
     int64_t n_owned;
     int64_t stride;
@@ -147,6 +171,49 @@ __device__ __forceinline__ void nb_row_dot_dict(const StreamArgs& A, int alpha_m
     double a0 = 0.0, a1 = 0.0;
     if (C->streamed) nb_dict_accumulate<NRHS, true>(W, L, K, P, x0, x1, a0, a1);
     else nb_dict_accumulate<NRHS, false>(W, L, K, P, x0, x1, a0, a1);
+    y0 = a0;
+    y1 = a1;
+}
+
+// Staged row product: support values from shared memory (xs0/xs1 + off), weights from the k-major pattern pool.
+// Same summation order as the other formats (k = 0..K-1 as stored).
+template <int NRHS, bool STREAMED>
+__device__ __forceinline__ void nb_staged_accumulate(const double* __restrict__ W, int K, int64_t P,
+                                                     const double* __restrict__ s0, const double* __restrict__ s1,
+                                                     double& a0, double& a1)
+{
+    int k = 0;
+    for (; k + 8 <= K; k += 8) {
+        double vv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            a0 += vv[j] * s0[k + j];
+            if (NRHS == 2) a1 += vv[j] * s1[k + j];
+        }
+    }
+    for (; k < K; k++) {
+        const double vv = STREAMED ? __ldcs(W + (int64_t)k * P) : __ldg(W + (int64_t)k * P);
+        a0 += vv * s0[k];
+        if (NRHS == 2) a1 += vv * s1[k];
+    }
+}
+
+template <int NRHS>
+__device__ __forceinline__ void nb_row_dot_staged(const StreamArgs& A, int alpha_m1, int2 d, const double* __restrict__ xs0,
+                                                  const double* __restrict__ xs1, double& y0, double& y1)
+{
+    const unsigned dx = (unsigned)d.x;
+    const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + (dx >> 16);
+    const int K = C->K;
+    const int64_t P = C->P;
+    const double* __restrict__ W = C->W + (unsigned)d.y;
+    const double* __restrict__ s0 = xs0 + (dx & 0xffffu);
+    const double* __restrict__ s1 = xs1 + (dx & 0xffffu);
+    double a0 = 0.0, a1 = 0.0;
+    if (C->streamed) nb_staged_accumulate<NRHS, true>(W, K, P, s0, s1, a0, a1);
+    else nb_staged_accumulate<NRHS, false>(W, K, P, s0, s1, a0, a1);
     y0 = a0;
     y1 = a1;
 }

@@ -19,8 +19,14 @@ TOL_CONS = 1e-13      # conserved sums vs oracle
 # device formats of the streaming matrix: library default (dictionary, value tolerance 1e-14), bit-faithful
 # dictionary (tolerance 0) and the generic warp-sliced ELL
 # (format, value tolerance, cell-blocked internal DoF order)
-FORMATS = [None, ("dict", 1e-14, True), ("dict", 0.0, False), ("ell", 0.0, False), ("ell", 0.0, True)]
-FORMAT_IDS = ["dict-default", "dict-cellorder", "dict-exact", "ell", "ell-cellorder"]
+FORMATS = [None, ("dict", 1e-14, True), ("dict", 0.0, False), ("ell", 0.0, False), ("ell", 0.0, True),
+           ("dict-unstaged", 1e-14, False), ("dict-unstaged", 1e-14, True)]
+FORMAT_IDS = ["dict-default", "dict-cellorder", "dict-exact", "ell", "ell-cellorder", "dict-unstaged", "dict-unstaged-cellorder"]
+
+
+def _fmt_code(name):
+    from natrium_b200 import _capi
+    return {"dict": _capi.FORMAT_DICT, "ell": _capi.FORMAT_ELL, "dict-unstaged": _capi.FORMAT_DICT_UNSTAGED}[name]
 
 
 def make_ctx(case, with_matrix=True, fmt=None):
@@ -31,7 +37,7 @@ def make_ctx(case, with_matrix=True, fmt=None):
     part = harness.SlabPartition(pb, st, dt)
     ctx.set_layout(part.n_owned, part.n_ghost, bool(c.get("with_g")))
     if fmt is not None:
-        ctx.set_matrix_format(_capi.FORMAT_DICT if fmt[0] == "dict" else _capi.FORMAT_ELL, fmt[1])
+        ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
         if fmt[2]:
             ctx.set_dof_order(part.cell_blocked_order())
     if with_matrix:
@@ -67,6 +73,31 @@ def test_stream_matches_oracle(case, fmt, oracle_lib):
         ctx.upload_populations(1, o["g"])
         ctx.stream(1)
         assert rel_err(ctx.download_populations(1), oracle_lib.stream(o["blocks"], o["g"])) <= TOL_STEP
+    ctx.close()
+
+
+def test_staged_kernels_selected():
+    """The default dictionary format drives the staged kernels on the meshes of the path and falls back to the
+    per-row kernels when told to (FORMAT_DICT_UNSTAGED) or when rows share too little (random sparse block)."""
+    import scipy.sparse as sp
+    from natrium_b200 import Context, Stencil
+    for case in ["c1_tgv2d_d2q9", "tgv3d_d3q19_small", "tgv3d_d3q45"]:
+        for fmt, want in [(None, True), (("dict", 1e-14, True), True), (("dict-unstaged", 1e-14, True), False)]:
+            ctx = make_ctx(case, fmt=fmt)[0]
+            info = ctx.matrix_format_info()
+            assert info["staged"] == want, (case, fmt, info)
+            if want:
+                assert 0 < info["largest_pass"] <= info["pass_capacity"]
+            ctx.close()
+    st = Stencil("D2Q9", 1.0)
+    n = 1000
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+    ctx.set_layout(n, 0, False)
+    m = sp.random(n, n, density=0.15, random_state=np.random.default_rng(1), format="csr", dtype=np.float64)
+    ctx.upload_block_csr(0, 0, m.indptr, m.indices, m.data)
+    ctx.finalize_matrix()
+    assert not ctx.matrix_format_info()["staged"]
     ctx.close()
 
 
@@ -342,7 +373,7 @@ def test_ragged_and_offdiagonal_blocks(fmt, oracle_lib):
     ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
     ctx.set_layout(n, 0, False)
     if fmt is not None:
-        ctx.set_matrix_format(_capi.FORMAT_DICT if fmt[0] == "dict" else _capi.FORMAT_ELL, fmt[1])
+        ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
         if fmt[2]:
             ctx.set_dof_order(rng.permutation(n))
     for (bi, bj), m in blocks.items():

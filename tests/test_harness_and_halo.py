@@ -13,6 +13,8 @@ from natrium_b200 import harness
 from natrium_b200.stencils import Stencil
 from oracle import assembly, stencils as ost
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 REF = "/root/reference/src/library/natrium/stencils"
 
 
@@ -137,3 +139,17 @@ def test_equilibrium_init_against_oracle():
         f1, g1 = harness.quartic_equilibrium_distributions(st, rho, u, T, 1.4)
         f2, g2 = fields.quartic_equilibrium_init(e, w, cs2, 1.3, rho, u, T, 1.4)
         assert np.max(np.abs(f1 - f2) / np.abs(f2)) <= 1e-11 and np.max(np.abs(g1 - g2) / np.abs(g2)) <= 1e-11
+
+
+def test_staging_tables_replay(tmp_path):
+    """Host-side builder of the staged driving tables (natrium_b200/csrc/dict_build.h): a CPU replay of the kernel's
+    access pattern over the tables equals the CSR product, passes respect their capacity and cover every
+    direction once, and an unshareable matrix is reported infeasible (the library then keeps the plain kernels)."""
+    import subprocess
+    exe = str(tmp_path / "staging_check")
+    src = os.path.join(ROOT, "tests", "cpp", "staging_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, src], check=True)
+    for args, expect in [(("1000", "4", "16", "9", "4096", "1"), "OK"), (("5000", "18", "64", "25", "600", "3"), "OK"),
+                         (("300000", "6", "32", "5", "256", "4"), "OK"), (("777", "3", "1", "40", "4096", "5"), "INFEASIBLE")]:
+        out = subprocess.run([exe, *args], check=True, capture_output=True, text=True).stdout
+        assert out.startswith(expect), out
