@@ -133,23 +133,13 @@ k_stream_collide_f_staged(StreamArgs A, const double* __restrict__ x, double* __
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();          // the previous pass's rows are done with xs
-        for (int a = ps.a0; a < ps.a1; a++) {
-            const int2 d = active ? __ldcs(A.sdesc + (int64_t)a * A.desc_stride + row) : nb_empty_desc(A, a);
-            reinterpret_cast<int2*>(&tile[a + 1][tid])[0] = d;
+        if (active) {
+            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.desc_stride + row;
+            for (int a = ps.a0; a < ps.a1; a++, dp += A.desc_stride) nb_cp_async8(&tile[a + 1][tid], reinterpret_cast<const double*>(dp));
+        } else {
+            for (int a = ps.a0; a < ps.a1; a++) reinterpret_cast<int2*>(&tile[a + 1][tid])[0] = nb_empty_desc(A, a);
         }
-        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
-        int e = tid;
-        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
-            int32_t c4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
-            double v4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) v4[j] = __ldg(x + c4[j]);
-#pragma unroll
-            for (int j = 0; j < 4; j++) xs[e + j * NB_CTA_ROWS] = v4[j];
-        }
-        for (; e < ps.count; e += NB_CTA_ROWS) xs[e] = __ldg(x + __ldcs(sc + e));
+        nb_stage_pass<1>(A.stage_col + ps.begin, ps.count, tid, x, x, xs, xs);
         __syncthreads();
 #pragma unroll 1
         for (int a = ps.a0; a < ps.a1; a++) {
@@ -194,27 +184,13 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();
-        for (int a = ps.a0; a < ps.a1; a++) {
-            const int2 d = active ? __ldcs(A.sdesc + (int64_t)a * A.desc_stride + row) : nb_empty_desc(A, a);
-            reinterpret_cast<int2*>(&tf[a + 1][tid])[0] = d;
+        if (active) {
+            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.desc_stride + row;
+            for (int a = ps.a0; a < ps.a1; a++, dp += A.desc_stride) nb_cp_async8(&tf[a + 1][tid], reinterpret_cast<const double*>(dp));
+        } else {
+            for (int a = ps.a0; a < ps.a1; a++) reinterpret_cast<int2*>(&tf[a + 1][tid])[0] = nb_empty_desc(A, a);
         }
-        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
-        int e = tid;
-        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
-            int32_t c4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
-            double v4[4], w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { v4[j] = __ldg(xf + c4[j]); w4[j] = __ldg(xg + c4[j]); }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { xsf[e + j * NB_CTA_ROWS] = v4[j]; xsg[e + j * NB_CTA_ROWS] = w4[j]; }
-        }
-        for (; e < ps.count; e += NB_CTA_ROWS) {
-            const int32_t cc = __ldcs(sc + e);
-            xsf[e] = __ldg(xf + cc);
-            xsg[e] = __ldg(xg + cc);
-        }
+        nb_stage_pass<2>(A.stage_col + ps.begin, ps.count, tid, xf, xg, xsf, xsg);
         __syncthreads();
 #pragma unroll 1
         for (int a = ps.a0; a < ps.a1; a++) {

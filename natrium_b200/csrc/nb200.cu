@@ -127,6 +127,7 @@ struct nb200_ctx {
     NbStagePass* d_stage_pass = nullptr;
     int32_t* d_stage_cta = nullptr;
     int64_t stage_values = 0, stage_passes = 0, stage_max_pass = 0;
+    std::vector<NbDirClass> cls0;            // class 0 of every direction (copied into the kernel arguments)
     int stage_cap = 0;
     // collision
     const NbStencilOps* ops = nullptr;
@@ -297,29 +298,13 @@ k_stream_staged(StreamArgs A, int Q, const double* __restrict__ x0, const double
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();
-        int2 dn = active ? __ldcs(A.sdesc + (int64_t)ps.a0 * A.desc_stride + row) : empty;
-        const int32_t* __restrict__ sc = A.stage_col + ps.begin;
-        int e = tid;
-        for (; e + 3 * NB_CTA_ROWS < ps.count; e += 4 * NB_CTA_ROWS) {
-            int32_t c4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) c4[j] = __ldcs(sc + e + j * NB_CTA_ROWS);
-            double v4[4], w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { v4[j] = __ldg(x0 + c4[j]); if (NRHS == 2) w4[j] = __ldg(x1 + c4[j]); }
-#pragma unroll
-            for (int j = 0; j < 4; j++) { xs0[e + j * NB_CTA_ROWS] = v4[j]; if (NRHS == 2) xs1[e + j * NB_CTA_ROWS] = w4[j]; }
-        }
-        for (; e < ps.count; e += NB_CTA_ROWS) {
-            const int32_t cc = __ldcs(sc + e);
-            xs0[e] = __ldg(x0 + cc);
-            if (NRHS == 2) xs1[e] = __ldg(x1 + cc);
-        }
+        int2 dn = active ? nb_ld_once(A.sdesc + (int64_t)ps.a0 * A.desc_stride + row) : empty;
+        nb_stage_pass<NRHS>(A.stage_col + ps.begin, ps.count, tid, x0, x1, xs0, xs1);
         __syncthreads();
 #pragma unroll 1
         for (int a = ps.a0; a < ps.a1; a++) {
             const int2 d = dn;
-            if (a + 1 < ps.a1 && active) dn = __ldcs(A.sdesc + (int64_t)(a + 1) * A.desc_stride + row);
+            if (a + 1 < ps.a1 && active) dn = nb_ld_once(A.sdesc + (int64_t)(a + 1) * A.desc_stride + row);
             double r0, r1;
             nb_row_dot_staged<NRHS>(A, a, d, xs0, xs1, r0, r1);
             if (active) {
@@ -757,7 +742,7 @@ static int finalize_dict(nb200_ctx* c)
             }
             nbdict::ClassBuild& B = d.cls[(size_t)ci];
             const int K = B.K;
-            const int64_t P = ((B.n_pats() + 31) / 32) * 32, NL = ((int64_t)K + 3) / 4 * 4;   // NL: list pitch
+            const int64_t P = std::max<int64_t>(4, ((B.n_pats() + 3) / 4) * 4), NL = ((int64_t)K + 3) / 4 * 4;   // NL: list pitch
             double *dW = nullptr, *sW = nullptr;
             int32_t* dL = nullptr;
             CUDA_TRY(c, cudaMalloc(&dW, (size_t)K * P * 8));
@@ -812,6 +797,8 @@ static int finalize_dict(nb200_ctx* c)
         CUDA_TRY(c, cudaMemcpy(c->d_stage_pass, SB.passes.data(), SB.passes.size() * sizeof(NbStagePass), cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMalloc(&c->d_stage_cta, SB.cta_ptr.size() * sizeof(int32_t)));
         CUDA_TRY(c, cudaMemcpy(c->d_stage_cta, SB.cta_ptr.data(), SB.cta_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->cls0.resize((size_t)nb);
+        for (int a = 0; a < nb; a++) c->cls0[(size_t)a] = hcls[(size_t)a * NB_MAX_CLS];
         c->staged = true;
         c->stage_values = (int64_t)SB.stage_col.size();
         c->stage_passes = (int64_t)SB.passes.size();
@@ -1152,6 +1139,12 @@ static StreamArgs stream_args(nb200_ctx* c)
     A.ell_val = c->ell_val; A.ell_idx = c->ell_idx; A.slice_off = c->d_slice_off;
     A.desc = c->d_desc; A.cls = c->d_cls; A.desc_stride = c->desc_stride;
     A.sdesc = c->d_sdesc; A.stage_col = c->d_stage_col; A.stage_pass = c->d_stage_pass; A.stage_cta = c->d_stage_cta;
+    for (int a = 0; a < NB_MAX_DIRS; a++) {
+        const bool have = c->staged && a < (int)c->cls0.size();
+        A.c0_W[a] = have ? c->cls0[(size_t)a].W : nullptr;
+        A.c0_P[a] = have ? (int32_t)c->cls0[(size_t)a].P : 32;
+        A.c0_K[a] = have ? (c->cls0[(size_t)a].K | (c->cls0[(size_t)a].streamed << 30)) : 0;
+    }
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
     return A;
 }

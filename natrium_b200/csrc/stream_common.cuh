@@ -23,8 +23,11 @@
 enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
 
 #define NB_CTA_ROWS 128
-#define NB_STAGE_CAP 4096          // doubles per pass and distribution (f only)
-#define NB_STAGE_CAP_FG 2048       // doubles per pass and distribution when f and g are staged together
+// Pass capacity in doubles per distribution.  Deliberately small: with 4 CTAs per SM the staged values take
+// 4 x 16 KB, which leaves the L1 large enough to keep the weight patterns resident.
+#define NB_STAGE_CAP 2048          // f only
+#define NB_STAGE_CAP_FG 2048       // f and g staged together (two arrays of this size)
+#define NB_MAX_DIRS 44             // Q - 1 of the largest stencil on the path (D3Q45)
 
 #define NB_CLS_BITS 6
 #define NB_MAX_CLS (1 << NB_CLS_BITS)           // row-length classes per direction
@@ -61,6 +64,11 @@ struct StreamArgs {
     const int32_t* __restrict__ stage_col;   // flat population index of every staged support value, pass after pass
     const struct NbStagePass* __restrict__ stage_pass;
     const int32_t* __restrict__ stage_cta;   // [n_cta + 1] first pass of every CTA
+    // class 0 of every direction (the row length almost every row has) is described right here in the kernel
+    // arguments, so the common case needs no dependent table load between descriptor and weights
+    const double* c0_W[NB_MAX_DIRS];
+    int32_t c0_P[NB_MAX_DIRS];
+    int32_t c0_K[NB_MAX_DIRS];               // K | streamed << 30
     int64_t n_slices;
     int64_t n_owned;
     int64_t stride;
@@ -175,29 +183,73 @@ __device__ __forceinline__ void nb_row_dot_dict(const StreamArgs& A, int alpha_m
     y1 = a1;
 }
 
+// ---- cache-policy loads for the staged kernels.  The L1 is shared by three streams of very different reuse:
+// weight patterns (re-read by every CTA on the SM: keep), descriptors / staging indices (read once: do not
+// allocate), gathered support values (some reuse between neighbouring CTAs: default policy).
+__device__ __forceinline__ double nb_ld_keep(const double* p)
+{
+    double v;
+    asm volatile("ld.global.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int32_t nb_ld_once(const int32_t* p)
+{
+    int32_t v;
+    asm volatile("ld.global.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int2 nb_ld_once(const int2* p)
+{
+    int2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // Staged row product: support values from shared memory (xs0/xs1 + off), weights from the k-major pattern pool.
-// Same summation order as the other formats (k = 0..K-1 as stored).
+// Same summation order as the other formats (k = 0..K-1 as stored).  All weights of a batch are requested before
+// the first is used; the last batch is predicated (index clamped, weight forced to 0) instead of falling back to
+// one load at a time, so a row of K entries waits ceil(K / B) load latencies.
+template <int NRHS, bool STREAMED, int B>
+__device__ __forceinline__ void nb_staged_batches(const double* __restrict__ W, int K, int64_t P,
+                                                  const double* __restrict__ s0, const double* __restrict__ s1,
+                                                  double& a0, double& a1)
+{
+    int k = 0;
+    for (; k + B <= K; k += B) {
+        double vv[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : nb_ld_keep(W + (int64_t)(k + j) * P);
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            a0 += vv[j] * s0[k + j];
+            if (NRHS == 2) a1 += vv[j] * s1[k + j];
+        }
+    }
+    if (k < K) {
+        double vv[B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            const int kj = min(k + j, K - 1);
+            vv[j] = STREAMED ? __ldcs(W + (int64_t)kj * P) : nb_ld_keep(W + (int64_t)kj * P);
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (k + j < K) {
+                a0 += vv[j] * s0[k + j];
+                if (NRHS == 2) a1 += vv[j] * s1[k + j];
+            }
+        }
+    }
+}
+
 template <int NRHS, bool STREAMED>
 __device__ __forceinline__ void nb_staged_accumulate(const double* __restrict__ W, int K, int64_t P,
                                                      const double* __restrict__ s0, const double* __restrict__ s1,
                                                      double& a0, double& a1)
 {
-    int k = 0;
-    for (; k + 8 <= K; k += 8) {
-        double vv[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            a0 += vv[j] * s0[k + j];
-            if (NRHS == 2) a1 += vv[j] * s1[k + j];
-        }
-    }
-    for (; k < K; k++) {
-        const double vv = STREAMED ? __ldcs(W + (int64_t)k * P) : __ldg(W + (int64_t)k * P);
-        a0 += vv * s0[k];
-        if (NRHS == 2) a1 += vv * s1[k];
-    }
+    // K = (p+1)^k on the path: 5 / 25 / 125 for the FE order of the benchmark configurations
+    if (K <= 8) nb_staged_batches<NRHS, STREAMED, 8>(W, K, P, s0, s1, a0, a1);
+    else nb_staged_batches<NRHS, STREAMED, 13>(W, K, P, s0, s1, a0, a1);
 }
 
 template <int NRHS>
@@ -205,17 +257,61 @@ __device__ __forceinline__ void nb_row_dot_staged(const StreamArgs& A, int alpha
                                                   const double* __restrict__ xs1, double& y0, double& y1)
 {
     const unsigned dx = (unsigned)d.x;
-    const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + (dx >> 16);
-    const int K = C->K;
-    const int64_t P = C->P;
-    const double* __restrict__ W = C->W + (unsigned)d.y;
+    const unsigned cls = dx >> 16;
+    int K, streamed;
+    int64_t P;
+    const double* __restrict__ W;
+    if (cls == 0) {
+        const int kk = A.c0_K[alpha_m1];
+        K = kk & 0x3fffffff;
+        streamed = kk >> 30;
+        P = A.c0_P[alpha_m1];
+        W = A.c0_W[alpha_m1] + (unsigned)d.y;
+    } else {
+        const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + cls;
+        K = C->K;
+        streamed = C->streamed;
+        P = C->P;
+        W = C->W + (unsigned)d.y;
+    }
     const double* __restrict__ s0 = xs0 + (dx & 0xffffu);
     const double* __restrict__ s1 = xs1 + (dx & 0xffffu);
     double a0 = 0.0, a1 = 0.0;
-    if (C->streamed) nb_staged_accumulate<NRHS, true>(W, K, P, s0, s1, a0, a1);
+    if (streamed) nb_staged_accumulate<NRHS, true>(W, K, P, s0, s1, a0, a1);
     else nb_staged_accumulate<NRHS, false>(W, K, P, s0, s1, a0, a1);
     y0 = a0;
     y1 = a1;
+}
+
+// ---- staging: 8-byte asynchronous copies global -> shared (LDGSTS), so that a thread has all its gathers of a
+// pass in flight at once instead of waiting for each batch to land in registers ----
+__device__ __forceinline__ void nb_cp_async8(double* smem_dst, const double* gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void nb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Copies the `count` staged values of a pass: xs0[e] = x0[sc[e]] (and xs1[e] = x1[sc[e]]).  A pass holds at most
+// NB_STAGE_CAP values = B per thread, so all index loads are in flight together (one latency) and all copies after
+// them (one more).
+template <int NRHS>
+__device__ __forceinline__ void nb_stage_pass(const int32_t* __restrict__ sc, int count, int tid,
+                                              const double* __restrict__ x0, const double* __restrict__ x1,
+                                              double* __restrict__ xs0, double* __restrict__ xs1)
+{
+    constexpr int B = NB_STAGE_CAP / NB_CTA_ROWS;
+    static_assert(NB_STAGE_CAP_FG <= NB_STAGE_CAP, "one batch must cover a whole pass");
+    int32_t idx[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) idx[j] = (tid + j * NB_CTA_ROWS < count) ? nb_ld_once(sc + tid + j * NB_CTA_ROWS) : -1;
+#pragma unroll
+    for (int j = 0; j < B; j++)
+        if (idx[j] >= 0) {
+            nb_cp_async8(xs0 + tid + j * NB_CTA_ROWS, x0 + idx[j]);
+            if (NRHS == 2) nb_cp_async8(xs1 + tid + j * NB_CTA_ROWS, x1 + idx[j]);
+        }
+    nb_cp_async_wait_all();
 }
 
 template <int FMT, int NRHS>

@@ -283,14 +283,17 @@ int orc_collide_bgk(int D, int Q, int64_t n, int64_t stride, double *f, double *
  * (:420-431), centred moments (:445-472), fStar/gStar (:484-515), Knudsen estimate (:474-481).
  * equilibrium: 0 = BGKEquilibrium (ignores T), 1 = QuarticEquilibrium.
  * ------------------------------------------------------------------------------------------ */
-int orc_collide_bgk_fg(int D, int Q, int64_t n, int64_t stride, double *f, double *g,
+static int orc_collide_fg_core(int D, int Q, int64_t n, int64_t stride, double *f, double *g,
                        double *rho_out, double *u_out, double *T_out, double *mss_out,
                        const double *e_scaled, const double *w, double scaling, double cs2_scaled,
                        double viscosity, double dt, int equilibrium, double gamma,
-                       int prandtl_set, double prandtl, int sutherland_set, int in_init)
+                       int prandtl_set, double prandtl, int sutherland_set, int in_init,
+                       int has_force, int force_type, const double *force)
 {
     orc_params P;
     orc_make_params(&P, D, Q, e_scaled, w, scaling, cs2_scaled, viscosity, dt);
+    if (has_force && force_type == 0) return -2;               /* Aux...h:335-339 */
+    if (has_force && force_type != 1 && force_type != 2) return -3;
     int bad = 0;
 #pragma omp parallel for schedule(static) reduction(| : bad) if (n > 50000)
     for (int64_t ii = 0; ii < n; ii++) {
@@ -314,6 +317,10 @@ int orc_collide_bgk_fg(int D, int Q, int64_t n, int64_t stride, double *f, doubl
         T_out[ii] = T;
         if (!in_init) {
             for (int j = 0; j < D; ++j) u_out[j * n + ii] = u[j] * P.scaling;
+            if (has_force && force_type == 1) {     /* applyMacroscopicForces + applyForces, SHIFTING_VELOCITY */
+                for (int j = 0; j < D; j++) u_out[j * n + ii] = u_out[j * n + ii] + 0.5 * dt * force[j] / rho;
+                for (int j = 0; j < D; j++) u[j] += P.tau * dt * force[j] / rho / P.scaling;
+            }
         } else {
             for (int j = 0; j < D; ++j) u[j] = u_out[j * n + ii] / P.scaling;
         }
@@ -362,12 +369,44 @@ int orc_collide_bgk_fg(int D, int Q, int64_t n, int64_t stride, double *f, doubl
             fl[p] -= visc_omega * fNeq[p] - prandtl_diff * fStar[p];
             gl[p] -= visc_omega * gNeq[p] - prandtl_diff * gStar[p];
         }
+        if (has_force && force_type == 2) {     /* postCollisionApplyForces, EXACT_DIFFERENCE: f only (Aux...h:399-411) */
+            double shifted[ORC_MAXQ];
+            for (int j = 0; j < D; j++) {
+                u[j] += dt * force[j] / rho / P.scaling;
+                u_out[j * n + ii] = u_out[j * n + ii] + 0.5 * dt * force[j] / rho;
+            }
+            if (equilibrium == 0) orc_feq_bgk(&P, rho, u, shifted);
+            else orc_feq_quartic(&P, rho, u, T, shifted);
+            for (int i = 0; i < Q; i++) fl[i] += (shifted[i] - feq[i]);
+        }
         for (int p = 0; p < Q; ++p) {
             f[p * stride + ii] = fl[p];
             g[p * stride + ii] = gl[p];
         }
     }
     return bad ? -1 : 0;
+}
+
+int orc_collide_bgk_fg(int D, int Q, int64_t n, int64_t stride, double *f, double *g,
+                       double *rho_out, double *u_out, double *T_out, double *mss_out,
+                       const double *e_scaled, const double *w, double scaling, double cs2_scaled,
+                       double viscosity, double dt, int equilibrium, double gamma,
+                       int prandtl_set, double prandtl, int sutherland_set, int in_init)
+{
+    return orc_collide_fg_core(D, Q, n, stride, f, g, rho_out, u_out, T_out, mss_out, e_scaled, w, scaling, cs2_scaled,
+                               viscosity, dt, equilibrium, gamma, prandtl_set, prandtl, sutherland_set, in_init, 0, 0, NULL);
+}
+
+/* f + g with an external force (C5: EXACT_DIFFERENCE forcing of the channel flow, step-turbulent-channel.cpp) */
+int orc_collide_bgk_fg_forced(int D, int Q, int64_t n, int64_t stride, double *f, double *g,
+                              double *rho_out, double *u_out, double *T_out, double *mss_out,
+                              const double *e_scaled, const double *w, double scaling, double cs2_scaled,
+                              double viscosity, double dt, int equilibrium, double gamma,
+                              int prandtl_set, double prandtl, int sutherland_set, int in_init,
+                              int force_type, const double *force)
+{
+    return orc_collide_fg_core(D, Q, n, stride, f, g, rho_out, u_out, T_out, mss_out, e_scaled, w, scaling, cs2_scaled,
+                               viscosity, dt, equilibrium, gamma, prandtl_set, prandtl, sutherland_set, in_init, 1, force_type, force);
 }
 
 /* equilibrium evaluation entry points (used by tests and by initial conditions) */
@@ -466,6 +505,104 @@ int orc_step_fg(int D, int Q, int64_t n, int64_t stride, double *f, double *g, d
     return orc_collide_bgk_fg(D, Q, n, stride, f, g, rho_out, u_out, T_out, mss_out, e_scaled, w, scaling,
                               cs2_scaled, viscosity, dt, equilibrium, gamma, prandtl_set, prandtl,
                               sutherland_set, 0);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * collideAll, f only, remaining rows of selectCollision (CollisionSelection.h:85-88,179-196):
+ *   scheme 0  BGKCollision::relax            CollisionSchemes.h:28-41
+ *   scheme 1  Regularized::relax             CollisionSchemes.h:122-203 (Q tensor :136-148)
+ *   scheme 2  MultipleRelaxationTime::relax  CollisionSchemes.h:206-265; M, T, omega are what
+ *             AuxiliaryMRTFunctions::make_M / make_T / make_diag return (AuxiliaryMRTFunctions.cpp)
+ * and the external-force hooks of collideAll (CollisionOperator.h:79-96):
+ *   applyMacroscopicForces Aux...h:332-360, applyForces :362-386, postCollisionApplyForces :388-417.
+ * force_type follows ForceType (ConfigNames.h:114-119): 0 NO_FORCING, 1 SHIFTING_VELOCITY,
+ * 2 EXACT_DIFFERENCE, 3 GUO.  has_force mirrors problemDescription.hasExternalForce().
+ * Returns 0, -1 (density < 1e-10), -2 (NATriuMException: forcing switched off), -3 (NotImplemented).
+ * ------------------------------------------------------------------------------------------ */
+int orc_collide_advanced_f(int D, int Q, int64_t n, int64_t stride, double *f, double *rho_out, double *u_out,
+                           const double *e_scaled, const double *w, double scaling, double cs2_scaled,
+                           double viscosity, double dt, int equilibrium, int scheme, int in_init,
+                           int has_force, int force_type, const double *force,
+                           const double *M, const double *T, const double *omega)
+{
+    orc_params P;
+    orc_make_params(&P, D, Q, e_scaled, w, scaling, cs2_scaled, viscosity, dt);
+    if (has_force && force_type == 0) return -2;
+    if (has_force && force_type != 1 && force_type != 2) return -3;
+    double Qt[ORC_MAXQ][3][3];                       /* Regularized::SpecificCollisionData::initializeQ */
+    for (int a = 0; a < Q; a++)
+        for (int b = 0; b < D; b++)
+            for (int c = 0; c < D; c++) {
+                Qt[a][b][c] = P.e[a][b] * P.e[a][c];
+                if (b == c) Qt[a][b][c] -= P.cs2;
+            }
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) if (n > 50000)
+    for (int64_t ii = 0; ii < n; ii++) {
+        double fl[ORC_MAXQ], feq[ORC_MAXQ], u[3] = {0, 0, 0};
+        for (int p = 0; p < Q; ++p) fl[p] = f[p * stride + ii];
+        double rho = orc_density(fl, Q);
+        if (rho < 1e-10) bad |= 1;
+        rho_out[ii] = rho;
+        orc_velocity(&P, fl, rho, u);
+        if (!in_init) {
+            for (int j = 0; j < D; ++j) u_out[j * n + ii] = u[j] * P.scaling;
+            if (has_force) {
+                if (force_type == 1) {      /* SHIFTING_VELOCITY */
+                    for (int j = 0; j < D; j++) u_out[j * n + ii] = u_out[j * n + ii] + 0.5 * dt * force[j] / rho;
+                    for (int j = 0; j < D; j++) u[j] += P.tau * dt * force[j] / rho / P.scaling;
+                }
+            }
+        } else {
+            for (int j = 0; j < D; ++j) u[j] = u_out[j * n + ii] / P.scaling;
+        }
+        if (equilibrium == 0) orc_feq_bgk(&P, rho, u, feq);
+        else orc_feq_quartic(&P, rho, u, 1.0, feq);
+        if (scheme == 0) {
+            for (int p = 0; p < Q; ++p) fl[p] -= 1. / P.tau * (fl[p] - feq[p]);
+        } else if (scheme == 1) {
+            double pi[3][3], pieq[3][3], fi1[ORC_MAXQ];
+            for (int m = 0; m < D; m++) for (int k = 0; k < D; k++) { pi[m][k] = 0.0; pieq[m][k] = 0.0; }
+            for (int j = 0; j < Q; j++)
+                for (int m = 0; m < D; m++)
+                    for (int k = 0; k < D; k++) {
+                        pi[m][k] += fl[j] * P.e[j][m] * P.e[j][k];
+                        pieq[m][k] += feq[j] * P.e[j][m] * P.e[j][k];
+                    }
+            for (int m = 0; m < D; m++) for (int k = 0; k < D; k++) pi[m][k] -= pieq[m][k];
+            for (int a = 0; a < Q; a++) {
+                fi1[a] = 0.0;
+                for (int b = 0; b < D; b++)
+                    for (int c = 0; c < D; c++)
+                        fi1[a] += P.w[a] / (2 * P.cs2 * P.cs2) * Qt[a][b][c] * pi[b][c];
+            }
+            for (int i = 0; i < Q; ++i) fl[i] = feq[i] + (1. - 1. / P.tau) * fi1[i];
+        } else {
+            double m[ORC_MAXQ], meq[ORC_MAXQ];
+            for (int i = 0; i < Q; i++) {
+                m[i] = 0.0; meq[i] = 0.0;
+                for (int j = 0; j < Q; j++) m[i] += M[i * Q + j] * fl[j];
+                for (int j = 0; j < Q; j++) meq[i] += M[i * Q + j] * feq[j];
+            }
+            for (int i = 0; i < Q; i++) m[i] = m[i] - omega[i] * (m[i] - meq[i]);
+            for (int i = 0; i < Q; i++) {
+                fl[i] = 0.0;
+                for (int j = 0; j < Q; j++) fl[i] += T[i * Q + j] * m[j];
+            }
+        }
+        if (has_force && force_type == 2) {     /* EXACT_DIFFERENCE, postCollisionApplyForces */
+            double shifted[ORC_MAXQ];
+            for (int j = 0; j < D; j++) {
+                u[j] += dt * force[j] / rho / P.scaling;
+                u_out[j * n + ii] = u_out[j * n + ii] + 0.5 * dt * force[j] / rho;
+            }
+            if (equilibrium == 0) orc_feq_bgk(&P, rho, u, shifted);
+            else orc_feq_quartic(&P, rho, u, 1.0, shifted);
+            for (int i = 0; i < Q; i++) fl[i] += (shifted[i] - feq[i]);
+        }
+        for (int p = 0; p < Q; ++p) f[p * stride + ii] = fl[p];
+    }
+    return bad ? -1 : 0;
 }
 
 int orc_num_threads(void)
