@@ -43,7 +43,17 @@ enum nb200_status {
 enum nb200_collision_scheme {
     NB200_BGK_STANDARD = 0,     /* collision_advanced BGKCollision, CollisionSchemes.h:17-119 */
     NB200_KBC_STANDARD = 1,     /* legacy KBCStandard::collideAll (D2Q9, D3Q15), L/collision/KBCStandard.cpp:88-1028 */
-    NB200_MRT_ENTROPIC = 2      /* legacy MRTEntropic::collideAllD3Q19, L/collision/MRTEntropic.cpp:167-305 */
+    NB200_MRT_ENTROPIC = 2,     /* legacy MRTEntropic::collideAllD3Q19, L/collision/MRTEntropic.cpp:167-305 */
+    NB200_BGK_REGULARIZED = 3,  /* collision_advanced Regularized (D2Q9, D3Q15, D3Q19), CollisionSchemes.h:122-203 */
+    NB200_MRT_STANDARD = 4      /* collision_advanced MultipleRelaxationTime (D2Q9, D3Q19), CollisionSchemes.h:206-265;
+                                   needs nb200_set_mrt() */
+};
+/* ForceType (L/utilities/ConfigNames.h:114-119) */
+enum nb200_force_type {
+    NB200_NO_FORCING = 0,
+    NB200_SHIFTING_VELOCITY = 1,
+    NB200_EXACT_DIFFERENCE = 2,
+    NB200_GUO = 3               /* "Force Type not implemented" in the reference (Aux...h:356-359) */
 };
 enum nb200_equilibrium_scheme {
     NB200_BGK_EQUILIBRIUM = 0,     /* Equilibria.h:17-83 */
@@ -63,6 +73,9 @@ typedef struct nb200_collision_params {
     int32_t prandtl_set;       /* isPrandtlNumberSet() */
     int32_t sutherland_set;    /* isSutherlandLawSet() */
     double prandtl;            /* getPrandtlNumber() (default 1) */
+    int32_t has_external_force; /* problemDescription.hasExternalForce() (CollisionOperator.h:83,93) */
+    int32_t force_type;        /* nb200_force_type = configuration.getForcingScheme() */
+    double force[3];           /* getExternalForce()->getForce() (GeneralCollisionData ctor, Aux...h:179-183) */
 } nb200_collision_params;
 
 /* ---- lifecycle ------------------------------------------------------------------------- */
@@ -138,6 +151,22 @@ int nb200_staging_info(const nb200_ctx *ctx, int64_t out[5]);
 int nb200_set_halo(nb200_ctx *ctx, int n_nbr, const int32_t *nbr_rank, const int64_t *send_off,
                    const int32_t *send_idx, const int64_t *recv_off);
 
+/* Wall hits of the semi-Lagrangian boundary handler (SemiLagrangianBoundaryHandler::addHit,
+ * L/boundaries/SemiLagrangianBoundaryHandler.cpp:14-23; BoundaryHit.h), flattened in HitList iteration order
+ * (cell, point, hit -- the order SemiLagrangianBoundaryHandler::operate walks, :43-109).  Applied after the SpMV of
+ * f inside nb200_stream(ctx, 0) and nb200_step, exactly where m_boundaryHandler.apply(f, f_old[, g], t) sits
+ * (SemiLagrangian.h:163-169, CFDSolver.cpp:673, CompressibleCFDSolver.h:195).  The bounce itself is part of the
+ * matrix (off-diagonal blocks); this is the per-hit correction:
+ *   NB200_WALL_VELOCITY_NEQ_BOUNCE_BACK  value[h] = 2 w_dir rho (e_dir . u_wall(x_hit, t - dtHit)) / cs2 with rho = 1,
+ *       evaluated by the host that owns the wall-velocity function (VelocityNeqBounceBack.cpp:137-195); it is added
+ *       to f[dest_direction](dest_index).  Re-upload when the wall velocity changes in time.
+ *   NB200_WALL_THERMAL_BOUNCE_BACK       value[h] = wall temperature (ThermalBounceBack.cpp:50-109; D3Q45 with g):
+ *       f and g of the destination DoF are re-equilibrated to it (all 45 populations).
+ * dest_index: owned local DoF (LagrangianPathDestination::index), dest_direction: its direction.  n_hits = 0 clears. */
+enum nb200_wall_kind { NB200_WALL_VELOCITY_NEQ_BOUNCE_BACK = 0, NB200_WALL_THERMAL_BOUNCE_BACK = 1 };
+int nb200_set_wall_hits(nb200_ctx *ctx, int64_t n_hits, const int32_t *dest_index, const int32_t *dest_direction,
+                        const int32_t *kind, const double *value);
+
 /* ---- DistributionFunctions storage (L/solver/DistributionFunctions.h:47-300) -------------- */
 
 /* which: 0 = f, 1 = g.  q in [0,Q): f.at(q).  host: n_owned contiguous doubles, the array
@@ -161,6 +190,12 @@ int nb200_upload_density(nb200_ctx *ctx, const double *rho, int64_t n);
 /* ---- per-step operators ------------------------------------------------------------------ */
 
 int nb200_set_collision(nb200_ctx *ctx, const nb200_collision_params *p);
+
+/* Tables of MultipleRelaxationTime::SpecificCollisionData (CollisionSchemes.h:209-236): M = make_M(basis),
+ * T = make_T(basis) (both Q x Q row-major), omega = make_diag(tau, basis, relax mode) (Q entries), all from
+ * L/collision_advanced/AuxiliaryMRTFunctions.cpp.  Call before nb200_set_collision(scheme = NB200_MRT_STANDARD);
+ * omega depends on tau, so call again when viscosity or dt change. */
+int nb200_set_mrt(nb200_ctx *ctx, int Q, const double *M, const double *T, const double *omega);
 
 /* DistributionFunctions::updateGhosted() for f (and g): NCCL neighbour exchange. No-op on 1 rank. */
 int nb200_update_ghosted(nb200_ctx *ctx);

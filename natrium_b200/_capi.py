@@ -20,7 +20,9 @@ NB200_ERR_UNSUPPORTED = -4
 NB200_ERR_DENSITY = -5
 NB200_ERR_NO_DEVICE = -6
 
-BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = 0, 1, 2
+BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC, BGK_REGULARIZED, MRT_STANDARD = 0, 1, 2, 3, 4
+NO_FORCING, SHIFTING_VELOCITY, EXACT_DIFFERENCE, GUO = 0, 1, 2, 3
+WALL_VELOCITY_NEQ_BOUNCE_BACK, WALL_THERMAL_BOUNCE_BACK = 0, 1
 BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = 0, 1
 FORMAT_ELL, FORMAT_DICT, FORMAT_DICT_UNSTAGED = 0, 1, 2
 
@@ -28,7 +30,8 @@ FORMAT_ELL, FORMAT_DICT, FORMAT_DICT_UNSTAGED = 0, 1, 2
 class CollisionParams(C.Structure):
     _fields_ = [("scheme", C.c_int32), ("equilibrium", C.c_int32), ("with_g", C.c_int32), ("in_init", C.c_int32),
                 ("viscosity", C.c_double), ("dt", C.c_double), ("gamma", C.c_double),
-                ("prandtl_set", C.c_int32), ("sutherland_set", C.c_int32), ("prandtl", C.c_double)]
+                ("prandtl_set", C.c_int32), ("sutherland_set", C.c_int32), ("prandtl", C.c_double),
+                ("has_external_force", C.c_int32), ("force_type", C.c_int32), ("force", C.c_double * 3)]
 
 
 class NatriumB200Error(RuntimeError):
@@ -68,6 +71,8 @@ SIGNATURES = {
     "nb200_upload_velocity": (C.c_int, [_vp, _dp, C.c_int64]),
     "nb200_upload_density": (C.c_int, [_vp, _dp, C.c_int64]),
     "nb200_set_collision": (C.c_int, [_vp, C.POINTER(CollisionParams)]),
+    "nb200_set_mrt": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "nb200_set_wall_hits": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, _i32p, _dp]),
     "nb200_update_ghosted": (C.c_int, [_vp]),
     "nb200_stream": (C.c_int, [_vp, C.c_int]),
     "nb200_collide": (C.c_int, [_vp]),
@@ -237,10 +242,31 @@ class Context:
 
     # ---- operators
     def set_collision(self, viscosity, dt, scheme=BGK_STANDARD, equilibrium=BGK_EQUILIBRIUM, with_g=False,
-                      in_init=False, gamma=1.4, prandtl=None, sutherland=False):
+                      in_init=False, gamma=1.4, prandtl=None, sutherland=False, force=None, force_type=NO_FORCING):
+        """force: external force vector (problemDescription.getExternalForce()->getForce()) or None for
+        hasExternalForce() == false; force_type: configuration.getForcingScheme()."""
+        fv = (C.c_double * 3)(0.0, 0.0, 0.0)
+        if force is not None:
+            for j, v in enumerate(force):
+                fv[j] = float(v)
         p = CollisionParams(scheme, equilibrium, 1 if with_g else 0, 1 if in_init else 0, viscosity, dt, gamma,
-                            0 if prandtl is None else 1, 1 if sutherland else 0, 1.0 if prandtl is None else prandtl)
+                            0 if prandtl is None else 1, 1 if sutherland else 0, 1.0 if prandtl is None else prandtl,
+                            0 if force is None else 1, force_type, fv)
         self._check(self.lib.nb200_set_collision(self._h, C.byref(p)))
+
+    def set_wall_hits(self, dest_index, dest_direction, kind, value):
+        """Flattened HitList of the semi-Lagrangian boundary handler (nb200_set_wall_hits)."""
+        di = np.ascontiguousarray(dest_index, dtype=np.int32)
+        dd = np.ascontiguousarray(dest_direction, dtype=np.int32)
+        kk = np.ascontiguousarray(kind, dtype=np.int32)
+        vv = _as_f64(value)
+        self._check(self.lib.nb200_set_wall_hits(self._h, len(di), di.ctypes.data_as(_i32p), dd.ctypes.data_as(_i32p),
+                                                 kk.ctypes.data_as(_i32p), _dptr(vv)))
+
+    def set_mrt(self, M, T, omega):
+        """Tables of MultipleRelaxationTime::SpecificCollisionData (make_M / make_T / make_diag)."""
+        M, T, omega = _as_f64(M), _as_f64(T), _as_f64(omega)
+        self._check(self.lib.nb200_set_mrt(self._h, int(len(omega)), _dptr(M), _dptr(T), _dptr(omega)))
 
     def update_ghosted(self):
         self._check(self.lib.nb200_update_ghosted(self._h))

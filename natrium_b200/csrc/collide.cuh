@@ -188,10 +188,128 @@ __device__ __forceinline__ void nb_collide_bgk(double (&f)[Q], double& rho, doub
     for (int p = 0; p < Q; ++p) f[p] -= omega * (f[p] - feq[p]);
 }
 
+// MultipleRelaxationTime tables: what make_M / make_T / make_diag return (AuxiliaryMRTFunctions.cpp), handed over
+// through nb200_set_mrt().  Only stencils with an MRT row in selectCollision carry them (Q <= 19).
+#define NB_MRT_MAXQ 19
+struct NbMrtStd {
+    double M[NB_MRT_MAXQ][NB_MRT_MAXQ];
+    double T[NB_MRT_MAXQ][NB_MRT_MAXQ];
+    double omega[NB_MRT_MAXQ];
+};
+__constant__ NbMrtStd cS;
+
+// collideAll body, f only, every scheme of selectCollision on the path (CollisionOperator.h:52-104):
+// SCHEME 0 BGKCollision::relax (CollisionSchemes.h:28-41), 1 Regularized::relax (:150-203),
+// 2 MultipleRelaxationTime::relax (:238-263).  FORCE compiles the external-force hooks in
+// (applyMacroscopicForces / applyForces / postCollisionApplyForces, Aux...h:332-417; force type from cP).
+// v_out: scaled velocity written to the global vector (input when in_init); u: velocity the equilibrium used.
+template <int D, int Q, int EQ, int SCHEME, bool FORCE>
+__device__ __forceinline__ void nb_collide_adv(double (&f)[Q], double& rho, double (&v_out)[3], bool in_init)
+{
+    double u[3];
+    rho = nb_density<Q>(f);
+    nb_velocity<D, Q>(f, rho, u);
+    if (!in_init) {
+#pragma unroll
+        for (int j = 0; j < D; j++) v_out[j] = u[j] * cP.scaling;
+        if (FORCE && cP.force_type == 1) {      // SHIFTING_VELOCITY
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                v_out[j] = v_out[j] + 0.5 * cP.dt * cP.force[j] / rho;
+                u[j] += cP.tau * cP.dt * cP.force[j] / rho / cP.scaling;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; j++) u[j] = v_out[j] / cP.scaling;
+    }
+    double feq[Q];
+    if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, feq);
+    else nb_feq_quartic<D, Q>(rho, u, 1.0, feq);
+    if (SCHEME == 0) {
+        const double omega = cP.inv_tau;
+#pragma unroll
+        for (int p = 0; p < Q; ++p) f[p] -= omega * (f[p] - feq[p]);
+    } else if (SCHEME == 1) {
+        double pi[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int n = 0; n < 3; n++) pi[m][n] = 0.0;
+        // pi - pieq accumulated as two sums and subtracted, as the reference does (no cancellation shortcuts)
+        double pieq[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int n = 0; n < 3; n++) pieq[m][n] = 0.0;
+#pragma unroll
+        for (int j = 0; j < Q; j++)
+#pragma unroll
+            for (int m = 0; m < D; m++)
+#pragma unroll
+                for (int n = 0; n < D; n++) {
+                    pi[m][n] += f[j] * cP.e[j][m] * cP.e[j][n];
+                    pieq[m][n] += feq[j] * cP.e[j][m] * cP.e[j][n];
+                }
+#pragma unroll
+        for (int m = 0; m < D; m++)
+#pragma unroll
+            for (int n = 0; n < D; n++) pi[m][n] -= pieq[m][n];
+        const double cs2 = cP.cs2;
+        const double pref = 1.0 / (2 * cs2 * cs2);
+        const double keep = 1. - cP.inv_tau;
+#pragma unroll
+        for (int a = 0; a < Q; a++) {
+            double fi1 = 0.0;
+#pragma unroll
+            for (int b = 0; b < D; b++)
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+                    const double Qabc = cP.e[a][b] * cP.e[a][c] - (b == c ? cs2 : 0.0);
+                    fi1 += cP.w[a] * pref * Qabc * pi[b][c];
+                }
+            f[a] = feq[a] + keep * fi1;
+        }
+    } else {
+        double m[Q];
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+            double mi = 0.0, meq = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; j++) mi += cS.M[i][j] * f[j];
+#pragma unroll
+            for (int j = 0; j < Q; j++) meq += cS.M[i][j] * feq[j];
+            m[i] = mi - cS.omega[i] * (mi - meq);
+        }
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; j++) acc += cS.T[i][j] * m[j];
+            f[i] = acc;
+        }
+    }
+    if (FORCE && cP.force_type == 2) {          // EXACT_DIFFERENCE
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            u[j] += cP.dt * cP.force[j] / rho / cP.scaling;
+            v_out[j] = v_out[j] + 0.5 * cP.dt * cP.force[j] / rho;
+        }
+        double shifted[Q];
+        if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, shifted);
+        else nb_feq_quartic<D, Q>(rho, u, 1.0, shifted);
+#pragma unroll
+        for (int i = 0; i < Q; i++) f[i] += (shifted[i] - feq[i]);
+    }
+}
+
 // collideAll body, f + g (relaxWithG).  Writes T and the Knudsen-estimate sensor.
-template <int D, int Q, int EQ>
+// FORCE: external-force hooks; v_force then receives the value of the global (scaled) velocity vector:
+// raw moment * scaling (or the stored velocity in the initialization procedure) + 0.5 dt F / rho.
+template <int D, int Q, int EQ, bool FORCE = false>
 __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q], double& rho, double (&u)[3],
-                                                  double& T, double& sensor, const double* u_override)
+                                                  double& T, double& sensor, const double* u_override,
+                                                  double* v_force = nullptr)
 {
     const double cs2 = cP.cs2;
     rho = nb_density<Q>(f);
@@ -210,6 +328,17 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
     if (u_override) {
 #pragma unroll
         for (int j = 0; j < D; j++) u[j] = u_override[j] / cP.scaling;
+    }
+    if (FORCE) {
+#pragma unroll
+        for (int j = 0; j < D; j++) v_force[j] = u_override ? u_override[j] : u[j] * cP.scaling;
+        if (!u_override && cP.force_type == 1) {     // SHIFTING_VELOCITY (not in the initialization procedure)
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                v_force[j] = v_force[j] + 0.5 * cP.dt * cP.force[j] / rho;
+                u[j] += cP.tau * cP.dt * cP.force[j] / rho / cP.scaling;
+            }
+        }
     }
     double feq[Q];
     if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, feq);
@@ -275,5 +404,17 @@ __device__ __forceinline__ void nb_collide_bgk_fg(double (&f)[Q], double (&g)[Q]
         const double gneq = g[i] - feq[i] * gfac;
         f[i] -= visc_omega * fneq - prandtl_diff * fStar;
         g[i] -= visc_omega * gneq - prandtl_diff * gStar;
+    }
+    if (FORCE && cP.force_type == 2) {          // EXACT_DIFFERENCE: f only (Aux...h:399-411)
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            u[j] += cP.dt * cP.force[j] / rho / cP.scaling;
+            v_force[j] = v_force[j] + 0.5 * cP.dt * cP.force[j] / rho;
+        }
+        double shifted[Q];
+        if (EQ == NB_EQ_BGK) nb_feq_bgk<D, Q>(rho, u, shifted);
+        else nb_feq_quartic<D, Q>(rho, u, T, shifted);
+#pragma unroll
+        for (int i = 0; i < Q; i++) f[i] += (shifted[i] - feq[i]);
     }
 }

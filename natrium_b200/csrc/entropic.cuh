@@ -237,6 +237,12 @@ __device__ __forceinline__ bool nb_collide_f(double (&f)[Q], double& rho, double
         if (rho_prev < 1e-10) { rho = rho_prev; return true; }
         nb_collide_mrt_entropic_d3q19(f, rho, v, in_init);
         return false;
+    } else if constexpr (KIND == NB_KIND_REGULARIZED) {
+        nb_collide_adv<D, Q, NB_EQ_BGK, 1, false>(f, rho, v, in_init);
+        return rho < 1e-10;
+    } else if constexpr (KIND == NB_KIND_MRT && Q <= NB_MRT_MAXQ) {
+        nb_collide_adv<D, Q, NB_EQ_BGK, 2, false>(f, rho, v, in_init);
+        return rho < 1e-10;
     } else {
         double u[3];
         nb_collide_bgk<D, Q, KIND == NB_EQ_QUARTIC ? NB_EQ_QUARTIC : NB_EQ_BGK>(f, rho, u, in_init ? v : nullptr);
@@ -246,4 +252,15 @@ __device__ __forceinline__ bool nb_collide_f(double (&f)[Q], double& rho, double
         }
         return rho < 1e-10;
     }
+}
+
+// Same with the external-force hooks compiled in (stand-alone collide kernels only: a forced problem runs stream
+// and collide as two kernels).  Entropic kinds have no force hooks in the reference's collideAll.
+template <int D, int Q, int KIND>
+__device__ __forceinline__ bool nb_collide_f_forced(double (&f)[Q], double& rho, double (&v)[3], bool in_init)
+{
+    if constexpr (KIND == NB_KIND_REGULARIZED) nb_collide_adv<D, Q, NB_EQ_BGK, 1, true>(f, rho, v, in_init);
+    else if constexpr (KIND == NB_KIND_MRT && Q <= NB_MRT_MAXQ) nb_collide_adv<D, Q, NB_EQ_BGK, 2, true>(f, rho, v, in_init);
+    else nb_collide_adv<D, Q, KIND == NB_EQ_QUARTIC ? NB_EQ_QUARTIC : NB_EQ_BGK, 0, true>(f, rho, v, in_init);
+    return rho < 1e-10;
 }

@@ -24,6 +24,20 @@
 #else
 #define NB_IF_MRTE(stmt) return -1
 #endif
+// collision_advanced rows of selectCollision: Regularized D2Q9 / D3Q15 / D3Q19, MultipleRelaxationTime D2Q9 / D3Q19
+// (CollisionSelection.h:87-88,182-186)
+#if (NB_D == 2 && NB_Q == 9) || (NB_D == 3 && NB_Q == 15) || (NB_D == 3 && NB_Q == 19)
+#define NB_IF_REG(stmt) stmt
+#else
+#define NB_IF_REG(stmt) return -1
+#endif
+#if (NB_D == 2 && NB_Q == 9) || (NB_D == 3 && NB_Q == 19)
+#define NB_IF_MRT(stmt) stmt
+#define NB_HAS_MRT 1
+#else
+#define NB_IF_MRT(stmt) return -1
+#define NB_HAS_MRT 0
+#endif
 
 namespace {
 
@@ -42,6 +56,13 @@ int bind(const NbLaunch& L)
             e = cudaMemcpyToSymbolAsync(cM, L.mrt, sizeof(NbMrtTables), 0, cudaMemcpyHostToDevice, L.stream);
             if (e != cudaSuccess) return (int)e;
         }
+#if NB_HAS_MRT
+        if (L.mrt_std) {
+            static_assert(sizeof(NbMrtStd) == sizeof(NbMrtStdHost), "MRT table layout");
+            e = cudaMemcpyToSymbolAsync(cS, L.mrt_std, sizeof(NbMrtStd), 0, cudaMemcpyHostToDevice, L.stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+#endif
         s_owner = L.owner;
         s_version = L.version;
     }
@@ -54,7 +75,7 @@ int fused(const NbLaunch& L)
 {
     int rc = bind(L);
     if (rc) return rc;
-    const unsigned grid = grid_for(L.A.n_slices * 32, 128);
+    const unsigned grid = L.grid_override ? L.grid_override : grid_for(L.A.n_slices * 32, 128);
     if (!L.with_g) {
 #if NB_FUSE_F
 #define NB_LAUNCH_F(EQ, FMT) k_stream_collide_f<D, Q, EQ, FMT><<<grid, 128, 0, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag)
@@ -64,6 +85,8 @@ int fused(const NbLaunch& L)
         else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_F(NB_EQ_QUARTIC, FMT);                         \
         else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_F(NB_KIND_KBC, FMT)); }              \
         else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_F(NB_KIND_MRT_ENTROPIC, FMT)); } \
+        else if (L.eq == NB_KIND_REGULARIZED) { NB_IF_REG(NB_LAUNCH_F(NB_KIND_REGULARIZED, FMT)); } \
+        else if (L.eq == NB_KIND_MRT) { NB_IF_MRT(NB_LAUNCH_F(NB_KIND_MRT, FMT)); }              \
         else return -1;                                                                          \
     } while (0)
         if (L.fmt == NB_FMT_STAGED) {
@@ -82,6 +105,8 @@ int fused(const NbLaunch& L)
             else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_FS(NB_EQ_QUARTIC);
             else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_FS(NB_KIND_KBC)); }
             else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_FS(NB_KIND_MRT_ENTROPIC)); }
+            else if (L.eq == NB_KIND_REGULARIZED) { NB_IF_REG(NB_LAUNCH_FS(NB_KIND_REGULARIZED)); }
+            else if (L.eq == NB_KIND_MRT) { NB_IF_MRT(NB_LAUNCH_FS(NB_KIND_MRT)); }
             else return -1;
 #undef NB_LAUNCH_FS
         }
@@ -137,17 +162,31 @@ int collide(const NbLaunch& L)
     const int64_t n = L.A.n_owned;
     const unsigned grid = grid_for(n, 128);
     if (!L.with_g) {
-#define NB_LAUNCH_C(EQ) k_collide_f<D, Q, EQ><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag)
+#define NB_LAUNCH_C(EQ)                                                                                               \
+    do {                                                                                                              \
+        if (L.force) k_collide_f<D, Q, EQ, true><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);  \
+        else k_collide_f<D, Q, EQ, false><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag);         \
+    } while (0)
+#define NB_LAUNCH_C_NOFORCE(EQ) k_collide_f<D, Q, EQ, false><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.rho, L.u, L.in_init, L.flag)
         if (L.eq == NB_EQ_BGK) NB_LAUNCH_C(NB_EQ_BGK);
         else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_C(NB_EQ_QUARTIC);
-        else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_C(NB_KIND_KBC)); }
-        else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_C(NB_KIND_MRT_ENTROPIC)); }
+        else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_C_NOFORCE(NB_KIND_KBC)); }
+        else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_C_NOFORCE(NB_KIND_MRT_ENTROPIC)); }
+        else if (L.eq == NB_KIND_REGULARIZED) { NB_IF_REG(NB_LAUNCH_C(NB_KIND_REGULARIZED)); }
+        else if (L.eq == NB_KIND_MRT) { NB_IF_MRT(NB_LAUNCH_C(NB_KIND_MRT)); }
         else return -1;
 #undef NB_LAUNCH_C
+#undef NB_LAUNCH_C_NOFORCE
     } else {
 #if NB_WITH_G
-        if (L.eq == NB_EQ_BGK) k_collide_fg<D, Q, NB_EQ_BGK><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);
-        else k_collide_fg<D, Q, NB_EQ_QUARTIC><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);
+#define NB_LAUNCH_CG(EQ)                                                                                              \
+    do {                                                                                                              \
+        if (L.force) k_collide_fg<D, Q, EQ, true><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);  \
+        else k_collide_fg<D, Q, EQ, false><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);         \
+    } while (0)
+        if (L.eq == NB_EQ_BGK) NB_LAUNCH_CG(NB_EQ_BGK);
+        else NB_LAUNCH_CG(NB_EQ_QUARTIC);
+#undef NB_LAUNCH_CG
 #else
         return -1;
 #endif
@@ -164,13 +203,23 @@ int conserved(const NbLaunch& L)
     return (int)cudaGetLastError();
 }
 
+int wall(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    if (L.n_hit_groups <= 0) return 0;
+    k_wall_hits<D, Q><<<grid_for(L.n_hit_groups, 64), 64, 0, L.stream>>>(L.n_hit_groups, L.hit_group_dof, L.hit_group_off, L.hit_dir,
+                                                                         L.hit_kind, L.hit_val, L.A.stride, L.yf, L.yg);
+    return (int)cudaGetLastError();
+}
+
 const NbStencilOps ops = {D, Q,
 #if NB_FUSE_F || (NB_WITH_G && NB_FUSE_G)
                           fused,
 #else
                           nullptr,
 #endif
-                          collide, conserved};
+                          collide, conserved, wall};
 
 }  // namespace
 

@@ -107,8 +107,10 @@ k_stream_collide_fg(StreamArgs A, const double* __restrict__ xf, const double* _
 // (= one DoF) takes its rows from there.  Dynamic shared memory: [tile(s)][staged values].
 // The descriptors of a pass's directions are parked in the tile slots their results will overwrite.
 // ---------------------------------------------------------------------------------------------
+// 5 CTAs per SM: 102 registers per thread (the BGK epilogue fits without spilling) and 5 x 36 KB of shared memory;
+// measured 0.76 ms per step against 0.83 ms at 4 CTAs on configuration 2 (profiles/).
 #ifndef NB_STAGED_OCC_F
-#define NB_STAGED_OCC_F 4
+#define NB_STAGED_OCC_F 5
 #endif
 __device__ __forceinline__ int2 nb_empty_desc(const StreamArgs& A, int alpha_m1)
 {
@@ -126,10 +128,11 @@ k_stream_collide_f_staged(StreamArgs A, const double* __restrict__ x, double* __
     double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_staged);   // [Q][128]
     double* xs = smem_staged + Q * NB_CTA_ROWS;                                              // [NB_STAGE_CAP]
     const int tid = threadIdx.x;
-    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const int64_t cta = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t row = cta * NB_CTA_ROWS + tid;
     const bool active = row < A.n_owned;
     tile[0][tid] = active ? x[row] : 0.0;
-    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    const int p0 = __ldg(A.stage_cta + cta), p1 = __ldg(A.stage_cta + cta + 1);
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();          // the previous pass's rows are done with xs
@@ -176,11 +179,12 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
     double* xsf = smem_staged + 2 * Q * NB_CTA_ROWS;
     double* xsg = xsf + NB_STAGE_CAP_FG;
     const int tid = threadIdx.x;
-    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const int64_t cta = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t row = cta * NB_CTA_ROWS + tid;
     const bool active = row < A.n_owned;
     tf[0][tid] = active ? xf[row] : 0.0;
     tg[0][tid] = active ? xg[row] : 0.0;
-    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    const int p0 = __ldg(A.stage_cta + cta), p1 = __ldg(A.stage_cta + cta + 1);
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();
@@ -223,8 +227,8 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
     for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
 }
 
-// Stand-alone collide (in place), f only.
-template <int D, int Q, int EQ>
+// Stand-alone collide (in place), f only.  FORCE: external-force hooks compiled in.
+template <int D, int Q, int EQ, bool FORCE>
 __global__ void __launch_bounds__(128)
 k_collide_f(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __restrict__ rho_out,
             double* __restrict__ u_out, int in_init, int* __restrict__ flag)
@@ -239,18 +243,23 @@ k_collide_f(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __rest
 #pragma unroll
         for (int j = 0; j < D; j++) v[j] = u_out[(int64_t)j * n + row];
     }
-    if (nb_collide_f<D, Q, EQ>(f, rho, v, in_init != 0, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
+    bool bad;
+    if constexpr (FORCE) bad = nb_collide_f_forced<D, Q, EQ>(f, rho, v, in_init != 0);
+    else bad = nb_collide_f<D, Q, EQ>(f, rho, v, in_init != 0, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0);
+    if (bad) *flag = 1;
 #pragma unroll
     for (int q = 0; q < Q; q++) fbuf[(int64_t)q * stride + row] = f[q];
     rho_out[row] = rho;
-    if (!in_init) {
+    // the exact-difference force shifts the stored velocity even in the initialization procedure
+    // (postCollisionApplyForces runs unconditionally, CollisionOperator.h:93-96)
+    if (!in_init || (FORCE && cP.force_type == 2)) {
 #pragma unroll
         for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = v[j];
     }
 }
 
 // Stand-alone collide (in place), f and g.
-template <int D, int Q, int EQ>
+template <int D, int Q, int EQ, bool FORCE>
 __global__ void __launch_bounds__(128)
 k_collide_fg(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf,
              double* __restrict__ rho_out, double* __restrict__ u_out, double* __restrict__ T_out,
@@ -264,12 +273,12 @@ k_collide_fg(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __res
         f[q] = fbuf[(int64_t)q * stride + row];
         g[q] = gbuf[(int64_t)q * stride + row];
     }
-    double rho, u[3], uo[3], T, sensor;
+    double rho, u[3], uo[3], T, sensor, vf[3] = {0.0, 0.0, 0.0};
     if (in_init) {
 #pragma unroll
         for (int j = 0; j < D; j++) uo[j] = u_out[(int64_t)j * n + row];
     }
-    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, in_init ? uo : nullptr);
+    nb_collide_bgk_fg<D, Q, EQ, FORCE>(f, g, rho, u, T, sensor, in_init ? uo : nullptr, vf);
     if (rho < 1e-10) *flag = 1;
 #pragma unroll
     for (int q = 0; q < Q; q++) {
@@ -279,9 +288,79 @@ k_collide_fg(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __res
     rho_out[row] = rho;
     T_out[row] = T;
     s_out[row] = sensor;
-    if (!in_init) {
+    if (FORCE) {
+        // u carries the equilibrium shift; the global vector gets raw moment * scaling + 0.5 dt F / rho (vf)
+        if (!in_init || cP.force_type == 2) {
+#pragma unroll
+            for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = vf[j];
+        }
+    } else if (!in_init) {
 #pragma unroll
         for (int j = 0; j < D; j++) u_out[(int64_t)j * n + row] = u[j] * cP.scaling;
+    }
+}
+
+// Wall hits after streaming (SemiLagrangianBoundaryHandler::operate, L/boundaries/SemiLagrangianBoundaryHandler.cpp:43-109).
+// Both wall models on the path only touch the destination DoF, so one thread owns one DoF and replays that DoF's
+// hits in the reference's iteration order; different DoFs are independent.
+//   kind 0  VelocityNeqBounceBack (VelocityNeqBounceBack.cpp:137-195): f[dir](idx) += value (= 2 w rho e.u_wall / cs2,
+//           evaluated by the host that owns the wall-velocity function)
+//   kind 1  ThermalBounceBack (ThermalBounceBack.cpp:50-109, D3Q45, gamma = 1.4 hard-wired there): f and g of the DoF
+//           are re-equilibrated to the wall temperature `value`
+template <int D, int Q>
+__global__ void __launch_bounds__(64)
+k_wall_hits(int64_t n_groups, const int32_t* __restrict__ group_dof, const int64_t* __restrict__ group_off,
+            const int32_t* __restrict__ hit_dir, const int32_t* __restrict__ hit_kind, const double* __restrict__ hit_val,
+            int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf)
+{
+    const int64_t grp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (grp >= n_groups) return;
+    const int64_t idx = group_dof[grp];
+    for (int64_t h = group_off[grp]; h < group_off[grp + 1]; h++) {
+        const int kind = hit_kind[h];
+        if (kind == 0) {
+            double* p = fbuf + (int64_t)hit_dir[h] * stride + idx;
+            *p = *p + hit_val[h];
+        } else if constexpr (D == 3 && Q == 45) {
+            const double gamma = 1.4, Tw = hit_val[h];
+            double fd[Q], gd[Q], feq[Q];
+#pragma unroll
+            for (int i = 0; i < Q; i++) {
+                fd[i] = fbuf[(int64_t)i * stride + idx];
+                gd[i] = gbuf[(int64_t)i * stride + idx];
+            }
+            const double rho = nb_density<Q>(fd);
+            double u[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int i = 0; i < Q; i++) sacc += cP.e[i][j] * fd[i];
+                u[j] = sacc * 1.0 / rho;
+            }
+            double T = 0.0;
+#pragma unroll
+            for (int i = 0; i < Q; i++) {
+                double sum = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; a++) sum += (cP.e[i][a] - u[a]) * (cP.e[i][a] - u[a]);
+                T += sum * fd[i] * cP.inv_cs2 + gd[i];
+            }
+            const double C_v = 1. / (gamma - 1.0);
+            T = T * 0.5 / (rho * C_v);
+            if (fabs(T - Tw) > 0.00001) {
+                nb_feq_quartic<D, Q>(rho, u, T, feq);
+#pragma unroll
+                for (int i = 0; i < Q; i++) fd[i] -= feq[i];
+                nb_feq_quartic<D, Q>(rho, u, Tw, feq);
+                const double gfac = (Tw) * (2.0 * C_v - D);
+#pragma unroll
+                for (int i = 0; i < Q; i++) {
+                    fbuf[(int64_t)i * stride + idx] = fd[i] + feq[i];
+                    gbuf[(int64_t)i * stride + idx] = feq[i] * gfac;
+                }
+            }
+        }
     }
 }
 

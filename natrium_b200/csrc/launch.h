@@ -7,6 +7,7 @@
 
 struct NbConst;
 struct NbMrtHost;
+struct NbMrtStdHost;
 
 struct NbLaunch {
     cudaStream_t stream;
@@ -22,6 +23,12 @@ struct NbLaunch {
     // constant-block ownership: the unit re-uploads when (owner, version) changed
     const NbConst* hc; const void* owner; uint64_t version;
     const NbMrtHost* mrt;   // MRTEntropic tables (D3Q19 unit only)
+    const NbMrtStdHost* mrt_std;   // MultipleRelaxationTime tables (D2Q9 / D3Q19 units)
+    int force;              // external-force hooks (stand-alone collide kernels)
+    unsigned grid_override; // staged kernels over a CTA subset (A.cta_map): number of CTAs to launch, 0 = all
+    // wall hits (k_wall_hits)
+    int64_t n_hit_groups; const int32_t* hit_group_dof; const int64_t* hit_group_off;
+    const int32_t* hit_dir; const int32_t* hit_kind; const double* hit_val;
     // conserved sums
     double* partial; int n_partial_blocks; double* out;
 };
@@ -31,6 +38,7 @@ struct NbStencilOps {
     int (*fused)(const NbLaunch&);       // stream + collide in one kernel; nullptr if not built
     int (*collide)(const NbLaunch&);     // in-place collide
     int (*conserved)(const NbLaunch&);   // deterministic conserved sums
+    int (*wall)(const NbLaunch&);        // wall hits on yf (and yg)
 };
 
 const NbStencilOps* nb_ops_d2q9();

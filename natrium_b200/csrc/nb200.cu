@@ -80,6 +80,14 @@ struct CsrBlock {
     double* val;
 };
 
+// one (neighbour, distribution, population) triple of the ghost exchange, see k_halo_pack
+struct NbHaloSeg {
+    int64_t idx_off;    // pack: first entry in send_idx; unpack: first ghost slot (relative to n_owned)
+    int64_t cnt;
+    int64_t buf_off;    // doubles from the start of the send / receive buffer
+    int32_t which, pop; // distribution (0 f, 1 g), population q
+};
+
 struct nb200_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t stream = nullptr;
@@ -136,15 +144,39 @@ struct nb200_ctx {
     bool collision_set = false;
     int kind = NB_EQ_BGK;                    // kernel template selector (NB_EQ_* / NB_KIND_*)
     NbMrtHost mrt;                           // MRTEntropic D3Q19 tables
+    NbMrtStdHost mrt_std;                    // MultipleRelaxationTime tables (nb200_set_mrt)
+    bool mrt_std_set = false;
     // halo
     int n_nbr = 0;
     std::vector<int32_t> nbr_rank;
     std::vector<int64_t> send_off, recv_off;
     int32_t* d_send_idx = nullptr;
-    int64_t *d_seg_send = nullptr, *d_seg_recv = nullptr, *d_send_off = nullptr, *d_recv_off = nullptr;
     int64_t n_send = 0, n_recv = 0;
     double *d_sendbuf = nullptr, *d_recvbuf = nullptr;
     ncclComm_t comm = nullptr;
+    // which ghost slots each streamed population reads (marked while the CSR blocks arrive): [(Q-1)][n_ghost]
+    std::vector<uint8_t> ghost_ref;
+    bool ghost_ref_any = false;
+    // exchange plans, built on first use: index = (pruned ? 4 : 0) + (f ? 1 : 0) + (g ? 2 : 0)
+    struct HaloPlan {
+        bool ready = false;
+        std::vector<NbHaloSeg> send_segs, recv_segs;
+        NbHaloSeg *d_send_segs = nullptr, *d_recv_segs = nullptr;
+        std::vector<int64_t> nbr_send_off, nbr_send_cnt, nbr_recv_off, nbr_recv_cnt;   // per neighbour, doubles
+        int64_t max_send_cnt = 0, max_recv_cnt = 0, send_total = 0, recv_total = 0;
+    } plans[8];
+    // wall hits (nb200_set_wall_hits), grouped by destination DoF in list order
+    int64_t n_hits = 0, n_hit_groups = 0;
+    bool hits_thermal = false;
+    int32_t *d_hit_group_dof = nullptr, *d_hit_dir = nullptr, *d_hit_kind = nullptr;
+    int64_t* d_hit_group_off = nullptr;
+    double* d_hit_val = nullptr;
+    // overlap of the exchange with the rows that read no ghost (staged kernels): second stream + CTA lists
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_prev = nullptr, ev_halo = nullptr;
+    int32_t *d_cta_interior = nullptr, *d_cta_boundary = nullptr;
+    int64_t n_cta_interior = 0, n_cta_boundary = 0;
+    bool overlap = true;
 };
 
 static const NbStencilOps* find_ops(int D, int Q);
@@ -238,7 +270,7 @@ __global__ void k_ell_pad(int64_t n_rows, int64_t n_slices, const int64_t* __res
     }
 }
 
-// dictionary pools: host layout [entry][K] -> device layout [K][stride] (k-major)
+// dictionary pools: host layout [pattern][K] -> device layout [(K+1)/2][P][2] (k-pair-major, nb_w_off)
 template <typename T>
 __global__ void k_pool_transpose(int64_t n, int K, int64_t stride, const T* __restrict__ in, T* __restrict__ out)
 {
@@ -246,7 +278,7 @@ __global__ void k_pool_transpose(int64_t n, int K, int64_t stride, const T* __re
     if (t >= n * K) return;
     const int64_t p = t / K;
     const int k = (int)(t - p * K);
-    out[(int64_t)k * stride + p] = in[t];
+    out[nb_w_off(k, stride) + 2 * p] = in[t];
 }
 
 // Stream only: y_alpha = sum_beta M_{alpha beta} x_beta, y_0 = x_0.  grid.y = Q (direction).
@@ -287,14 +319,15 @@ k_stream_staged(StreamArgs A, int Q, const double* __restrict__ x0, const double
     double* xs0 = xs_all;
     double* xs1 = xs_all + (NRHS == 2 ? cap : 0);
     const int tid = threadIdx.x;
-    const int64_t row = blockIdx.x * (int64_t)NB_CTA_ROWS + tid;
+    const int64_t cta = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t row = cta * NB_CTA_ROWS + tid;
     const bool active = row < A.n_owned;
     if (active) {
         y0[row] = x0[row];
         if (NRHS == 2) y1[row] = x1[row];
     }
     const int2 empty = make_int2((int)((unsigned)(NB_MAX_CLS - 1) << 16), 0);
-    const int p0 = __ldg(A.stage_cta + blockIdx.x), p1 = __ldg(A.stage_cta + blockIdx.x + 1);
+    const int p0 = __ldg(A.stage_cta + cta), p1 = __ldg(A.stage_cta + cta + 1);
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();
@@ -326,36 +359,24 @@ __global__ void k_permute_rows(int64_t n, int rows, const int32_t* __restrict__ 
     dst[(int64_t)r * dst_stride + k] = src[(int64_t)r * src_stride + map[k]];
 }
 
-// halo pack / unpack: buffer layout [neighbour segment][population][entry]
-__global__ void k_halo_pack(int64_t n_send, int n_pop, const int32_t* __restrict__ send_idx,
-                            const int64_t* __restrict__ seg_of, const int64_t* __restrict__ send_off,
-                            int64_t stride, const double* __restrict__ x, int q0, double* __restrict__ buf,
-                            int64_t buf_pop_base, int n_pop_total)
+// halo pack / unpack.  A segment = one (neighbour, distribution, population) triple that the receiving rank's
+// matrix actually reads; segments of one neighbour are contiguous in the buffer.
+__global__ void k_halo_pack(const NbHaloSeg* __restrict__ segs, const int32_t* __restrict__ send_idx, int64_t stride,
+                            const double* __restrict__ xf, const double* __restrict__ xg, double* __restrict__ buf)
 {
-    // entry k of neighbour s, population p -> buf[(send_off[s]*n_pop_total) + (buf_pop_base+p)*cnt_s + (k-send_off[s])]
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_send * n_pop) return;
-    const int p = (int)(t / n_send);
-    const int64_t k = t % n_send;
-    const int64_t s = seg_of[k];
-    const int64_t cnt = send_off[s + 1] - send_off[s];
-    buf[send_off[s] * n_pop_total + (buf_pop_base + p) * cnt + (k - send_off[s])] =
-        x[(int64_t)(q0 + p) * stride + send_idx[k]];
+    const NbHaloSeg sg = segs[blockIdx.y];
+    const double* __restrict__ x = (sg.which ? xg : xf) + (int64_t)sg.pop * stride;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < sg.cnt; e += (int64_t)gridDim.x * blockDim.x)
+        buf[sg.buf_off + e] = x[send_idx[sg.idx_off + e]];
 }
 
-__global__ void k_halo_unpack(int64_t n_recv, int n_pop, const int64_t* __restrict__ seg_of,
-                              const int64_t* __restrict__ recv_off, int64_t stride, int64_t n_owned,
-                              double* __restrict__ x, int q0, const double* __restrict__ buf,
-                              int64_t buf_pop_base, int n_pop_total)
+__global__ void k_halo_unpack(const NbHaloSeg* __restrict__ segs, int64_t stride, int64_t n_owned,
+                              double* __restrict__ xf, double* __restrict__ xg, const double* __restrict__ buf)
 {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= n_recv * n_pop) return;
-    const int p = (int)(t / n_recv);
-    const int64_t k = t % n_recv;
-    const int64_t s = seg_of[k];
-    const int64_t cnt = recv_off[s + 1] - recv_off[s];
-    x[(int64_t)(q0 + p) * stride + n_owned + k] =
-        buf[recv_off[s] * n_pop_total + (buf_pop_base + p) * cnt + (k - recv_off[s])];
+    const NbHaloSeg sg = segs[blockIdx.y];
+    double* __restrict__ x = (sg.which ? xg : xf) + (int64_t)sg.pop * stride + n_owned + sg.idx_off;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < sg.cnt; e += (int64_t)gridDim.x * blockDim.x)
+        x[e] = buf[sg.buf_off + e];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -392,6 +413,13 @@ extern "C" int nb200_create(nb200_ctx** out, int device, int rank, int nranks, c
         return NB200_ERR_CUDA;
     }
     if (nranks > 1) {
+        if (cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_prev, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess) { delete c; return NB200_ERR_CUDA; }
+        {
+            static const char* env = getenv("NB200_OVERLAP");      // experiments only: NB200_OVERLAP=0 serialises exchange and kernels
+            c->overlap = !(env && env[0] == '0');
+        }
         if (!nccl_unique_id || !g_nccl.load(c->err)) { delete c; return NB200_ERR_NCCL; }
         ncclUniqueId id;
         memcpy(&id, nccl_unique_id, sizeof(id));
@@ -436,8 +464,13 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     cudaFree(c->d_flag); cudaFree(c->d_partial);
     cudaFree(c->d_order); cudaFree(c->d_perm); cudaFree(c->d_stage);
     cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
-    cudaFree(c->d_seg_send); cudaFree(c->d_seg_recv); cudaFree(c->d_send_off); cudaFree(c->d_recv_off);
+    for (auto& pl : c->plans) { cudaFree(pl.d_send_segs); cudaFree(pl.d_recv_segs); }
+    cudaFree(c->d_cta_interior); cudaFree(c->d_cta_boundary);
+    cudaFree(c->d_hit_group_dof); cudaFree(c->d_hit_dir); cudaFree(c->d_hit_kind); cudaFree(c->d_hit_group_off); cudaFree(c->d_hit_val);
     if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->ev_prev) cudaEventDestroy(c->ev_prev);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -553,6 +586,10 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
     c->d_order = c->d_perm = nullptr; c->d_stage = nullptr;
     c->has_order = false;
     c->order.clear(); c->perm.clear();
+    c->ghost_ref.clear();
+    c->ghost_ref_any = false;
+    c->n_hits = c->n_hit_groups = 0;
+    for (auto& pl : c->plans) { cudaFree(pl.d_send_segs); cudaFree(pl.d_recv_segs); pl = nb200_ctx::HaloPlan(); }
     return NB200_OK;
 }
 
@@ -636,6 +673,17 @@ extern "C" int nb200_upload_block_csr(nb200_ctx* c, int bi, int bj, int64_t n_ro
     for (int64_t i = 0; i < n_rows; i++) if (rowptr[i + 1] < rowptr[i]) return fail(c, NB200_ERR_ARG, "upload_block_csr: rowptr not monotone");
     for (int64_t k = 0; k < nnz; k++)
         if (col[k] < 0 || col[k] >= c->n_owned + c->n_ghost) return fail(c, NB200_ERR_ARG, "upload_block_csr: column %d outside owned+ghost range", (int)col[k]);
+    // ghost slots population bj+1 is read at: drives the pruned halo exchange
+    if (c->matrix_ready || c->ghost_ref.size() != (size_t)(c->Q - 1) * c->n_ghost) {     // first block of a new matrix
+        c->ghost_ref.assign((size_t)(c->Q - 1) * c->n_ghost, 0);
+        c->ghost_ref_any = false;
+        for (auto& pl : c->plans) { cudaFree(pl.d_send_segs); cudaFree(pl.d_recv_segs); pl = nb200_ctx::HaloPlan(); }
+    }
+    if (c->n_ghost > 0) {
+        uint8_t* gr = c->ghost_ref.data() + (size_t)bj * c->n_ghost;
+        for (int64_t k = 0; k < nnz; k++) if (col[k] >= c->n_owned) gr[col[k] - c->n_owned] = 1;
+        c->ghost_ref_any = true;
+    }
     // internal DoF order: row k of the device matrix is user row order[k]; owned columns map through perm
     std::vector<int64_t> p_rowptr;
     std::vector<int32_t> p_col;
@@ -745,12 +793,13 @@ static int finalize_dict(nb200_ctx* c)
             const int64_t P = std::max<int64_t>(4, ((B.n_pats() + 3) / 4) * 4), NL = ((int64_t)K + 3) / 4 * 4;   // NL: list pitch
             double *dW = nullptr, *sW = nullptr;
             int32_t* dL = nullptr;
-            CUDA_TRY(c, cudaMalloc(&dW, (size_t)K * P * 8));
+            const size_t w_bytes_cls = (size_t)((K + 1) / 2) * 2 * P * 8;
+            CUDA_TRY(c, cudaMalloc(&dW, w_bytes_cls));
             c->pools.push_back(dW);
             const size_t l_bytes = (size_t)std::max<int64_t>(1, B.n_lists()) * NL * 4;
             CUDA_TRY(c, cudaMalloc(&dL, l_bytes));
             c->pools.push_back(dL);
-            CUDA_TRY(c, cudaMemsetAsync(dW, 0, (size_t)K * P * 8, c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(dW, 0, w_bytes_cls, c->stream));
             CUDA_TRY(c, cudaMemsetAsync(dL, 0, l_bytes, c->stream));
             CUDA_TRY(c, cudaMalloc(&sW, B.pats.size() * 8));
             CUDA_TRY(c, cudaMemcpyAsync(sW, B.pats.data(), B.pats.size() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -764,7 +813,7 @@ static int finalize_dict(nb200_ctx* c)
             H.W = dW; H.L = dL; H.K = K; H.P = P; H.NL = NL; H.streamed = streamed;
             c->dict_patterns += B.n_pats();
             c->dict_lists += B.n_lists();
-            c->dict_pool_bytes += (int64_t)K * P * 8 + (int64_t)l_bytes;
+            c->dict_pool_bytes += (int64_t)w_bytes_cls + (int64_t)l_bytes;
             c->dict_classes++;
             // the host copy of this class is not needed any more
             std::vector<double>().swap(B.pats);
@@ -797,6 +846,31 @@ static int finalize_dict(nb200_ctx* c)
         CUDA_TRY(c, cudaMemcpy(c->d_stage_pass, SB.passes.data(), SB.passes.size() * sizeof(NbStagePass), cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMalloc(&c->d_stage_cta, SB.cta_ptr.size() * sizeof(int32_t)));
         CUDA_TRY(c, cudaMemcpy(c->d_stage_cta, SB.cta_ptr.data(), SB.cta_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        {   // CTAs whose staged values include a ghost slot must wait for the halo exchange; the others overlap it
+            std::vector<int32_t> interior, boundary;
+            const int64_t n_cta = (int64_t)SB.cta_ptr.size() - 1;
+            for (int64_t b = 0; b < n_cta; b++) {
+                bool ghost = false;
+                for (int32_t pp = SB.cta_ptr[(size_t)b]; pp < SB.cta_ptr[(size_t)b + 1] && !ghost; pp++) {
+                    const auto& ps = SB.passes[(size_t)pp];
+                    for (int64_t e = ps.begin; e < ps.begin + ps.count; e++)
+                        if (SB.stage_col[(size_t)e] % c->stride >= c->n_owned) { ghost = true; break; }
+                }
+                (ghost ? boundary : interior).push_back((int32_t)b);
+            }
+            cudaFree(c->d_cta_interior); cudaFree(c->d_cta_boundary);
+            c->d_cta_interior = c->d_cta_boundary = nullptr;
+            c->n_cta_interior = (int64_t)interior.size();
+            c->n_cta_boundary = (int64_t)boundary.size();
+            if (!interior.empty()) {
+                CUDA_TRY(c, cudaMalloc(&c->d_cta_interior, interior.size() * sizeof(int32_t)));
+                CUDA_TRY(c, cudaMemcpy(c->d_cta_interior, interior.data(), interior.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
+            if (!boundary.empty()) {
+                CUDA_TRY(c, cudaMalloc(&c->d_cta_boundary, boundary.size() * sizeof(int32_t)));
+                CUDA_TRY(c, cudaMemcpy(c->d_cta_boundary, boundary.data(), boundary.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+            }
+        }
         c->cls0.resize((size_t)nb);
         for (int a = 0; a < nb; a++) c->cls0[(size_t)a] = hcls[(size_t)a * NB_MAX_CLS];
         c->staged = true;
@@ -881,9 +955,8 @@ extern "C" int nb200_set_halo(nb200_ctx* c, int n_nbr, const int32_t* nbr_rank, 
     if (!c || !c->stride || n_nbr < 0) return fail(c, NB200_ERR_ARG, "set_halo: call set_layout first");
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
-    cudaFree(c->d_seg_send); cudaFree(c->d_seg_recv); cudaFree(c->d_send_off); cudaFree(c->d_recv_off);
     c->d_send_idx = nullptr; c->d_sendbuf = c->d_recvbuf = nullptr;
-    c->d_seg_send = c->d_seg_recv = c->d_send_off = c->d_recv_off = nullptr;
+    for (auto& pl : c->plans) { cudaFree(pl.d_send_segs); cudaFree(pl.d_recv_segs); pl = nb200_ctx::HaloPlan(); }
     c->n_nbr = n_nbr;
     c->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
     c->send_off.assign(send_off, send_off + n_nbr + 1);
@@ -900,20 +973,6 @@ extern "C" int nb200_set_halo(nb200_ctx* c, int n_nbr, const int32_t* nbr_rank, 
         if (c->has_order) for (auto& v : si) v = c->perm[(size_t)v];
         CUDA_TRY(c, cudaMalloc(&c->d_send_idx, (size_t)c->n_send * sizeof(int32_t)));
         CUDA_TRY(c, cudaMemcpy(c->d_send_idx, si.data(), (size_t)c->n_send * sizeof(int32_t), cudaMemcpyHostToDevice));
-    }
-    {   // entry -> neighbour segment lookup for the pack / unpack kernels
-        std::vector<int64_t> tmp((size_t)std::max<int64_t>(1, c->n_send), 0);
-        for (int s = 0; s < n_nbr; s++) for (int64_t k = send_off[s]; k < send_off[s + 1]; k++) tmp[k] = s;
-        CUDA_TRY(c, cudaMalloc(&c->d_seg_send, tmp.size() * sizeof(int64_t)));
-        CUDA_TRY(c, cudaMemcpy(c->d_seg_send, tmp.data(), tmp.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-        tmp.assign((size_t)std::max<int64_t>(1, c->n_recv), 0);
-        for (int s = 0; s < n_nbr; s++) for (int64_t k = recv_off[s]; k < recv_off[s + 1]; k++) tmp[k] = s;
-        CUDA_TRY(c, cudaMalloc(&c->d_seg_recv, tmp.size() * sizeof(int64_t)));
-        CUDA_TRY(c, cudaMemcpy(c->d_seg_recv, tmp.data(), tmp.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-        CUDA_TRY(c, cudaMalloc(&c->d_send_off, (n_nbr + 1) * sizeof(int64_t)));
-        CUDA_TRY(c, cudaMemcpy(c->d_send_off, c->send_off.data(), (n_nbr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-        CUDA_TRY(c, cudaMalloc(&c->d_recv_off, (n_nbr + 1) * sizeof(int64_t)));
-        CUDA_TRY(c, cudaMemcpy(c->d_recv_off, c->recv_off.data(), (n_nbr + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
     }
     const int n_pop_total = (c->Q - 1) * (c->with_g ? 2 : 1);
     if (c->n_send) CUDA_TRY(c, cudaMalloc(&c->d_sendbuf, (size_t)c->n_send * n_pop_total * sizeof(double)));
@@ -1029,11 +1088,21 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
 {
     if (!c || !p || !c->stencil_set) return fail(c, NB200_ERR_ARG, "set_collision: call set_stencil first");
     if (p->viscosity <= 0 || p->dt <= 0) return fail(c, NB200_ERR_ARG, "set_collision: viscosity and dt must be positive");
-    if (p->scheme != NB200_BGK_STANDARD && p->scheme != NB200_KBC_STANDARD && p->scheme != NB200_MRT_ENTROPIC)
+    if (p->scheme != NB200_BGK_STANDARD && p->scheme != NB200_KBC_STANDARD && p->scheme != NB200_MRT_ENTROPIC
+        && p->scheme != NB200_BGK_REGULARIZED && p->scheme != NB200_MRT_STANDARD)
         return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- scheme %d", p->scheme);
+    if (p->has_external_force) {
+        // applyMacroscopicForces / applyForces (Aux...h:332-386)
+        if (p->force_type == NB200_NO_FORCING)
+            return fail(c, NB200_ERR_ARG, "Problem requires forcing scheme, but forcing was switched off. Please set forcing to SHIFTING_VELOCITY in the Solver Configuration.");
+        if (p->force_type != NB200_SHIFTING_VELOCITY && p->force_type != NB200_EXACT_DIFFERENCE)
+            return fail(c, NB200_ERR_UNSUPPORTED, "Force Type not implemented. Use Shifting Velocity instead.");
+        if (p->scheme == NB200_KBC_STANDARD || p->scheme == NB200_MRT_ENTROPIC)
+            return fail(c, NB200_ERR_UNSUPPORTED, "external forces are not part of the legacy entropic collideAll");
+    }
     if (p->equilibrium != NB200_BGK_EQUILIBRIUM && p->equilibrium != NB200_QUARTIC_EQUILIBRIUM) return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- equilibrium %d", p->equilibrium);
     if (!c->ops) return fail(c, NB200_ERR_UNSUPPORTED, "Collision model not implemented yet -- D%dQ%d", c->D, c->Q);
-    if (p->scheme != NB200_BGK_STANDARD) {
+    if (p->scheme == NB200_KBC_STANDARD || p->scheme == NB200_MRT_ENTROPIC) {
         // legacy entropic family: KBCStandard::collideAll (D2Q9, D3Q15; KBCStandard.cpp:70-85 throws otherwise),
         // MRTEntropic::collideAll (D3Q19; the D2Q9 branch of MRTEntropic.cpp:39-165 is not on the path)
         const bool kbc = p->scheme == NB200_KBC_STANDARD;
@@ -1054,6 +1123,25 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     // The dispatch table of selectCollision (CollisionSelection.h:85-91,141-149,179-202,251), restricted to
     // the stencils on the path.  Anything else throws "Collision model not implemented yet" there.
     int eq = p->equilibrium;
+    int kind_override = -1;
+    if (p->scheme == NB200_BGK_REGULARIZED || p->scheme == NB200_MRT_STANDARD) {
+        const int D = c->D, Q = c->Q;
+        const bool reg = p->scheme == NB200_BGK_REGULARIZED;
+        bool ok;
+        if (p->with_g) {
+            // reference quirk: the compressible BGK_REGULARIZED / BGK_EQUILIBRIUM row of D2Q25H instantiates the
+            // plain BGKCollision (CollisionSelection.h:150)
+            ok = reg && D == 2 && Q == 25 && eq == NB200_BGK_EQUILIBRIUM;
+        } else if (reg) {
+            ok = eq == NB200_BGK_EQUILIBRIUM && ((D == 2 && Q == 9) || (D == 3 && Q == 15) || (D == 3 && Q == 19));
+            kind_override = NB_KIND_REGULARIZED;
+        } else {
+            ok = eq == NB200_BGK_EQUILIBRIUM && ((D == 2 && Q == 9) || (D == 3 && Q == 19));
+            kind_override = NB_KIND_MRT;
+            if (ok && !c->mrt_std_set) return fail(c, NB200_ERR_ARG, "set_collision: MRT_STANDARD needs nb200_set_mrt() first");
+        }
+        if (!ok) return fail(c, NB200_ERR_UNSUPPORTED, "Severe error: Collision model not implemented yet -- cf. CollisionSelection.h (D%dQ%d, scheme %d, equilibrium %d, %s)", D, Q, p->scheme, eq, p->with_g ? "f+g" : "f");
+    } else
     {
         const int D = c->D, Q = c->Q;
         const bool bgk_eq = eq == NB200_BGK_EQUILIBRIUM;
@@ -1078,7 +1166,11 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     h.tau = p->viscosity / (p->dt * cs2_scaled) + 0.5;     // calculateTauFromNu
     h.inv_tau = 1.0 / h.tau;
     h.tau_legacy = p->viscosity / (p->dt * cs2_scaled);
-    c->kind = eq == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK;
+    c->kind = kind_override >= 0 ? kind_override : (eq == NB200_QUARTIC_EQUILIBRIUM ? NB_EQ_QUARTIC : NB_EQ_BGK);
+    h.has_force = p->has_external_force ? 1 : 0;
+    h.force_type = p->force_type;
+    for (int j = 0; j < 3; j++) h.force[j] = p->has_external_force ? p->force[j] : 0.0;
+    h.dt = p->dt;
     h.gamma = p->gamma;
     h.Cv = p->with_g ? 1. / (p->gamma - 1.0) : 0.0;
     h.prandtl = p->prandtl_set ? p->prandtl : (p->prandtl != 0.0 ? p->prandtl : 1.0);
@@ -1089,38 +1181,177 @@ extern "C" int nb200_set_collision(nb200_ctx* c, const nb200_collision_params* p
     return NB200_OK;
 }
 
+extern "C" int nb200_set_wall_hits(nb200_ctx* c, int64_t n_hits, const int32_t* dest_index, const int32_t* dest_direction,
+                                   const int32_t* kind, const double* value)
+{
+    if (!c || !c->stride || n_hits < 0) return fail(c, NB200_ERR_ARG, "set_wall_hits: call set_layout first");
+    if (n_hits > 0 && (!dest_index || !dest_direction || !kind || !value)) return fail(c, NB200_ERR_ARG, "set_wall_hits: null array");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    bool thermal = false;
+    for (int64_t h = 0; h < n_hits; h++) {
+        if (dest_index[h] < 0 || dest_index[h] >= c->n_owned) return fail(c, NB200_ERR_ARG, "set_wall_hits: destination index %d is not an owned DoF", (int)dest_index[h]);
+        if (dest_direction[h] < 0 || dest_direction[h] >= c->Q) return fail(c, NB200_ERR_ARG, "set_wall_hits: direction %d out of range", (int)dest_direction[h]);
+        if (kind[h] == NB200_WALL_THERMAL_BOUNCE_BACK) {
+            thermal = true;
+            if (!(c->D == 3 && c->Q == 45) || !c->with_g) return fail(c, NB200_ERR_UNSUPPORTED, "ThermalBounceBack needs D3Q45 with the g distribution (ThermalBounceBack.cpp:61)");
+        } else if (kind[h] != NB200_WALL_VELOCITY_NEQ_BOUNCE_BACK) {
+            return fail(c, NB200_ERR_UNSUPPORTED, "set_wall_hits: boundary kind %d is not on the path", (int)kind[h]);
+        }
+    }
+    cudaFree(c->d_hit_group_dof); cudaFree(c->d_hit_dir); cudaFree(c->d_hit_kind); cudaFree(c->d_hit_group_off); cudaFree(c->d_hit_val);
+    c->d_hit_group_dof = c->d_hit_dir = c->d_hit_kind = nullptr; c->d_hit_group_off = nullptr; c->d_hit_val = nullptr;
+    c->n_hits = n_hits; c->n_hit_groups = 0; c->hits_thermal = thermal;
+    if (n_hits == 0) return NB200_OK;
+    // group by destination DoF (internal numbering), keeping the list order inside a group
+    std::vector<int64_t> ord((size_t)n_hits);
+    for (int64_t h = 0; h < n_hits; h++) ord[(size_t)h] = h;
+    auto dof_of = [&](int64_t h) { return c->has_order ? c->perm[(size_t)dest_index[h]] : dest_index[h]; };
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return dof_of(a) < dof_of(b); });
+    std::vector<int32_t> gdof, hdir((size_t)n_hits), hkind((size_t)n_hits);
+    std::vector<int64_t> goff;
+    std::vector<double> hval((size_t)n_hits);
+    for (int64_t k = 0; k < n_hits; k++) {
+        const int64_t h = ord[(size_t)k];
+        if (k == 0 || dof_of(h) != gdof.back()) { gdof.push_back(dof_of(h)); goff.push_back(k); }
+        hdir[(size_t)k] = dest_direction[h]; hkind[(size_t)k] = kind[h]; hval[(size_t)k] = value[h];
+    }
+    goff.push_back(n_hits);
+    c->n_hit_groups = (int64_t)gdof.size();
+    CUDA_TRY(c, cudaMalloc(&c->d_hit_group_dof, gdof.size() * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_hit_group_off, goff.size() * 8));
+    CUDA_TRY(c, cudaMalloc(&c->d_hit_dir, (size_t)n_hits * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_hit_kind, (size_t)n_hits * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_hit_val, (size_t)n_hits * 8));
+    CUDA_TRY(c, cudaMemcpy(c->d_hit_group_dof, gdof.data(), gdof.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_hit_group_off, goff.data(), goff.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_hit_dir, hdir.data(), (size_t)n_hits * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_hit_kind, hkind.data(), (size_t)n_hits * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_hit_val, hval.data(), (size_t)n_hits * 8, cudaMemcpyHostToDevice));
+    return NB200_OK;
+}
+
+extern "C" int nb200_set_mrt(nb200_ctx* c, int Q, const double* M, const double* T, const double* omega)
+{
+    if (!c || !c->stencil_set || !M || !T || !omega) return fail(c, NB200_ERR_ARG, "set_mrt: call set_stencil first / null table");
+    if (Q != c->Q) return fail(c, NB200_ERR_ARG, "set_mrt: tables are for Q=%d, stencil has Q=%d", Q, c->Q);
+    if (!((c->D == 2 && Q == 9) || (c->D == 3 && Q == 19)))
+        return fail(c, NB200_ERR_UNSUPPORTED, "There seems to be no MRT model implemented for your stencil (D%dQ%d)", c->D, Q);
+    memset(&c->mrt_std, 0, sizeof(c->mrt_std));
+    for (int i = 0; i < Q; i++) {
+        for (int j = 0; j < Q; j++) { c->mrt_std.M[i][j] = M[i * Q + j]; c->mrt_std.T[i][j] = T[i * Q + j]; }
+        c->mrt_std.omega[i] = omega[i];
+    }
+    c->mrt_std_set = true;
+    c->const_version = ++g_const_stamp;
+    return NB200_OK;
+}
+
 // ---- halo -------------------------------------------------------------------------------------
-static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g)
+// Builds the exchange plan for the distributions in `mask` (bit 0 f, bit 1 g).  pruned: only the populations whose
+// ghost entries the receiver's matrix reads (the reference gets the same effect from the per-block column maps of
+// Epetra: block (alpha,alpha) imports only what its rows touch); otherwise every streamed population
+// (DistributionFunctions::updateGhosted).  The receivers' needs are swapped once over NCCL.
+static int halo_plan(nb200_ctx* c, int mask, bool pruned, nb200_ctx::HaloPlan** out)
+{
+    nb200_ctx::HaloPlan& P = c->plans[(pruned ? 4 : 0) + mask];
+    *out = &P;
+    if (P.ready) return NB200_OK;
+    const int npq = c->Q - 1, nn = c->n_nbr;
+    // need_recv[k][b]: population b+1 of the ghosts owned by neighbour k is read by this rank
+    std::vector<int32_t> need_recv((size_t)nn * npq, 1), need_send((size_t)nn * npq, 1);
+    if (pruned && c->ghost_ref_any) {
+        for (int k = 0; k < nn; k++)
+            for (int b = 0; b < npq; b++) {
+                int32_t any = 0;
+                const uint8_t* r = c->ghost_ref.data() + (size_t)b * c->n_ghost;
+                for (int64_t g = c->recv_off[(size_t)k]; g < c->recv_off[(size_t)k + 1] && !any; g++) any = r[g];
+                need_recv[(size_t)k * npq + b] = any;
+            }
+    }
+    if (pruned) {
+        int32_t *d_a = nullptr, *d_b = nullptr;
+        const size_t bytes = std::max<size_t>(4, (size_t)nn * npq * sizeof(int32_t));
+        CUDA_TRY(c, cudaMalloc(&d_a, bytes));
+        CUDA_TRY(c, cudaMalloc(&d_b, bytes));
+        CUDA_TRY(c, cudaMemcpyAsync(d_a, need_recv.data(), (size_t)nn * npq * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        NCCL_TRY(c, g_nccl.GroupStart());
+        for (int k = 0; k < nn; k++) {
+            NCCL_TRY(c, g_nccl.Send(d_a + (size_t)k * npq, (size_t)npq, 2 /* ncclInt32 */, c->nbr_rank[(size_t)k], c->comm, c->stream));
+            NCCL_TRY(c, g_nccl.Recv(d_b + (size_t)k * npq, (size_t)npq, 2, c->nbr_rank[(size_t)k], c->comm, c->stream));
+        }
+        NCCL_TRY(c, g_nccl.GroupEnd());
+        CUDA_TRY(c, cudaMemcpyAsync(need_send.data(), d_b, (size_t)nn * npq * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        cudaFree(d_a); cudaFree(d_b);
+    }
+    P.send_segs.clear(); P.recv_segs.clear();
+    P.nbr_send_off.assign((size_t)nn, 0); P.nbr_send_cnt.assign((size_t)nn, 0);
+    P.nbr_recv_off.assign((size_t)nn, 0); P.nbr_recv_cnt.assign((size_t)nn, 0);
+    int64_t so = 0, ro = 0;
+    P.max_send_cnt = P.max_recv_cnt = 0;
+    for (int k = 0; k < nn; k++) {
+        const int64_t scnt = c->send_off[(size_t)k + 1] - c->send_off[(size_t)k];
+        const int64_t rcnt = c->recv_off[(size_t)k + 1] - c->recv_off[(size_t)k];
+        P.nbr_send_off[(size_t)k] = so; P.nbr_recv_off[(size_t)k] = ro;
+        for (int w = 0; w < 2; w++) {
+            if (!(mask & (1 << w)) || (w == 1 && !c->with_g)) continue;
+            for (int b = 0; b < npq; b++) {
+                if (need_send[(size_t)k * npq + b] && scnt > 0) {
+                    P.send_segs.push_back(NbHaloSeg{c->send_off[(size_t)k], scnt, so, w, b + 1});
+                    so += scnt;
+                    P.max_send_cnt = std::max(P.max_send_cnt, scnt);
+                }
+                if (need_recv[(size_t)k * npq + b] && rcnt > 0) {
+                    P.recv_segs.push_back(NbHaloSeg{c->recv_off[(size_t)k], rcnt, ro, w, b + 1});
+                    ro += rcnt;
+                    P.max_recv_cnt = std::max(P.max_recv_cnt, rcnt);
+                }
+            }
+        }
+        P.nbr_send_cnt[(size_t)k] = so - P.nbr_send_off[(size_t)k];
+        P.nbr_recv_cnt[(size_t)k] = ro - P.nbr_recv_off[(size_t)k];
+    }
+    P.send_total = so; P.recv_total = ro;
+    if (!P.send_segs.empty()) {
+        CUDA_TRY(c, cudaMalloc(&P.d_send_segs, P.send_segs.size() * sizeof(NbHaloSeg)));
+        CUDA_TRY(c, cudaMemcpy(P.d_send_segs, P.send_segs.data(), P.send_segs.size() * sizeof(NbHaloSeg), cudaMemcpyHostToDevice));
+    }
+    if (!P.recv_segs.empty()) {
+        CUDA_TRY(c, cudaMalloc(&P.d_recv_segs, P.recv_segs.size() * sizeof(NbHaloSeg)));
+        CUDA_TRY(c, cudaMemcpy(P.d_recv_segs, P.recv_segs.data(), P.recv_segs.size() * sizeof(NbHaloSeg), cudaMemcpyHostToDevice));
+    }
+    P.ready = true;
+    return NB200_OK;
+}
+
+// One packed neighbour exchange of the current populations on stream `st`.
+static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true, cudaStream_t st = nullptr)
 {
     if (c->nranks == 1 || c->n_nbr == 0) return NB200_OK;
-    const int npq = c->Q - 1;
-    const int n_pop_total = npq * (c->with_g ? 2 : 1);
-    for (int w = 0; w < 2; w++) {
-        if ((w == 0 && !do_f) || (w == 1 && (!do_g || !c->with_g))) continue;
-        if (c->n_send) {
-            k_halo_pack<<<grid_for(c->n_send * npq, 256), 256, 0, c->stream>>>(
-                c->n_send, npq, c->d_send_idx, c->d_seg_send, c->d_send_off, c->stride, c->pop[w][c->cur[w]], 1,
-                c->d_sendbuf, (int64_t)w * npq, n_pop_total);
-            c->launches++;
-        }
+    if (!st) st = c->stream;
+    const int mask = (do_f ? 1 : 0) | ((do_g && c->with_g) ? 2 : 0);
+    if (!mask) return NB200_OK;
+    nb200_ctx::HaloPlan* P = nullptr;
+    int rc = halo_plan(c, mask, pruned, &P);
+    if (rc) return rc;
+    double* xf = c->pop[0][c->cur[0]];
+    double* xg = c->with_g ? c->pop[1][c->cur[1]] : nullptr;
+    if (!P->send_segs.empty()) {
+        dim3 grid((unsigned)std::min<int64_t>(64, (P->max_send_cnt + 255) / 256), (unsigned)P->send_segs.size());
+        k_halo_pack<<<grid, 256, 0, st>>>(P->d_send_segs, c->d_send_idx, c->stride, xf, xg, c->d_sendbuf);
+        c->launches++;
     }
-    // When only one of f/g is exchanged the other half of each segment is simply stale and ignored.
     NCCL_TRY(c, g_nccl.GroupStart());
     for (int s = 0; s < c->n_nbr; s++) {
-        const int64_t scnt = (c->send_off[s + 1] - c->send_off[s]) * n_pop_total;
-        const int64_t rcnt = (c->recv_off[s + 1] - c->recv_off[s]) * n_pop_total;
-        if (scnt) NCCL_TRY(c, g_nccl.Send(c->d_sendbuf + c->send_off[s] * n_pop_total, (size_t)scnt, ncclFloat64, c->nbr_rank[s], c->comm, c->stream));
-        if (rcnt) NCCL_TRY(c, g_nccl.Recv(c->d_recvbuf + c->recv_off[s] * n_pop_total, (size_t)rcnt, ncclFloat64, c->nbr_rank[s], c->comm, c->stream));
+        const int64_t scnt = P->nbr_send_cnt[(size_t)s], rcnt = P->nbr_recv_cnt[(size_t)s];
+        if (scnt) NCCL_TRY(c, g_nccl.Send(c->d_sendbuf + P->nbr_send_off[(size_t)s], (size_t)scnt, ncclFloat64, c->nbr_rank[(size_t)s], c->comm, st));
+        if (rcnt) NCCL_TRY(c, g_nccl.Recv(c->d_recvbuf + P->nbr_recv_off[(size_t)s], (size_t)rcnt, ncclFloat64, c->nbr_rank[(size_t)s], c->comm, st));
     }
     NCCL_TRY(c, g_nccl.GroupEnd());
-    for (int w = 0; w < 2; w++) {
-        if ((w == 0 && !do_f) || (w == 1 && (!do_g || !c->with_g))) continue;
-        if (c->n_recv) {
-            k_halo_unpack<<<grid_for(c->n_recv * npq, 256), 256, 0, c->stream>>>(
-                c->n_recv, npq, c->d_seg_recv, c->d_recv_off, c->stride, c->n_owned, c->pop[w][c->cur[w]], 1,
-                c->d_recvbuf, (int64_t)w * npq, n_pop_total);
-            c->launches++;
-        }
+    if (!P->recv_segs.empty()) {
+        dim3 grid((unsigned)std::min<int64_t>(64, (P->max_recv_cnt + 255) / 256), (unsigned)P->recv_segs.size());
+        k_halo_unpack<<<grid, 256, 0, st>>>(P->d_recv_segs, c->stride, c->n_owned, xf, xg, c->d_recvbuf);
+        c->launches++;
     }
     return NB200_OK;
 }
@@ -1129,7 +1360,7 @@ extern "C" int nb200_update_ghosted(nb200_ctx* c)
 {
     if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "update_ghosted: call set_layout first");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    return halo_exchange(c, true, true);
+    return halo_exchange(c, true, true, /*pruned=*/false);      // updateGhosted(): every ghost of every population
 }
 
 // ---- dispatch ----------------------------------------------------------------------------------
@@ -1139,6 +1370,7 @@ static StreamArgs stream_args(nb200_ctx* c)
     A.ell_val = c->ell_val; A.ell_idx = c->ell_idx; A.slice_off = c->d_slice_off;
     A.desc = c->d_desc; A.cls = c->d_cls; A.desc_stride = c->desc_stride;
     A.sdesc = c->d_sdesc; A.stage_col = c->d_stage_col; A.stage_pass = c->d_stage_pass; A.stage_cta = c->d_stage_cta;
+    A.cta_map = nullptr;
     for (int a = 0; a < NB_MAX_DIRS; a++) {
         const bool have = c->staged && a < (int)c->cls0.size();
         A.c0_W[a] = have ? c->cls0[(size_t)a].W : nullptr;
@@ -1156,18 +1388,24 @@ static const NbStencilOps* find_ops(int D, int Q)
     return nullptr;
 }
 
-static NbLaunch make_launch(nb200_ctx* c)
+static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0)
 {
     NbLaunch L;
     memset(&L, 0, sizeof(L));
     L.stream = c->stream;
     L.A = stream_args(c);
+    L.A.cta_map = cta_map;
+    L.grid_override = cta_map ? (unsigned)n_cta : 0u;
     L.rho = c->rho; L.u = c->u; L.T = c->T; L.sensor = c->sensor; L.flag = c->d_flag;
     L.eq = c->kind;
     L.mrt = c->kind == NB_KIND_MRT_ENTROPIC ? &c->mrt : nullptr;
+    L.mrt_std = c->kind == NB_KIND_MRT ? &c->mrt_std : nullptr;
+    L.force = c->cp.has_external_force ? 1 : 0;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
     L.fmt = (c->fmt == NB_FMT_DICT && c->staged) ? NB_FMT_STAGED : c->fmt;
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;
+    L.n_hit_groups = c->n_hit_groups; L.hit_group_dof = c->d_hit_group_dof; L.hit_group_off = c->d_hit_group_off;
+    L.hit_dir = c->d_hit_dir; L.hit_kind = c->d_hit_kind; L.hit_val = c->d_hit_val;
     L.partial = c->d_partial; L.n_partial_blocks = c->n_partial_blocks;
     L.out = c->d_partial ? c->d_partial + (size_t)c->n_partial_blocks * 5 : nullptr;
     return L;
@@ -1180,16 +1418,19 @@ static int cuda_rc(nb200_ctx* c, int rc, const char* what)
     return fail(c, NB200_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString((cudaError_t)rc));
 }
 
-static int dispatch_fused(nb200_ctx* c)
+// flip: swap the ping-pong buffers afterwards (false for the first of two partial launches of one step)
+static int dispatch_fused(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0, bool flip = true)
 {
-    NbLaunch L = make_launch(c);
+    NbLaunch L = make_launch(c, cta_map, n_cta);
     L.xf = c->pop[0][c->cur[0]];
     L.yf = c->pop[0][c->cur[0] ^ 1];
     if (c->cp.with_g) { L.xg = c->pop[1][c->cur[1]]; L.yg = c->pop[1][c->cur[1] ^ 1]; }
     int rc = cuda_rc(c, c->ops->fused(L), "fused stream+collide");
     if (rc) return rc;
-    c->cur[0] ^= 1;
-    if (c->cp.with_g) c->cur[1] ^= 1;
+    if (flip) {
+        c->cur[0] ^= 1;
+        if (c->cp.with_g) c->cur[1] ^= 1;
+    }
     c->launches++;
     return NB200_OK;
 }
@@ -1205,27 +1446,42 @@ static int dispatch_collide(nb200_ctx* c)
     return NB200_OK;
 }
 
-static int launch_stream(nb200_ctx* c, bool do_f, bool do_g)
+// SemiLagrangianBoundaryHandler::apply on the current (just streamed) f and the current g
+static int dispatch_wall(nb200_ctx* c)
 {
-    const StreamArgs A = stream_args(c);
+    if (c->n_hit_groups == 0) return NB200_OK;
+    if (!c->ops || !c->ops->wall) return fail(c, NB200_ERR_UNSUPPORTED, "wall hits: no kernels built for D%dQ%d", c->D, c->Q);
+    NbLaunch L = make_launch(c);
+    L.yf = c->pop[0][c->cur[0]];
+    L.yg = c->with_g ? c->pop[1][c->cur[1]] : nullptr;
+    int rc = cuda_rc(c, c->ops->wall(L), "wall hits");
+    if (rc) return rc;
+    c->launches++;
+    return NB200_OK;
+}
+
+static int launch_stream(nb200_ctx* c, bool do_f, bool do_g, const int32_t* cta_map = nullptr, int64_t n_cta = 0, bool flip = true)
+{
+    StreamArgs A = stream_args(c);
+    A.cta_map = cta_map;
     dim3 grid(grid_for(c->n_slices * 32, 128), (unsigned)c->Q);
     // the staged tables are sized for two distributions when the layout has g (NB_STAGE_CAP_FG), which a
     // single-distribution pass can use as well
     if (c->fmt == NB_FMT_DICT && c->staged) {
-        const unsigned g1 = grid_for(c->n_owned, NB_CTA_ROWS);
+        const unsigned g1 = cta_map ? (unsigned)n_cta : grid_for(c->n_owned, NB_CTA_ROWS);
         if (do_f && do_g) {
             static bool attr2 = false;
             const size_t sm = (size_t)2 * NB_STAGE_CAP_FG * sizeof(double);
             if (!attr2) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr2 = true; }
             k_stream_staged<2><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
-            c->cur[0] ^= 1; c->cur[1] ^= 1;
+            if (flip) { c->cur[0] ^= 1; c->cur[1] ^= 1; }
         } else {
             const int w = do_f ? 0 : 1;
             static bool attr1 = false;
             const size_t sm = (size_t)NB_STAGE_CAP * sizeof(double);
             if (!attr1) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr1 = true; }
             k_stream_staged<1><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
-            c->cur[w] ^= 1;
+            if (flip) c->cur[w] ^= 1;
         }
         c->launches++;
         return NB200_OK;
@@ -1264,6 +1520,7 @@ extern "C" int nb200_stream(nb200_ctx* c, int which)
     if (rc) return rc;
     if (c->n_slices == 0) return NB200_OK;
     rc = launch_stream(c, which == 0, which == 1);
+    if (!rc && which == 0) rc = dispatch_wall(c);     // m_boundaryHandler.apply(f, f_old, t) / apply(f, f_old, g, t)
     CUDA_TRY(c, cudaGetLastError());
     return rc;
 }
@@ -1287,7 +1544,8 @@ static bool use_fused(const nb200_ctx* c)
 {
     static const char* env = getenv("NB200_FUSE");   // experiments only: NB200_FUSE=0 forces stream + collide
     if (env && env[0] == '0') return false;
-    return c->ops->fused != nullptr && c->Q <= 25;
+    // a forced problem runs stream and collide as two kernels: the force hooks live in the stand-alone collide only
+    return c->ops->fused != nullptr && c->Q <= 25 && !c->cp.has_external_force;
 }
 
 extern "C" int nb200_step(nb200_ctx* c, int n_steps)
@@ -1297,14 +1555,49 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
     if (n_steps < 0) return fail(c, NB200_ERR_ARG, "step: n_steps < 0");
     if (c->cp.in_init) return fail(c, NB200_ERR_ARG, "step: in_init collisions are only available through nb200_collide");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    // With the staged kernels the exchange runs on its own stream while the CTAs that read no ghost slot work;
+    // the CTAs that do are launched behind it ("overlapped with interior-row SpMV").
+    const bool do_g = c->cp.with_g != 0;
+    const bool split = c->overlap && c->nranks > 1 && c->n_nbr > 0 && c->fmt == NB_FMT_DICT && c->staged
+        && c->n_cta_interior > 0 && c->n_cta_boundary > 0;
     for (int s = 0; s < n_steps; s++) {
-        rc = halo_exchange(c, true, c->cp.with_g != 0);
+        if (c->n_hit_groups > 0) {
+            // walls: reference order stream(f) -> wall hits (on the new f and the not yet streamed g) -> gStream -> collide
+            // (CompressibleCFDSolver.h:181-314); the hit kernel sits between the two streams, so nothing is fused
+            rc = halo_exchange(c, true, do_g);
+            if (!rc && c->n_slices > 0) rc = launch_stream(c, true, false);
+            if (!rc) rc = dispatch_wall(c);
+            if (!rc && do_g && c->n_slices > 0) rc = launch_stream(c, false, true);
+            if (!rc && c->n_owned > 0) rc = dispatch_collide(c);
+            if (rc) return rc;
+            continue;
+        }
+        if (split) {
+            CUDA_TRY(c, cudaEventRecord(c->ev_prev, c->stream));            // populations of the previous step are final
+            CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, c->ev_prev, 0));
+            rc = halo_exchange(c, true, do_g, true, c->comm_stream);
+            if (rc) return rc;
+            CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+            if (use_fused(c)) {
+                rc = dispatch_fused(c, c->d_cta_interior, c->n_cta_interior, false);
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+                if (!rc) rc = dispatch_fused(c, c->d_cta_boundary, c->n_cta_boundary, true);
+            } else {
+                rc = launch_stream(c, true, do_g, c->d_cta_interior, c->n_cta_interior, false);
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+                if (!rc) rc = launch_stream(c, true, do_g, c->d_cta_boundary, c->n_cta_boundary, true);
+                if (!rc) rc = dispatch_collide(c);
+            }
+            if (rc) return rc;
+            continue;
+        }
+        rc = halo_exchange(c, true, do_g);
         if (rc) return rc;
         if (c->n_slices == 0) continue;
         if (use_fused(c)) {
             rc = dispatch_fused(c);
         } else {
-            rc = launch_stream(c, true, c->cp.with_g != 0);
+            rc = launch_stream(c, true, do_g);
             if (!rc) rc = dispatch_collide(c);
         }
         if (rc) return rc;

@@ -23,13 +23,23 @@ struct NbConst {
     double tau_legacy;   // nu/(dt*cs2_scaled): relaxation parameter of the legacy CollisionModel family
     double gamma, Cv, prandtl;
     int prandtl_set, sutherland_set;
+    int has_force, force_type;      // problemDescription.hasExternalForce(), ForceType (ConfigNames.h:114-119)
+    double force[3];                // getExternalForce()->getForce()
+    double dt;
     int D, Q;
 };
 
 
 // collision kind = template parameter of the kernels: the two equilibria of the collision_advanced BGK
 // scheme, and the legacy entropic models
-enum { NB_EQ_BGK = 0, NB_EQ_QUARTIC = 1, NB_KIND_KBC = 2, NB_KIND_MRT_ENTROPIC = 3 };
+enum { NB_EQ_BGK = 0, NB_EQ_QUARTIC = 1, NB_KIND_KBC = 2, NB_KIND_MRT_ENTROPIC = 3, NB_KIND_REGULARIZED = 4, NB_KIND_MRT = 5 };
+
+// MultipleRelaxationTime tables (host copy, uploaded to the D2Q9 / D3Q19 units)
+struct NbMrtStdHost {
+    double M[19][19];
+    double T[19][19];
+    double omega[19];
+};
 
 // MRTEntropic D3Q19 moment matrix and inverse (host copy, uploaded to the D3Q19 unit)
 struct NbMrtHost {

@@ -34,9 +34,15 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
 #define NB_PAT_BITS (32 - NB_CLS_BITS)
 #define NB_PAT_MASK ((1u << NB_PAT_BITS) - 1u)
 
+// Weight pool layout of a class: pairs of consecutive entries of a pattern sit next to each other,
+// W[((k >> 1) * P + pattern) * 2 + (k & 1)], k-pair-major: the lanes of a warp hold different (neighbouring)
+// patterns, so one 16-byte load per lane fetches two weights from one or two adjacent lines.  Odd K is padded
+// with a zero weight.
+__host__ __device__ __forceinline__ int64_t nb_w_off(int k, int64_t P) { return (int64_t)(k >> 1) * (2 * P) + (k & 1); }
+
 // one row-length class of one direction
 struct NbDirClass {
-    const double* __restrict__ W;     // [K][P]  weight patterns, k-major (lanes of a warp hold different patterns)
+    const double* __restrict__ W;     // [(K+1)/2][P][2]  weight patterns, see nb_w_off
     const int32_t* __restrict__ L;    // [n_lists][NL] column lists (flat population index), list-major, 16-byte aligned rows
     int32_t K;
     int32_t streamed;                 // pools too large to stay cached: read with evict-first
@@ -64,6 +70,7 @@ struct StreamArgs {
     const int32_t* __restrict__ stage_col;   // flat population index of every staged support value, pass after pass
     const struct NbStagePass* __restrict__ stage_pass;
     const int32_t* __restrict__ stage_cta;   // [n_cta + 1] first pass of every CTA
+    const int32_t* __restrict__ cta_map;     // launch over a subset of the CTAs (interior / boundary lists); null = all
     // class 0 of every direction (the row length almost every row has) is described right here in the kernel
     // arguments, so the common case needs no dependent table load between descriptor and weights
     const double* c0_W[NB_MAX_DIRS];
@@ -132,7 +139,7 @@ __device__ __forceinline__ void nb_dict_accumulate(const double* __restrict__ W,
         const int32_t ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
         double vv[8], xa[8], xb[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
+        for (int j = 0; j < 8; j++) vv[j] = STREAMED ? __ldcs(W + nb_w_off(k + j, P)) : __ldg(W + nb_w_off(k + j, P));
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             xa[j] = __ldg(x0 + ii[j]);
@@ -149,7 +156,7 @@ __device__ __forceinline__ void nb_dict_accumulate(const double* __restrict__ W,
         const int32_t ii[4] = {i0.x, i0.y, i0.z, i0.w};
         double vv[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : __ldg(W + (int64_t)(k + j) * P);
+        for (int j = 0; j < 4; j++) vv[j] = STREAMED ? __ldcs(W + nb_w_off(k + j, P)) : __ldg(W + nb_w_off(k + j, P));
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             a0 += vv[j] * __ldg(x0 + ii[j]);
@@ -158,7 +165,7 @@ __device__ __forceinline__ void nb_dict_accumulate(const double* __restrict__ W,
     }
     for (; k < K; k++) {
         const int32_t ii = __ldg(L + k);
-        const double vv = __ldg(W + (int64_t)k * P);
+        const double vv = __ldg(W + nb_w_off(k, P));
         a0 += vv * __ldg(x0 + ii);
         if (NRHS == 2) a1 += vv * __ldg(x1 + ii);
     }
@@ -173,7 +180,7 @@ __device__ __forceinline__ void nb_row_dot_dict(const StreamArgs& A, int alpha_m
     const unsigned cw = (unsigned)d.y;
     const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + (cw >> NB_PAT_BITS);
     const int K = C->K;
-    const double* __restrict__ W = C->W + (cw & NB_PAT_MASK);
+    const double* __restrict__ W = C->W + 2 * (int64_t)(cw & NB_PAT_MASK);
     const int32_t* __restrict__ L = C->L + (int64_t)d.x * C->NL;     // NL = list pitch (K rounded up to 4)
     const int64_t P = C->P;
     double a0 = 0.0, a1 = 0.0;
@@ -205,38 +212,46 @@ __device__ __forceinline__ int2 nb_ld_once(const int2* p)
     return v;
 }
 
-// Staged row product: support values from shared memory (xs0/xs1 + off), weights from the k-major pattern pool.
-// Same summation order as the other formats (k = 0..K-1 as stored).  All weights of a batch are requested before
-// the first is used; the last batch is predicated (index clamped, weight forced to 0) instead of falling back to
-// one load at a time, so a row of K entries waits ceil(K / B) load latencies.
-template <int NRHS, bool STREAMED, int B>
-__device__ __forceinline__ void nb_staged_batches(const double* __restrict__ W, int K, int64_t P,
+// Staged row product: support values from shared memory (xs0/xs1 + off), weights from the pair-packed pattern pool:
+// one 16-byte global load feeds two multiply-adds.  Same summation order as the other formats (k = 0..K-1 as
+// stored).  All weights of a batch are requested before the first is used; batches are predicated (address clamped),
+// so a row of K entries waits ceil(ceil(K/2) / B2) load latencies.
+__device__ __forceinline__ double2 nb_ld_keep2(const double2* p)
+{
+    double2 v;
+    asm volatile("ld.global.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double2 nb_ld_stream2(const double2* p)
+{
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+template <int NRHS, bool STREAMED, int B2>
+__device__ __forceinline__ void nb_staged_batches(const double2* __restrict__ W2, int K, int64_t P,
                                                   const double* __restrict__ s0, const double* __restrict__ s1,
                                                   double& a0, double& a1)
 {
-    int k = 0;
-    for (; k + B <= K; k += B) {
-        double vv[B];
+    const int Kh = (K + 1) >> 1;
+    for (int kk = 0; kk < Kh; kk += B2) {
+        double2 vv[B2];
 #pragma unroll
-        for (int j = 0; j < B; j++) vv[j] = STREAMED ? __ldcs(W + (int64_t)(k + j) * P) : nb_ld_keep(W + (int64_t)(k + j) * P);
-#pragma unroll
-        for (int j = 0; j < B; j++) {
-            a0 += vv[j] * s0[k + j];
-            if (NRHS == 2) a1 += vv[j] * s1[k + j];
-        }
-    }
-    if (k < K) {
-        double vv[B];
-#pragma unroll
-        for (int j = 0; j < B; j++) {
-            const int kj = min(k + j, K - 1);
-            vv[j] = STREAMED ? __ldcs(W + (int64_t)kj * P) : nb_ld_keep(W + (int64_t)kj * P);
+        for (int j = 0; j < B2; j++) {
+            const int kj = min(kk + j, Kh - 1);
+            vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
         }
 #pragma unroll
-        for (int j = 0; j < B; j++) {
-            if (k + j < K) {
-                a0 += vv[j] * s0[k + j];
-                if (NRHS == 2) a1 += vv[j] * s1[k + j];
+        for (int j = 0; j < B2; j++) {
+            const int k = 2 * (kk + j);
+            if (k < K) {
+                a0 += vv[j].x * s0[k];
+                if (NRHS == 2) a1 += vv[j].x * s1[k];
+            }
+            if (k + 1 < K) {        // the staged lists are not padded: never touch the slot behind an odd list
+                a0 += vv[j].y * s0[k + 1];
+                if (NRHS == 2) a1 += vv[j].y * s1[k + 1];
             }
         }
     }
@@ -247,9 +262,10 @@ __device__ __forceinline__ void nb_staged_accumulate(const double* __restrict__ 
                                                      const double* __restrict__ s0, const double* __restrict__ s1,
                                                      double& a0, double& a1)
 {
-    // K = (p+1)^k on the path: 5 / 25 / 125 for the FE order of the benchmark configurations
-    if (K <= 8) nb_staged_batches<NRHS, STREAMED, 8>(W, K, P, s0, s1, a0, a1);
-    else nb_staged_batches<NRHS, STREAMED, 13>(W, K, P, s0, s1, a0, a1);
+    // K = (p+1)^k on the path: 5 / 25 / 125 for the FE order of the benchmark configurations -> 3 / 13 / 63 pairs
+    const double2* W2 = reinterpret_cast<const double2*>(W);
+    if (K <= 8) nb_staged_batches<NRHS, STREAMED, 4>(W2, K, P, s0, s1, a0, a1);
+    else nb_staged_batches<NRHS, STREAMED, 7>(W2, K, P, s0, s1, a0, a1);
 }
 
 template <int NRHS>
@@ -266,13 +282,13 @@ __device__ __forceinline__ void nb_row_dot_staged(const StreamArgs& A, int alpha
         K = kk & 0x3fffffff;
         streamed = kk >> 30;
         P = A.c0_P[alpha_m1];
-        W = A.c0_W[alpha_m1] + (unsigned)d.y;
+        W = A.c0_W[alpha_m1] + 2 * (int64_t)(unsigned)d.y;
     } else {
         const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + cls;
         K = C->K;
         streamed = C->streamed;
         P = C->P;
-        W = C->W + (unsigned)d.y;
+        W = C->W + 2 * (int64_t)(unsigned)d.y;
     }
     const double* __restrict__ s0 = xs0 + (dx & 0xffffu);
     const double* __restrict__ s1 = xs1 + (dx & 0xffffu);

@@ -14,13 +14,18 @@ NATriuM build it is deal.II (INTEGRATION.md shows the C++ shim against the real 
 """
 import numpy as np
 
-from . import _capi, harness
+from . import _capi, harness, mrt
 from ._capi import CollisionException  # noqa: F401  (re-exported like natrium::CollisionException)
 from .stencils import Stencil
 
 BGK_STANDARD, KBC_STANDARD, MRT_ENTROPIC = "BGK_STANDARD", "KBC_STANDARD", "MRT_ENTROPIC"
+BGK_REGULARIZED, MRT_STANDARD = "BGK_REGULARIZED", "MRT_STANDARD"
 BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM = "BGK_EQUILIBRIUM", "QUARTIC_EQUILIBRIUM"
-_SCHEMES = {BGK_STANDARD: _capi.BGK_STANDARD, KBC_STANDARD: _capi.KBC_STANDARD, MRT_ENTROPIC: _capi.MRT_ENTROPIC}
+NO_FORCING, SHIFTING_VELOCITY, EXACT_DIFFERENCE, GUO = _capi.NO_FORCING, _capi.SHIFTING_VELOCITY, _capi.EXACT_DIFFERENCE, _capi.GUO
+DELLAR_D2Q9, LALLEMAND_D2Q9, DHUMIERES_D3Q19 = mrt.DELLAR_D2Q9, mrt.LALLEMAND_D2Q9, mrt.DHUMIERES_D3Q19
+RELAX_FULL, DELLAR_RELAX_ONLY_N, RELAX_DHUMIERES_PAPER = mrt.RELAX_FULL, mrt.DELLAR_RELAX_ONLY_N, mrt.RELAX_DHUMIERES_PAPER
+_SCHEMES = {BGK_STANDARD: _capi.BGK_STANDARD, KBC_STANDARD: _capi.KBC_STANDARD, MRT_ENTROPIC: _capi.MRT_ENTROPIC,
+            BGK_REGULARIZED: _capi.BGK_REGULARIZED, MRT_STANDARD: _capi.MRT_STANDARD}
 _EQUILIBRIA = {BGK_EQUILIBRIUM: _capi.BGK_EQUILIBRIUM, QUARTIC_EQUILIBRIUM: _capi.QUARTIC_EQUILIBRIUM}
 
 
@@ -33,6 +38,15 @@ class SolverConfiguration:
         self._collision, self._equilibrium = BGK_STANDARD, BGK_EQUILIBRIUM
         self._gamma, self._prandtl, self._prandtl_set, self._sutherland = 1.4, 1.0, False, False
         self._n_steps = 0
+        # "MRT basis" = Dellar D2Q9, "MRT relaxation times" = Full, forcing off (SolverConfiguration.cpp:133-141)
+        self._mrt_basis, self._mrt_relax, self._forcing = DELLAR_D2Q9, RELAX_FULL, NO_FORCING
+
+    def setMRTBasis(self, b): self._mrt_basis = b
+    def getMRTBasis(self): return self._mrt_basis
+    def setMRTRelaxationTimes(self, r): self._mrt_relax = r
+    def getMRTRelaxationTimes(self): return self._mrt_relax
+    def setForcingScheme(self, f): self._forcing = f
+    def getForcingScheme(self): return self._forcing
 
     def setStencil(self, s): self._stencil = s if s.startswith("Stencil_") else "Stencil_" + s
     def getStencil(self): return self._stencil
@@ -132,6 +146,27 @@ class SemiLagrangian:
         pass   # periodic problems: SemiLagrangianBoundaryHandler has no hits
 
 
+def _apply_collision_setup(ctx, configuration, problemDescription, stencil, viscosity, delta_t, with_g, in_init=False):
+    """What GeneralCollisionData + SpecificCollisionData pull out of the configuration, the problem and the stencil
+    (AuxiliaryCollisionFunctions.h:151-200, CollisionSchemes.h:209-236), flattened for the C ABI."""
+    scheme = configuration.getCollisionScheme()
+    if scheme == MRT_STANDARD and stencil.getQ() in (9, 19) and not with_g:
+        cs2 = stencil.getSpeedOfSoundSquare()
+        tau = viscosity / (delta_t * cs2) + 0.5          # calculateTauFromNu
+        basis = configuration.getMRTBasis()
+        if (stencil.getQ() == 9) != (basis in (DELLAR_D2Q9, LALLEMAND_D2Q9)):
+            raise CollisionException(_capi.NB200_ERR_UNSUPPORTED, f"MRT basis not defined for Q={stencil.getQ()}")
+        ctx.set_mrt(mrt.make_M(basis), mrt.make_T(basis), mrt.make_diag(tau, basis, configuration.getMRTRelaxationTimes()))
+    has_force = getattr(problemDescription, "hasExternalForce", lambda: False)()
+    ctx.set_collision(viscosity, delta_t, scheme=_SCHEMES[scheme],
+                      equilibrium=_EQUILIBRIA[configuration.getEquilibriumScheme()], with_g=with_g, in_init=in_init,
+                      gamma=configuration.getHeatCapacityRatioGamma(),
+                      prandtl=configuration.getPrandtlNumber() if configuration.isPrandtlNumberSet() else None,
+                      sutherland=configuration.isSutherlandLawSet(),
+                      force=problemDescription.getExternalForce().getForce() if has_force else None,
+                      force_type=configuration.getForcingScheme())
+
+
 def selectCollision(configuration, problemDescription, f, *args):
     """Both reference overloads:
        selectCollision(cfg, pd, f, densities, velocities, owned, viscosity, delta_t, stencil, inInit)
@@ -146,11 +181,7 @@ def selectCollision(configuration, problemDescription, f, *args):
     ctx = f._ctx
     if configuration.getStencil() != stencil.getStencilType():
         raise CollisionException(_capi.NB200_ERR_UNSUPPORTED, "Severe error: Collision model not implemented yet -- cf. CollisionSelection.h")
-    ctx.set_collision(viscosity, delta_t, scheme=_SCHEMES[configuration.getCollisionScheme()],
-                      equilibrium=_EQUILIBRIA[configuration.getEquilibriumScheme()], with_g=with_g, in_init=in_init,
-                      gamma=configuration.getHeatCapacityRatioGamma(),
-                      prandtl=configuration.getPrandtlNumber() if configuration.isPrandtlNumberSet() else None,
-                      sutherland=configuration.isSutherlandLawSet())
+    _apply_collision_setup(ctx, configuration, problemDescription, stencil, viscosity, delta_t, with_g, in_init)
     if in_init:
         ctx.upload_velocity(np.asarray(velocities))
     ctx.collide()
@@ -208,11 +239,7 @@ class CFDSolver:
 
     def _configure_collision(self):
         cfg = self.m_configuration
-        self.ctx.set_collision(self.m_viscosity, self.getTimeStepSize(), scheme=_SCHEMES[cfg.getCollisionScheme()],
-                               equilibrium=_EQUILIBRIA[cfg.getEquilibriumScheme()], with_g=self._with_g,
-                               gamma=cfg.getHeatCapacityRatioGamma(),
-                               prandtl=cfg.getPrandtlNumber() if cfg.isPrandtlNumberSet() else None,
-                               sutherland=cfg.isSutherlandLawSet())
+        _apply_collision_setup(self.ctx, cfg, self.m_problem, self.m_stencil, self.m_viscosity, self.getTimeStepSize(), self._with_g)
 
     def stream(self):
         self.m_advectionOperator.stream(self.m_f, self.m_f, self.m_time)

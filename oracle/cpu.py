@@ -102,6 +102,100 @@ def collide_bgk_fg(st, f, g, viscosity, dt, equilibrium=1, gamma=1.4, prandtl=No
     return rho, u, T, mss, rc
 
 
+_GOLDEN = os.path.join(os.path.dirname(_HERE), "tests", "golden", "mrt_tables.npz")
+_MRT_NAMES = {"DELLAR_D2Q9": "MRTDellarD2Q9", "LALLEMAND_D2Q9": "MRTLallemandD2Q9", "DHUMIERES_D3Q19": "MRTDHumieresD3Q19"}
+
+
+def mrt_tables(basis):
+    """(M, T) of AuxiliaryMRTFunctions::make_M / make_T: the reference's own literals, extracted once by
+    tests/golden/make_mrt_golden.py (AuxiliaryMRTFunctions.cpp:15-205)."""
+    g = np.load(_GOLDEN)
+    n = _MRT_NAMES[basis]
+    return np.ascontiguousarray(g[n + "_moment_trafo"]), np.ascontiguousarray(g[n + "_inverse_trafo"])
+
+
+def mrt_diag(tau, basis, relax_mode="RELAX_FULL"):
+    """make_diag (AuxiliaryMRTFunctions.cpp:226-404)."""
+    if basis in ("DELLAR_D2Q9", "LALLEMAND_D2Q9"):
+        d = np.full(9, 1.0 / tau)
+        if relax_mode == "RELAX_FULL":
+            d[6] = d[7] = d[8] = 1.0
+        elif relax_mode == "DELLAR_RELAX_ONLY_N":
+            assert basis == "DELLAR_D2Q9"
+            d[8] = 1.0
+        else:
+            raise ValueError("MRT relaxation not defined")
+        return d
+    d = np.full(19, 1.0 / tau)
+    if relax_mode == "RELAX_FULL":
+        for i in (4, 6, 8, 10, 12, 2, 16, 17, 18):
+            d[i] = 1.0
+    elif relax_mode == "RELAX_DHUMIERES_PAPER":
+        s9 = s13 = 1.0 / tau
+        s1, s2, s10, s4, s16 = 1.19, 1.4, 1.4, 1.2, 1.98
+        d = np.array([0, s1, s2, 0, s4, 0, s4, 0, s4, s9, s10, s9, s10, s13, s13, s13, s16, s16, s16], dtype=np.float64)
+    else:
+        raise ValueError("MRT relaxation not defined")
+    return d
+
+
+_ADV_SCHEMES = {"BGK_STANDARD": 0, "BGK_REGULARIZED": 1, "MRT_STANDARD": 2}
+_FORCE_TYPES = {"NO_FORCING": 0, "SHIFTING_VELOCITY": 1, "EXACT_DIFFERENCE": 2, "GUO": 3}
+
+
+def collide_advanced(st, f, viscosity, dt, scheme="BGK_STANDARD", equilibrium=0, in_init=False, u_init=None,
+                     force=None, force_type="NO_FORCING", mrt_basis=None, relax_mode="RELAX_FULL", n=None):
+    """In-place collideAll (f only) for every scheme of selectCollision on the path, with the external-force hooks.
+    Returns (rho, u_scaled, status); status -2 / -3 mirror the NATriuMException / NotImplementedException of the
+    force helpers."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    rho = np.zeros(n)
+    u = np.zeros((st.D, n)) if u_init is None else np.ascontiguousarray(u_init, dtype=np.float64)
+    M = T = om = np.zeros(1)
+    if scheme == "MRT_STANDARD":
+        M, T = mrt_tables(mrt_basis)
+        om = mrt_diag(viscosity / (dt * st.cs2) + 0.5, mrt_basis, relax_mode)
+    fv = np.zeros(3)
+    if force is not None:
+        fv[:len(force)] = force
+    rc = lib().orc_collide_advanced_f(
+        C.c_int(st.D), C.c_int(Q), C.c_int64(n), C.c_int64(stride), _d(f), _d(rho), _d(u), _d(st.e), _d(st.w),
+        C.c_double(st.scaling), C.c_double(st.cs2), C.c_double(viscosity), C.c_double(dt), C.c_int(equilibrium),
+        C.c_int(_ADV_SCHEMES[scheme]), C.c_int(1 if in_init else 0), C.c_int(0 if force is None else 1),
+        C.c_int(_FORCE_TYPES[force_type]), _d(fv), _d(M), _d(T), _d(om))
+    return rho, u, rc
+
+
+def collide_bgk_fg_forced(st, f, g, viscosity, dt, force, force_type, equilibrium=1, gamma=1.4, prandtl=None,
+                          sutherland=False, n=None):
+    """collide_bgk_fg with hasExternalForce() == true."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    rho, T, mss = np.zeros(n), np.zeros(n), np.zeros(n)
+    u = np.zeros((st.D, n))
+    fv = np.zeros(3)
+    fv[:len(force)] = force
+    rc = lib().orc_collide_bgk_fg_forced(
+        C.c_int(st.D), C.c_int(Q), C.c_int64(n), C.c_int64(stride), _d(f), _d(g), _d(rho), _d(u), _d(T), _d(mss),
+        _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2), C.c_double(viscosity), C.c_double(dt),
+        C.c_int(equilibrium), C.c_double(gamma), C.c_int(0 if prandtl is None else 1),
+        C.c_double(1.0 if prandtl is None else prandtl), C.c_int(1 if sutherland else 0), C.c_int(0),
+        C.c_int(_FORCE_TYPES[force_type]), _d(fv))
+    return rho, u, T, mss, rc
+
+
+def apply_wall_hits(st, f, g, dest_index, dest_dir, kind, value):
+    """SemiLagrangianBoundaryHandler::apply over a flattened hit list, in place on f (post-stream) and g."""
+    di = np.ascontiguousarray(dest_index, dtype=np.int32)
+    dd = np.ascontiguousarray(dest_dir, dtype=np.int32)
+    kk = np.ascontiguousarray(kind, dtype=np.int32)
+    vv = np.ascontiguousarray(value, dtype=np.float64)
+    return lib().orc_apply_wall_hits(C.c_int(st.D), C.c_int(st.Q), C.c_int64(f.shape[1]), _d(f), None if g is None else _d(g),
+                                     C.c_int64(len(di)), di.ctypes.data_as(_i32p), dd.ctypes.data_as(_i32p),
+                                     kk.ctypes.data_as(_i32p), _d(vv), _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2))
+
+
 def collide_entropic(st, f, viscosity, dt, scheme, in_init=False, u_init=None, rho_prev=None, n=None):
     """Legacy entropic collideAll in place.  scheme: "KBC_STANDARD" (D2Q9, D3Q15; KBCStandard.cpp:88-1028) or
     "MRT_ENTROPIC" (D3Q19; MRTEntropic.cpp:167-305).  tau is the legacy nu/(dt cs2).  Returns (rho, u_scaled, status)."""

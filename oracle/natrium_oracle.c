@@ -605,6 +605,63 @@ int orc_collide_advanced_f(int D, int Q, int64_t n, int64_t stride, double *f, d
     return bad ? -1 : 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Wall hits after streaming: SemiLagrangianBoundaryHandler::apply / operate
+ * (L/boundaries/SemiLagrangianBoundaryHandler.cpp:26-109) over a flattened hit list in HitList
+ * iteration order.  kind 0: VelocityNeqBounceBack::calculateBoundaryValues
+ * (L/boundaries/VelocityNeqBounceBack.cpp:137-195): f_new[dir](idx) += 2 w_dir rho (e_dir . u_wall) / cs2 with
+ * rho = 1 -- the term is evaluated by the host (it owns the wall-velocity function) and arrives in value[].
+ * kind 1: ThermalBounceBack::calculateBoundaryValues (L/boundaries/ThermalBounceBack.cpp:50-109): D3Q45 only,
+ * gamma fixed to 1.4 there; re-equilibrates f and g of the destination DoF to the wall temperature value[].
+ * f is the post-stream f, g the not-yet-streamed g (CompressibleCFDSolver.h:194-195: the BC runs before gStream).
+ * ------------------------------------------------------------------------------------------ */
+int orc_apply_wall_hits(int D, int Q, int64_t stride, double *f, double *g, int64_t n_hits,
+                        const int32_t *dest_index, const int32_t *dest_dir, const int32_t *kind, const double *value,
+                        const double *e_scaled, const double *w, double scaling, double cs2_scaled)
+{
+    orc_params P;
+    orc_make_params(&P, D, Q, e_scaled, w, scaling, cs2_scaled, 1.0, 1.0);
+    for (int64_t h = 0; h < n_hits; h++) {
+        const int64_t idx = dest_index[h];
+        if (kind[h] == 0) {
+            f[(int64_t)dest_dir[h] * stride + idx] = f[(int64_t)dest_dir[h] * stride + idx] + value[h];
+        } else if (kind[h] == 1) {
+            if (Q != 45 || !g) return -3;
+            const double gamma = 1.4, Tw = value[h];
+            double fd[ORC_MAXQ], gd[ORC_MAXQ], feq[ORC_MAXQ], geq[ORC_MAXQ], u[3] = {0, 0, 0};
+            for (int i = 0; i < Q; i++) { fd[i] = f[(int64_t)i * stride + idx]; gd[i] = g[(int64_t)i * stride + idx]; }
+            const double rho = orc_density(fd, Q);
+            for (int j = 0; j < D; j++) {          /* calculateVelocity(f, u, rho, e), Aux...h:244-255 */
+                u[j] = 0.0;
+                for (int i = 0; i < Q; i++) u[j] += P.e[i][j] * fd[i];
+                u[j] = u[j] * 1.0 / rho;
+            }
+            double T = 0.0;                        /* calculateTemperature(f, g, u, rho, e, cs2, gamma), :309-325 */
+            for (int i = 0; i < Q; i++) {
+                double sum = 0.0;
+                for (int a = 0; a < D; a++) sum += (P.e[i][a] - u[a]) * (P.e[i][a] - u[a]);
+                T += sum * fd[i] / P.cs2 + gd[i];
+            }
+            const double C_v = 1. / (gamma - 1.0);
+            T = T * 0.5 / (rho * C_v);
+            if (fabs(T - Tw) > 0.00001) {
+                orc_feq_quartic(&P, rho, u, T, feq);
+                for (int i = 0; i < Q; i++) geq[i] = feq[i] * (T) * (2.0 * C_v - D);
+                for (int i = 0; i < Q; i++) { fd[i] -= feq[i]; gd[i] -= geq[i]; }
+                orc_feq_quartic(&P, rho, u, Tw, feq);
+                for (int i = 0; i < Q; i++) geq[i] = feq[i] * (Tw) * (2.0 * C_v - D);
+                for (int i = 0; i < Q; i++) {
+                    f[(int64_t)i * stride + idx] = fd[i] + feq[i];
+                    g[(int64_t)i * stride + idx] = geq[i];
+                }
+            }
+        } else {
+            return -3;
+        }
+    }
+    return 0;
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

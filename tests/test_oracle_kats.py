@@ -226,3 +226,93 @@ def test_entropic_dispatch_matches_reference(oracle_lib):
         oracle_lib.collide_entropic(oracle_lib.Stencil("D3Q19", 1.0), np.ones((19, 4)), 0.1, 0.1, "KBC_STANDARD")
     with pytest.raises(ValueError):
         oracle_lib.collide_entropic(oracle_lib.Stencil("D3Q15", 1.0), np.ones((15, 4)), 0.1, 0.1, "MRT_ENTROPIC")
+
+
+# ---------------------------------------------------------------------------------------------
+# collision_advanced Regularized / MultipleRelaxationTime / forcing
+# ---------------------------------------------------------------------------------------------
+def _relaxation_test_f(Q):
+    """Relaxation_test.cpp:37-40: f_i = 1.5 + sin(1.5 i) + 0.001 + i/(i+1) + (0.5 cos 0.5)^2, integer i/(i+1) = 0."""
+    i = np.arange(Q, dtype=np.float64)
+    return (1.5 + np.sin(1.5 * i) + 0.001 + (0.5 * math.cos(0.5)) ** 2)[:, None].copy()
+
+
+def test_mrt_tables_golden_vs_product():
+    """The product's host mirror rebuilds the three MRT bases from their definitions; the oracle uses the reference's
+    literals (tests/golden/mrt_tables.npz, AuxiliaryMRTFunctions.cpp:15-205).  They agree to round-off, M T = I,
+    and make_diag matches entry by entry."""
+    from natrium_b200 import mrt
+    for pb, ob in [(mrt.DELLAR_D2Q9, "DELLAR_D2Q9"), (mrt.LALLEMAND_D2Q9, "LALLEMAND_D2Q9"), (mrt.DHUMIERES_D3Q19, "DHUMIERES_D3Q19")]:
+        M, T = cpu.mrt_tables(ob)
+        assert np.array_equal(mrt.make_M(pb), M)
+        assert np.max(np.abs(mrt.make_T(pb) - T)) <= 1e-16
+        assert np.max(np.abs(M @ T - np.eye(len(M)))) <= 1e-15
+        for pm, om in [(mrt.RELAX_FULL, "RELAX_FULL")] + ([(mrt.DELLAR_RELAX_ONLY_N, "DELLAR_RELAX_ONLY_N")] if ob == "DELLAR_D2Q9" else []) \
+                + ([(mrt.RELAX_DHUMIERES_PAPER, "RELAX_DHUMIERES_PAPER")] if ob == "DHUMIERES_D3Q19" else []):
+            assert np.array_equal(mrt.make_diag(0.8, pb, pm), cpu.mrt_diag(0.8, ob, om))
+
+
+def test_relaxation_regularized(oracle_lib):
+    """Relaxation_Regularized_test (Relaxation_test.cpp:30-68): the x-velocity recomputed from the relaxed populations
+    stays what calculateVelocity gives (the test's bound is 1e-5; momentum is conserved to round-off)."""
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    f = _relaxation_test_f(9)
+    before = f.copy()
+    rho, u, rc = oracle_lib.collide_advanced(st, f, 1.0, 0.1, scheme="BGK_REGULARIZED")
+    assert rc == 0
+    ux = (f[1] - f[3] + f[5] - f[6] - f[7] + f[8]) / rho
+    assert abs(ux[0] - u[0, 0]) < 1e-5
+    assert abs(f.sum() - before.sum()) <= 1e-13 * before.sum()
+    assert np.max(np.abs(st.e.T @ f - st.e.T @ before)) <= 1e-13 * before.sum()
+
+
+@pytest.mark.parametrize("name,basis", [("D2Q9", "DELLAR_D2Q9"), ("D2Q9", "LALLEMAND_D2Q9"), ("D3Q19", "DHUMIERES_D3Q19")])
+def test_relaxation_mrt_conserves(name, basis, oracle_lib):
+    """Relaxation_MRT_D2Q9_test / _D3Q19_test (:74-196): density and velocity unchanged to 1e-10 % by the MRT
+    relaxation; scaling 4, dt 0.1, viscosity 1."""
+    st = oracle_lib.Stencil(name, 4.0)
+    f = _relaxation_test_f(st.Q)
+    rho0 = f.sum(0)
+    u0 = (st.e / st.scaling).T @ f / rho0
+    _, _, rc = oracle_lib.collide_advanced(st, f, 1.0, 0.1, scheme="MRT_STANDARD", mrt_basis=basis)
+    assert rc == 0
+    rho1 = f.sum(0)
+    u1 = (st.e / st.scaling).T @ f / rho1
+    assert abs(rho1[0] - rho0[0]) <= 1e-12 * rho0[0]
+    assert np.max(np.abs(u1 - u0)) <= 1e-12 * np.max(np.abs(u0))
+
+
+def test_relaxation_equiv_mrt_regularized(oracle_lib):
+    """Relaxation_Equiv_MRT_Reg_test (:200-255): Dellar-D2Q9 MRT with full relaxation of the ghost moments equals the
+    regularized scheme to 1e-10 %."""
+    st = oracle_lib.Stencil("D2Q9", 4.0)
+    f1, f2 = _relaxation_test_f(9), _relaxation_test_f(9)
+    oracle_lib.collide_advanced(st, f1, 1.0, 0.1, scheme="MRT_STANDARD", mrt_basis="DELLAR_D2Q9")
+    oracle_lib.collide_advanced(st, f2, 1.0, 0.1, scheme="BGK_REGULARIZED")
+    assert np.max(np.abs(f1 - f2) / np.abs(f2)) <= 1e-12
+
+
+def test_forcing_hooks(oracle_lib):
+    """External-force hooks of collideAll (CollisionOperator.h:79-96; Aux...h:332-417): without a force the advanced
+    entry equals the BGK oracle bit for bit; both force types add dt*F to the momentum to round-off (shifting
+    velocity: through the shifted equilibrium, tau*(1/tau); exact difference: f_eq(u + dt F/rho) - f_eq(u)); the stored
+    velocity is shifted by dt*F/(2 rho); NO_FORCING with a force and GUO raise (status -2 / -3)."""
+    st = oracle_lib.Stencil("D3Q19", 2.0)
+    n = 40
+    f0 = synthetic_populations(st.Q, n) * st.w[:, None]
+    nu, dt, F = 0.05, 0.1, np.array([1e-3, -2e-3, 5e-4])
+    a, b = f0.copy(), f0.copy()
+    ra, ua, _ = oracle_lib.collide_bgk(st, a, nu, dt)
+    rb, ub, rc = oracle_lib.collide_advanced(st, b, nu, dt)
+    assert rc == 0 and np.array_equal(a, b) and np.array_equal(ua, ub)
+    mom0 = st.e.T @ f0
+    for ft in ["SHIFTING_VELOCITY", "EXACT_DIFFERENCE"]:
+        c = f0.copy()
+        rho, u, rc = oracle_lib.collide_advanced(st, c, nu, dt, force=F, force_type=ft)
+        assert rc == 0
+        dmom = st.e.T @ c - mom0
+        assert np.max(np.abs(dmom - dt * F[:, None] * np.ones(n))) <= 1e-13
+        assert np.max(np.abs(u - (ua + 0.5 * dt * F[:, None] / rho))) <= 1e-14
+        assert np.max(np.abs(c.sum(0) - f0.sum(0))) <= 1e-14
+    assert oracle_lib.collide_advanced(st, f0.copy(), nu, dt, force=F, force_type="NO_FORCING")[2] == -2
+    assert oracle_lib.collide_advanced(st, f0.copy(), nu, dt, force=F, force_type="GUO")[2] == -3
