@@ -34,13 +34,14 @@ UNIT = "MDoF*Q/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=32, help="cells per axis per GPU (32 = refinement 5)")
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--stencil", default="D3Q19")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="pieces of the DoF range nb200_step_host pipelines over (1 = sequential legs)")
     ap.add_argument("--cpu-sample-layers", type=int, default=8, help="z cell layers of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="dict", choices=["dict", "dict-unstaged", "ell"], help="device format of the streaming matrix")
@@ -67,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
             t0 = time.time()
@@ -267,27 +268,28 @@ def run_ours(args):
     cons = ctx.conserved()
     assert np.isfinite(cons).all()
 
-    # ---- end to end: host buffers in, host buffers out, every step
-    hf = torch.empty((Q, n), dtype=torch.float64, pin_memory=True)
-    hf.numpy()[...] = ctx.download_populations(0)
-    hrho = np.empty(n); hu = np.empty((D, n))
+    # ---- end to end: host buffers in, host buffers out, every step (nb200_step_host: the call a host-resident
+    # DistributionFunctions makes; H2D of f, fused step, D2H of f, rho, u -- pipelined over chunks of the DoF range)
+    hf_a = torch.empty((Q, n), dtype=torch.float64, pin_memory=True)
+    hf_b = torch.empty((Q, n), dtype=torch.float64, pin_memory=True)
+    hf_a.numpy()[...] = ctx.download_populations(0)
+    hmom = torch.empty((1 + D, n), dtype=torch.float64, pin_memory=True)      # rho, u: pinned like f
     e2e_steps = max(1, args.e2e_steps)
-    import ctypes
-    _dp = ctypes.POINTER(ctypes.c_double)
+    bufs = [hf_a, hf_b]
+    rho_ptr, u_ptr = hmom.data_ptr(), hmom.data_ptr() + 8 * n
 
-    def e2e_step():
-        ctx.upload_populations_async(0, hf.data_ptr())
-        ctx.step(1)
-        ctx.download_populations_async(0, hf.data_ptr())
-        ctx.lib.nb200_download_moments(ctx._h, hrho.ctypes.data_as(_dp), hu.ctypes.data_as(_dp), None, None, n)
+    def e2e_step(i):
+        ctx.step_host(bufs[i & 1].data_ptr(), bufs[(i + 1) & 1].data_ptr(), rho_ptr, u_ptr, args.e2e_chunks)
 
-    e2e_step()
+    e2e_step(0)
+    e2e_step(1)
     barrier()
     ctx.timer_start()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for i in range(e2e_steps):
+        e2e_step(i)
     ms_e2e = ctx.timer_stop()
     barrier()
+    assert np.isfinite(hmom.numpy()).all() and np.isfinite(bufs[e2e_steps & 1].numpy()).all()
     if world > 1:
         t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,7 +325,8 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "chunks": args.e2e_chunks,
+                        "api": "nb200_step_host (pinned host buffers in and out every step)"},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base,
                 "n_dofs_global": n_global, "matrix_assembly_upload_s": t_asm,
                 "conserved": [float(x) for x in cons]}

@@ -213,6 +213,15 @@ int nb200_collide(nb200_ctx *ctx);
  * step, device resident (CFDSolver::run loop body, CFDSolver.cpp:877-902 without output()). */
 int nb200_step(nb200_ctx *ctx, int n_steps);
 
+/* One step driven with HOST buffers -- what a host-resident DistributionFunctions sees from
+ * SemiLagrangian::stream(f_old, f, t) followed by selectCollision (SemiLagrangian.h:150-161, CollisionSelection.h:60-67):
+ * f_in [Q][n] -> device, fused stream+collide, f_out [Q][n], rho [n], u [D][n] -> host (rho / u may be NULL).  Page-locked
+ * buffers make the copies asynchronous; the call returns after enqueue, nb200_synchronize() fences it.  With
+ * n_chunks > 1 upload, kernel and download are pipelined over pieces of the DoF range on separate streams (a piece's
+ * kernel waits only for the pieces its rows read), so the two PCIe directions overlap; n_chunks <= 1, several ranks,
+ * wall hits, f+g or a non-staged matrix format run the same legs in sequence.  Results are identical either way. */
+int nb200_step_host(nb200_ctx *ctx, const double *f_in, double *f_out, double *rho, double *u, int64_t n, int n_chunks);
+
 /* ---- results ----------------------------------------------------------------------------- */
 
 /* rho [n], u [D][n] (scaled, as written to m_velocity), T [n], sensor [n]; any pointer may be NULL. */

@@ -165,6 +165,19 @@ struct nb200_ctx {
         std::vector<int64_t> nbr_send_off, nbr_send_cnt, nbr_recv_off, nbr_recv_cnt;   // per neighbour, doubles
         int64_t max_send_cnt = 0, max_recv_cnt = 0, send_total = 0, recv_total = 0;
     } plans[8];
+    // host-buffer step (nb200_step_host): chunk pipeline over three streams
+    std::vector<int32_t> cta_max_user;       // per CTA: largest user DoF index its rows read (owned columns) or own
+    struct HostStep {
+        bool ready = false;
+        int C = 0;
+        std::vector<int64_t> u_off, cta_off;         // [C+1] user-index chunks / CTA chunks
+        std::vector<int> need_up, order, dl_after, dl_order;
+        int32_t* d_iota = nullptr;
+        double *d_in = nullptr, *d_out = nullptr;    // [Q][n] and [Q+1+D][n], user order
+        cudaStream_t s_up = nullptr, s_dn = nullptr;
+        std::vector<cudaEvent_t> ev_up, ev_done;
+        cudaEvent_t ev_start = nullptr, ev_dn = nullptr;
+    } hs;
     // wall hits (nb200_set_wall_hits), grouped by destination DoF in list order
     int64_t n_hits = 0, n_hit_groups = 0;
     bool hits_thermal = false;
@@ -359,6 +372,25 @@ __global__ void k_permute_rows(int64_t n, int rows, const int32_t* __restrict__ 
     dst[(int64_t)r * dst_stride + k] = src[(int64_t)r * src_stride + map[k]];
 }
 
+// Host-buffer step (nb200_step_host): user-order chunk [u0, u1) of `rows` arrays, staging (pitch n) <-> device arrays
+// in internal order (pitch dev_stride).  perm: user index -> internal position, null = identity.
+__global__ void k_chunk_scatter(int64_t u0, int64_t u1, int rows, const int32_t* __restrict__ perm,
+                                const double* __restrict__ stage, int64_t n, double* __restrict__ dev, int64_t dev_stride)
+{
+    const int64_t u = u0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= u1) return;
+    const int64_t i = perm ? perm[u] : u;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) dev[(int64_t)r * dev_stride + i] = stage[(int64_t)r * n + u];
+}
+__global__ void k_chunk_gather(int64_t u0, int64_t u1, int rows, const int32_t* __restrict__ perm,
+                               const double* __restrict__ dev, int64_t dev_stride, double* __restrict__ stage, int64_t n)
+{
+    const int64_t u = u0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (u >= u1) return;
+    const int64_t i = perm ? perm[u] : u;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) stage[(int64_t)r * n + u] = dev[(int64_t)r * dev_stride + i];
+}
+
 // halo pack / unpack.  A segment = one (neighbour, distribution, population) triple that the receiving rank's
 // matrix actually reads; segments of one neighbour are contiguous in the buffer.
 __global__ void k_halo_pack(const NbHaloSeg* __restrict__ segs, const int32_t* __restrict__ send_idx, int64_t stride,
@@ -449,6 +481,18 @@ static void free_matrix(nb200_ctx* c)
     c->d_sdesc = nullptr; c->d_stage_col = nullptr; c->d_stage_pass = nullptr; c->d_stage_cta = nullptr;
     c->staged = false;
     c->stage_values = c->stage_passes = c->stage_max_pass = 0;
+    {
+        auto& H = c->hs;
+        cudaFree(H.d_iota); cudaFree(H.d_in); cudaFree(H.d_out);
+        for (auto e : H.ev_up) cudaEventDestroy(e);
+        for (auto e : H.ev_done) cudaEventDestroy(e);
+        if (H.ev_start) cudaEventDestroy(H.ev_start);
+        if (H.ev_dn) cudaEventDestroy(H.ev_dn);
+        if (H.s_up) cudaStreamDestroy(H.s_up);
+        if (H.s_dn) cudaStreamDestroy(H.s_dn);
+        H = nb200_ctx::HostStep();
+    }
+    c->cta_max_user.clear();
     c->matrix_ready = false;
 }
 
@@ -849,13 +893,21 @@ static int finalize_dict(nb200_ctx* c)
         {   // CTAs whose staged values include a ghost slot must wait for the halo exchange; the others overlap it
             std::vector<int32_t> interior, boundary;
             const int64_t n_cta = (int64_t)SB.cta_ptr.size() - 1;
+            c->cta_max_user.assign((size_t)n_cta, 0);
             for (int64_t b = 0; b < n_cta; b++) {
                 bool ghost = false;
-                for (int32_t pp = SB.cta_ptr[(size_t)b]; pp < SB.cta_ptr[(size_t)b + 1] && !ghost; pp++) {
+                int32_t mx = 0;
+                for (int64_t r = b * NB_CTA_ROWS; r < std::min<int64_t>(n, (b + 1) * NB_CTA_ROWS); r++)
+                    mx = std::max(mx, c->has_order ? c->order[(size_t)r] : (int32_t)r);
+                for (int32_t pp = SB.cta_ptr[(size_t)b]; pp < SB.cta_ptr[(size_t)b + 1]; pp++) {
                     const auto& ps = SB.passes[(size_t)pp];
-                    for (int64_t e = ps.begin; e < ps.begin + ps.count; e++)
-                        if (SB.stage_col[(size_t)e] % c->stride >= c->n_owned) { ghost = true; break; }
+                    for (int64_t e = ps.begin; e < ps.begin + ps.count; e++) {
+                        const int64_t col = SB.stage_col[(size_t)e] % c->stride;
+                        if (col >= c->n_owned) ghost = true;
+                        else mx = std::max(mx, c->has_order ? c->order[(size_t)col] : (int32_t)col);
+                    }
                 }
+                c->cta_max_user[(size_t)b] = mx;
                 (ghost ? boundary : interior).push_back((int32_t)b);
             }
             cudaFree(c->d_cta_interior); cudaFree(c->d_cta_boundary);
@@ -1602,6 +1654,156 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
         }
         if (rc) return rc;
     }
+    CUDA_TRY(c, cudaGetLastError());
+    return NB200_OK;
+}
+
+// ---- host-buffer step ------------------------------------------------------------------------------
+static int host_step_plan(nb200_ctx* c, int C)
+{
+    auto& H = c->hs;
+    if (H.ready && H.C == C) return NB200_OK;
+    const int64_t n = c->n_owned, n_cta = (n + NB_CTA_ROWS - 1) / NB_CTA_ROWS;
+    if (!H.s_up) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&H.s_up, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&H.s_dn, cudaStreamNonBlocking));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&H.ev_start, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&H.ev_dn, cudaEventDisableTiming));
+        CUDA_TRY(c, cudaMalloc(&H.d_in, (size_t)c->Q * n * 8));
+        CUDA_TRY(c, cudaMalloc(&H.d_out, (size_t)(c->Q + 1 + c->D) * n * 8));
+        std::vector<int32_t> iota((size_t)n_cta);
+        for (int64_t b = 0; b < n_cta; b++) iota[(size_t)b] = (int32_t)b;
+        CUDA_TRY(c, cudaMalloc(&H.d_iota, (size_t)n_cta * 4));
+        CUDA_TRY(c, cudaMemcpy(H.d_iota, iota.data(), (size_t)n_cta * 4, cudaMemcpyHostToDevice));
+    }
+    for (auto e : H.ev_up) cudaEventDestroy(e);
+    for (auto e : H.ev_done) cudaEventDestroy(e);
+    H.ev_up.assign((size_t)C, nullptr);
+    H.ev_done.assign((size_t)C, nullptr);
+    for (int k = 0; k < C; k++) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&H.ev_up[(size_t)k], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&H.ev_done[(size_t)k], cudaEventDisableTiming));
+    }
+    H.C = C;
+    H.u_off.resize((size_t)C + 1);
+    H.cta_off.resize((size_t)C + 1);
+    for (int k = 0; k <= C; k++) {
+        H.u_off[(size_t)k] = (n * k / C) / 32 * 32;
+        H.cta_off[(size_t)k] = n_cta * k / C;
+    }
+    H.u_off[(size_t)C] = n;
+    auto chunk_of_user = [&](int64_t u) {
+        int k = (int)std::min<int64_t>(C - 1, u * C / std::max<int64_t>(1, n));
+        while (k > 0 && u < H.u_off[(size_t)k]) k--;
+        while (k < C - 1 && u >= H.u_off[(size_t)k + 1]) k++;
+        return k;
+    };
+    // CTA chunk k can run once user chunks 0..need_up[k] are on the device (uploads are issued in order)
+    H.need_up.assign((size_t)C, 0);
+    for (int k = 0; k < C; k++) {
+        int32_t mx = 0;
+        for (int64_t b = H.cta_off[(size_t)k]; b < H.cta_off[(size_t)k + 1]; b++) mx = std::max(mx, c->cta_max_user[(size_t)b]);
+        H.need_up[(size_t)k] = chunk_of_user(mx);
+    }
+    H.order.resize((size_t)C);
+    for (int k = 0; k < C; k++) H.order[(size_t)k] = k;
+    std::stable_sort(H.order.begin(), H.order.end(), [&](int a, int b) { return H.need_up[(size_t)a] < H.need_up[(size_t)b]; });
+    std::vector<int> pos((size_t)C);
+    for (int i = 0; i < C; i++) pos[(size_t)H.order[(size_t)i]] = i;
+    // user chunk j can be downloaded once every CTA chunk holding one of its DoFs is done
+    H.dl_after.assign((size_t)C, 0);
+    for (int64_t u = 0; u < n; u++) {
+        const int64_t i = c->has_order ? c->perm[(size_t)u] : u;
+        const int64_t b = i / NB_CTA_ROWS;
+        int k = (int)std::min<int64_t>(C - 1, b * C / std::max<int64_t>(1, n_cta));
+        while (k > 0 && b < H.cta_off[(size_t)k]) k--;
+        while (k < C - 1 && b >= H.cta_off[(size_t)k + 1]) k++;
+        const int j = chunk_of_user(u);
+        H.dl_after[(size_t)j] = std::max(H.dl_after[(size_t)j], pos[(size_t)k]);
+    }
+    H.dl_order.resize((size_t)C);
+    for (int j = 0; j < C; j++) H.dl_order[(size_t)j] = j;
+    std::stable_sort(H.dl_order.begin(), H.dl_order.end(), [&](int a, int b) { return H.dl_after[(size_t)a] < H.dl_after[(size_t)b]; });
+    H.ready = true;
+    return NB200_OK;
+}
+
+// One stream+collide step driven with HOST buffers (the call a host-resident DistributionFunctions makes:
+// SemiLagrangian::stream(f_old, f, t) + selectCollision, SemiLagrangian.h:150-161, CollisionSelection.h:60-67):
+// f_in -> device, fused step, f_out / rho / u -> host.  The three legs are pipelined over n_chunks pieces of the
+// DoF range on separate streams, so the upload of later pieces, the kernel of the current one and the download of
+// earlier ones overlap (PCIe is full duplex); a piece's kernel waits only for the pieces its rows read.
+extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, double* rho, double* u, int64_t n, int n_chunks)
+{
+    int rc = ready(c, true, true);
+    if (rc) return rc;
+    if (!f_in || !f_out || n != c->n_owned) return fail(c, NB200_ERR_ARG, "step_host: bad argument");
+    if (c->cp.in_init) return fail(c, NB200_ERR_ARG, "step_host: in_init collisions are only available through nb200_collide");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool pipelined = n_chunks > 1 && c->nranks == 1 && c->fmt == NB_FMT_DICT && c->staged && use_fused(c) && !c->cp.with_g
+        && c->n_hit_groups == 0 && n >= (int64_t)n_chunks * 4 * NB_CTA_ROWS;
+    if (!pipelined) {      // same result, legs in sequence
+        rc = copy_all(c, 0, const_cast<double*>(f_in), n, true, false);
+        if (!rc) rc = nb200_step(c, 1);
+        if (!rc) rc = copy_all(c, 0, f_out, n, false, false);
+        if (!rc && (rho || u)) rc = nb200_download_moments(c, rho, u, nullptr, nullptr, n);
+        return rc;
+    }
+    rc = host_step_plan(c, n_chunks);
+    if (rc) return rc;
+    auto& H = c->hs;
+    const int C = H.C, Q = c->Q, D = c->D;
+    const int32_t* perm = c->has_order ? c->d_perm : nullptr;
+    double* x = c->pop[0][c->cur[0]];
+    double* y = c->pop[0][c->cur[0] ^ 1];
+    CUDA_TRY(c, cudaEventRecord(H.ev_start, c->stream));          // earlier work on the context stream
+    CUDA_TRY(c, cudaStreamWaitEvent(H.s_up, H.ev_start, 0));
+    CUDA_TRY(c, cudaStreamWaitEvent(H.s_dn, H.ev_start, 0));
+    for (int k = 0; k < C; k++) {
+        const int64_t u0 = H.u_off[(size_t)k], u1 = H.u_off[(size_t)k + 1];
+        if (u1 > u0) {
+            CUDA_TRY(c, cudaMemcpy2DAsync(H.d_in + u0, (size_t)n * 8, f_in + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyHostToDevice, H.s_up));
+            k_chunk_scatter<<<dim3(grid_for(u1 - u0, 256), (unsigned)Q), 256, 0, H.s_up>>>(u0, u1, Q, perm, H.d_in, n, x, c->stride);
+            c->launches++;
+        }
+        CUDA_TRY(c, cudaEventRecord(H.ev_up[(size_t)k], H.s_up));
+    }
+    for (int i = 0; i < C; i++) {
+        const int k = H.order[(size_t)i];
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)H.need_up[(size_t)k]], 0));
+        const int64_t b0 = H.cta_off[(size_t)k], b1 = H.cta_off[(size_t)k + 1];
+        if (b1 > b0) {
+            NbLaunch L = make_launch(c, H.d_iota + b0, b1 - b0);
+            L.xf = x; L.yf = y;
+            rc = cuda_rc(c, c->ops->fused(L), "fused stream+collide (host step)");
+            if (rc) return rc;
+            c->launches++;
+        }
+        CUDA_TRY(c, cudaEventRecord(H.ev_done[(size_t)i], c->stream));
+    }
+    double* o_f = H.d_out;
+    double* o_rho = H.d_out + (size_t)Q * n;
+    double* o_u = o_rho + n;
+    for (int jj = 0; jj < C; jj++) {
+        const int j = H.dl_order[(size_t)jj];
+        const int64_t u0 = H.u_off[(size_t)j], u1 = H.u_off[(size_t)j + 1];
+        CUDA_TRY(c, cudaStreamWaitEvent(H.s_dn, H.ev_done[(size_t)H.dl_after[(size_t)j]], 0));
+        if (u1 <= u0) continue;
+        k_chunk_gather<<<dim3(grid_for(u1 - u0, 256), (unsigned)Q), 256, 0, H.s_dn>>>(u0, u1, Q, perm, y, c->stride, o_f, n);
+        c->launches++;
+        CUDA_TRY(c, cudaMemcpy2DAsync(f_out + u0, (size_t)n * 8, o_f + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyDeviceToHost, H.s_dn));
+        if (rho || u) {
+            k_chunk_gather<<<dim3(grid_for(u1 - u0, 256), 1), 256, 0, H.s_dn>>>(u0, u1, 1, perm, c->rho, n, o_rho, n);
+            k_chunk_gather<<<dim3(grid_for(u1 - u0, 256), (unsigned)D), 256, 0, H.s_dn>>>(u0, u1, D, perm, c->u, n, o_u, n);
+            c->launches += 2;
+            if (rho) CUDA_TRY(c, cudaMemcpyAsync(rho + u0, o_rho + u0, (size_t)(u1 - u0) * 8, cudaMemcpyDeviceToHost, H.s_dn));
+            if (u) CUDA_TRY(c, cudaMemcpy2DAsync(u + u0, (size_t)n * 8, o_u + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)D, cudaMemcpyDeviceToHost, H.s_dn));
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(H.ev_dn, H.s_dn));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_dn, 0));      // the context stream is the fence for callers
+    CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)C - 1], 0));
+    c->cur[0] ^= 1;
     CUDA_TRY(c, cudaGetLastError());
     return NB200_OK;
 }

@@ -706,3 +706,143 @@ def test_advanced_dispatch_errors():
     ctx = ctx_for("D2Q25H", with_g=True)
     ctx.set_collision(0.1, 0.1, scheme=_capi.BGK_REGULARIZED, equilibrium=_capi.BGK_EQUILIBRIUM, with_g=True)
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# wall hits
+# ---------------------------------------------------------------------------------------------
+def _synthetic_hits(rng, n, Q, n_hits, thermal):
+    """A flattened HitList: destination DoFs with several hits each (corner nodes are hit from more than one
+    direction), in arbitrary cell order."""
+    idx = rng.integers(0, n, size=n_hits).astype(np.int32)
+    idx[1::3] = idx[0:-1:3][:len(idx[1::3])]                 # repeated destinations
+    dirs = rng.integers(1, Q, size=n_hits).astype(np.int32)
+    kinds = (rng.random(n_hits) < 0.5).astype(np.int32) if thermal else np.zeros(n_hits, dtype=np.int32)
+    vals = np.where(kinds == 1, 0.85, 1e-2 * rng.standard_normal(n_hits))
+    return idx, dirs, kinds, vals
+
+
+@pytest.mark.parametrize("ordered", [False, True])
+def test_stream_with_wall_hits_f_only(ordered, oracle_lib):
+    """SemiLagrangian::stream = vmult + boundaryHandler.apply (SemiLagrangian.h:150-161): VelocityNeqBounceBack terms on
+    a D2Q9 problem, with and without an internal DoF order."""
+    case = "c1_tgv2d_d2q9"
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=("dict", 1e-14, ordered))
+    rng = np.random.default_rng(2)
+    idx, dirs, kinds, vals = _synthetic_hits(rng, part.n_owned, 9, 300, thermal=False)
+    ctx.set_wall_hits(idx, dirs, kinds, vals)
+    ctx.upload_populations(0, o["f"])
+    ctx.stream(0)
+    got = ctx.download_populations(0)
+    ref = oracle_lib.stream(o["blocks"], o["f"])
+    assert oracle_lib.apply_wall_hits(o["st"], ref, None, idx, dirs, kinds, vals) == 0
+    assert rel_err(got, ref) <= TOL_STEP
+    # fused step path falls back to stream -> hits -> collide
+    ctx.set_collision(c["nu"], dt)
+    ctx.upload_populations(0, o["f"])
+    ctx.step(2)
+    ctx.synchronize()
+    f = o["f"].copy()
+    for _ in range(2):
+        f = oracle_lib.stream(o["blocks"], f)
+        oracle_lib.apply_wall_hits(o["st"], f, None, idx, dirs, kinds, vals)
+        oracle_lib.collide_bgk(o["st"], f, c["nu"], dt)
+    assert rel_err(ctx.download_populations(0), f) <= 2 * TOL_STEP
+    ctx.set_wall_hits([], [], [], [])        # clearing the hit list restores the fused path
+    l0 = ctx.kernel_launches()
+    ctx.step(1)
+    assert ctx.kernel_launches() - l0 == 1
+    ctx.close()
+
+
+def test_compressible_step_with_thermal_walls(oracle_lib):
+    """CompressibleCFDSolver order (CompressibleCFDSolver.h:181-314): stream f, wall hits on the new f and the old g
+    (ThermalBounceBack re-equilibration + VelocityNeqBounceBack terms), then gStream, then collide."""
+    from natrium_b200 import _capi
+    case = "tgv3d_d3q45"
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case)
+    set_collision(ctx, c, dt)
+    rng = np.random.default_rng(4)
+    idx, dirs, kinds, vals = _synthetic_hits(rng, part.n_owned, 45, 200, thermal=True)
+    ctx.set_wall_hits(idx, dirs, kinds, vals)
+    f, g = o["f"].copy(), o["g"].copy()
+    ctx.upload_populations(0, f)
+    ctx.upload_populations(1, g)
+    for s in range(3):
+        ctx.step(1)
+        ctx.synchronize()
+        f = oracle_lib.stream(o["blocks"], f)
+        assert oracle_lib.apply_wall_hits(o["st"], f, g, idx, dirs, kinds, vals) == 0
+        g = oracle_lib.stream(o["blocks"], g)
+        _, _, _, _, rc = oracle_lib.collide_bgk_fg(o["st"], f, g, c["nu"], dt, equilibrium=1, gamma=1.4, prandtl=0.71, sutherland=True)
+        assert rc == 0
+        gf, gg = ctx.download_populations(0), ctx.download_populations(1)
+        assert rel_err(gf, f) <= TOL_STEP and rel_err(gg, g) <= TOL_STEP, (s, rel_err(gf, f), rel_err(gg, g))
+        ctx.upload_populations(0, f)
+        ctx.upload_populations(1, g)
+    ctx.close()
+
+
+def test_wall_hit_errors():
+    from natrium_b200 import CollisionException, Context, NatriumB200Error, Stencil, _capi
+    st = Stencil("D3Q19", 1.0)
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+    ctx.set_layout(16, 0, False)
+    with pytest.raises(CollisionException):      # thermal walls are a D3Q45 f+g model
+        ctx.set_wall_hits([1], [2], [_capi.WALL_THERMAL_BOUNCE_BACK], [0.85])
+    with pytest.raises(NatriumB200Error):
+        ctx.set_wall_hits([16], [2], [0], [0.1])
+    with pytest.raises(NatriumB200Error):
+        ctx.set_wall_hits([1], [19], [0], [0.1])
+    with pytest.raises(CollisionException):
+        ctx.set_wall_hits([1], [2], [7], [0.1])
+    ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# host-buffer step (nb200_step_host)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,ordered,chunks", [("c1_tgv2d_d2q9", False, 2), ("c1_tgv2d_d2q9", True, 2), ("tgv3d_d3q19_small", True, 4),
+                                                 ("tgv3d_d3q19_small", False, 3), ("tgv3d_d3q19_small", True, 1), ("tgv2d_d2q25", True, 4)])
+def test_step_host_equals_device_resident_step(case, ordered, chunks, oracle_lib):
+    """The chunk-pipelined host-buffer step gives bit-for-bit what upload + nb200_step + download gives (the kernels
+    and their per-row arithmetic are the same; only the launch is cut into pieces), over several chained steps with
+    the output buffer of one step feeding the next; f+g and chunks = 1 take the sequential legs."""
+    import torch
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=("dict", 1e-14, ordered))
+    set_collision(ctx, c, dt)
+    n, Q, D = part.n_owned, st.getQ(), st.getD()
+    with_g = bool(c.get("with_g"))
+    # reference: device-resident steps
+    ctx.upload_populations(0, o["f"])
+    if with_g:
+        ctx.upload_populations(1, o["g"])
+    ctx.step(3)
+    ctx.synchronize()
+    want = ctx.download_populations(0)
+    wrho, wu = ctx.download_moments()[:2]
+    # host-buffer steps
+    a = torch.empty((Q, n), dtype=torch.float64, pin_memory=True)
+    b = torch.empty((Q, n), dtype=torch.float64, pin_memory=True)
+    mom = torch.empty((1 + D, n), dtype=torch.float64, pin_memory=True)
+    a.numpy()[...] = o["f"]
+    if with_g:
+        ctx.upload_populations(1, o["g"])
+    bufs = [a, b]
+    l0 = ctx.kernel_launches()
+    for s in range(3):
+        ctx.step_host(bufs[s & 1].data_ptr(), bufs[(s + 1) & 1].data_ptr(), mom.data_ptr(), mom.data_ptr() + 8 * n, chunks)
+    ctx.synchronize()
+    got = bufs[3 & 1].numpy()
+    if with_g:
+        assert rel_err(got, want) <= TOL_STEP       # g stays on the device between the host steps
+    else:
+        assert np.array_equal(got, want)
+        assert np.array_equal(mom.numpy()[0], wrho) and np.array_equal(mom.numpy()[1:], wu)
+    if chunks > 1 and not with_g:
+        assert ctx.kernel_launches() - l0 >= 3 * chunks * 3          # scatter, fused, gather per piece
+    ctx.close()

@@ -316,3 +316,45 @@ def test_forcing_hooks(oracle_lib):
         assert np.max(np.abs(c.sum(0) - f0.sum(0))) <= 1e-14
     assert oracle_lib.collide_advanced(st, f0.copy(), nu, dt, force=F, force_type="NO_FORCING")[2] == -2
     assert oracle_lib.collide_advanced(st, f0.copy(), nu, dt, force=F, force_type="GUO")[2] == -3
+
+
+# ---------------------------------------------------------------------------------------------
+# wall hits
+# ---------------------------------------------------------------------------------------------
+def test_wall_hits_properties(oracle_lib):
+    """ThermalBounceBack (ThermalBounceBack.cpp:50-109) re-equilibrates the destination DoF to the wall temperature:
+    afterwards density and velocity of the DoF are unchanged, its temperature is T_wall up to the energy of the
+    non-equilibrium part that is kept, and g = g_eq(T_w).  VelocityNeqBounceBack adds its term to one population."""
+    from natrium_b200 import harness
+    from natrium_b200.stencils import Stencil as PStencil
+    st = oracle_lib.Stencil("D3Q45", 1.0)
+    pst = PStencil("D3Q45", 1.0)
+    n, gamma, Tw = 12, 1.4, 0.85
+    rng = np.random.default_rng(3)
+    rho = 1.0 + 0.05 * rng.standard_normal(n)
+    u = 0.05 * rng.standard_normal((3, n))
+    T = 1.0 + 0.05 * rng.standard_normal(n)
+    f, g = harness.quartic_equilibrium_distributions(pst, rho, u, T, gamma)
+    f *= 1.0 + 0.01 * rng.standard_normal(f.shape)
+    f0, g0 = f.copy(), g.copy()
+    idx = np.array([3, 7, 7, 1], dtype=np.int32)
+    dirs = np.array([5, 9, 11, 2], dtype=np.int32)
+    kinds = np.array([1, 1, 1, 0], dtype=np.int32)
+    vals = np.array([Tw, Tw, Tw, 0.125])
+    assert oracle_lib.apply_wall_hits(st, f, g, idx, dirs, kinds, vals) == 0
+    e = st.e
+    for i in (3, 7):
+        r0, r1 = f0[:, i].sum(), f[:, i].sum()
+        assert abs(r1 - r0) <= 1e-13
+        assert np.max(np.abs(e.T @ f[:, i] - e.T @ f0[:, i])) <= 1e-12
+        ui = e.T @ f[:, i] / r1
+        Cv = 1.0 / (gamma - 1.0)
+        Ti = 0.5 * (np.sum(((e - ui) ** 2).sum(1) * f[:, i]) / st.cs2 + g[:, i].sum()) / (r1 * Cv)
+        assert abs(Ti - Tw) <= 1e-3           # up to the energy carried by the kept non-equilibrium part
+    untouched = [k for k in range(n) if k not in (1, 3, 7)]
+    assert np.array_equal(f[:, untouched], f0[:, untouched]) and np.array_equal(g[:, untouched], g0[:, untouched])
+    assert f[2, 1] == f0[2, 1] + 0.125 and np.array_equal(np.delete(f[:, 1], 2), np.delete(f0[:, 1], 2))
+    assert np.array_equal(g[:, 1], g0[:, 1])
+    # thermal hits need D3Q45 and g
+    st19 = oracle_lib.Stencil("D3Q19", 1.0)
+    assert oracle_lib.apply_wall_hits(st19, np.ones((19, 4)), None, [0], [1], [1], [0.85]) == -3
