@@ -213,6 +213,14 @@ int nb200_collide(nb200_ctx *ctx);
  * step, device resident (CFDSolver::run loop body, CFDSolver.cpp:877-902 without output()). */
 int nb200_step(nb200_ctx *ctx, int n_steps);
 
+/* DataProcessor hook after collide (the loop over m_dataProcessors in CFDSolver::run, CFDSolver.cpp:889-891) for the one
+ * processor on the path: PseudoEntropicStabilizer::apply (L/dataprocessors/PseudoEntropicStabilizer.cpp:152-290) replaces
+ * the populations of every owned DoF by A f.  A (Q x Q, row-major) is the host's table (n/d, nd_d2q9_with_e or nd_d3q19,
+ * :27-150); D2Q9 and D3Q19 only, as in the reference.  Once set it runs after the collision of every nb200_step
+ * iteration; nb200_apply_post_collision applies it once to the current populations.  A = NULL removes it. */
+int nb200_set_post_collision_matrix(nb200_ctx *ctx, int Q, const double *A);
+int nb200_apply_post_collision(nb200_ctx *ctx);
+
 /* One step driven with HOST buffers -- what a host-resident DistributionFunctions sees from
  * SemiLagrangian::stream(f_old, f, t) followed by selectCollision (SemiLagrangian.h:150-161, CollisionSelection.h:60-67):
  * f_in [Q][n] -> device, fused stream+collide, f_out [Q][n], rho [n], u [D][n] -> host (rho / u may be NULL).  Page-locked

@@ -5,8 +5,8 @@ fused with collision, device-resident DistributionFunctions, NCCL ghost exchange
 through the C ABI in include/natrium_b200.h.  There is no CPU fallback: the CUDA library must
 be built (``__graft_entry__.build()``) and a GPU must be present to create a context.
 """
-from . import _capi, harness, host, stencils  # noqa: F401
+from . import _capi, harness, host, mrt, stencils  # noqa: F401
 from ._capi import CollisionException, Context, NatriumB200Error  # noqa: F401
-from .host import (CFDSolver, CompressibleCFDSolver, DistributionFunctions, SemiLagrangian,  # noqa: F401
-                   SolverConfiguration, selectCollision)
+from .host import (CFDSolver, CompressibleCFDSolver, DistributionFunctions, PseudoEntropicStabilizer,  # noqa: F401
+                   SemiLagrangian, SolverConfiguration, selectCollision)
 from .stencils import Stencil  # noqa: F401

@@ -72,6 +72,8 @@ SIGNATURES = {
     "nb200_upload_density": (C.c_int, [_vp, _dp, C.c_int64]),
     "nb200_set_collision": (C.c_int, [_vp, C.POINTER(CollisionParams)]),
     "nb200_set_mrt": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "nb200_set_post_collision_matrix": (C.c_int, [_vp, C.c_int, _dp]),
+    "nb200_apply_post_collision": (C.c_int, [_vp]),
     "nb200_set_wall_hits": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, _i32p, _dp]),
     "nb200_update_ghosted": (C.c_int, [_vp]),
     "nb200_stream": (C.c_int, [_vp, C.c_int]),
@@ -263,6 +265,17 @@ class Context:
         vv = _as_f64(value)
         self._check(self.lib.nb200_set_wall_hits(self._h, len(di), di.ctypes.data_as(_i32p), dd.ctypes.data_as(_i32p),
                                                  kk.ctypes.data_as(_i32p), _dptr(vv)))
+
+    def set_post_collision_matrix(self, A):
+        """PseudoEntropicStabilizer matrix (Q x Q); None removes it."""
+        if A is None:
+            self._check(self.lib.nb200_set_post_collision_matrix(self._h, 0, None))
+            return
+        A = _as_f64(A)
+        self._check(self.lib.nb200_set_post_collision_matrix(self._h, A.shape[0], _dptr(A)))
+
+    def apply_post_collision(self):
+        self._check(self.lib.nb200_apply_post_collision(self._h))
 
     def set_mrt(self, M, T, omega):
         """Tables of MultipleRelaxationTime::SpecificCollisionData (make_M / make_T / make_diag)."""

@@ -198,6 +198,10 @@ struct NbMrtStd {
 };
 __constant__ NbMrtStd cS;
 
+// Per-DoF linear map applied after the collision: the matrix of PseudoEntropicStabilizer::apply
+// (L/dataprocessors/PseudoEntropicStabilizer.cpp:27-150,225-262), handed over through nb200_set_post_collision_matrix().
+__constant__ double cA[NB_MRT_MAXQ][NB_MRT_MAXQ];
+
 // collideAll body, f only, every scheme of selectCollision on the path (CollisionOperator.h:52-104):
 // SCHEME 0 BGKCollision::relax (CollisionSchemes.h:28-41), 1 Regularized::relax (:150-203),
 // 2 MultipleRelaxationTime::relax (:238-263).  FORCE compiles the external-force hooks in

@@ -57,6 +57,10 @@ int bind(const NbLaunch& L)
             if (e != cudaSuccess) return (int)e;
         }
 #if NB_HAS_MRT
+        if (L.post_matrix) {
+            e = cudaMemcpyToSymbolAsync(cA, L.post_matrix, sizeof(double) * NB_MRT_MAXQ * NB_MRT_MAXQ, 0, cudaMemcpyHostToDevice, L.stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         if (L.mrt_std) {
             static_assert(sizeof(NbMrtStd) == sizeof(NbMrtStdHost), "MRT table layout");
             e = cudaMemcpyToSymbolAsync(cS, L.mrt_std, sizeof(NbMrtStd), 0, cudaMemcpyHostToDevice, L.stream);
@@ -213,13 +217,30 @@ int wall(const NbLaunch& L)
     return (int)cudaGetLastError();
 }
 
+#if NB_HAS_MRT
+int post(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    const int64_t n = L.A.n_owned;
+    k_post_matrix<Q><<<grid_for(n, 128), 128, 0, L.stream>>>(n, L.A.stride, L.yf);
+    return (int)cudaGetLastError();
+}
+#endif
+
 const NbStencilOps ops = {D, Q,
 #if NB_FUSE_F || (NB_WITH_G && NB_FUSE_G)
                           fused,
 #else
                           nullptr,
 #endif
-                          collide, conserved, wall};
+                          collide, conserved, wall,
+#if NB_HAS_MRT
+                          post
+#else
+                          nullptr
+#endif
+};
 
 }  // namespace
 

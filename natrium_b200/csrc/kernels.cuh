@@ -364,6 +364,29 @@ k_wall_hits(int64_t n_groups, const int32_t* __restrict__ group_dof, const int64
     }
 }
 
+// DataProcessor hook after collide (CFDSolver.cpp:889-891): f <- A f per owned DoF, A in constant memory
+// (PseudoEntropicStabilizer::apply_d2q9 / apply_d2q9_with_e / apply_d3q19, PseudoEntropicStabilizer.cpp:152-262).
+// Row sums in the reference's order: j = 0..Q-1 accumulated from 0.
+template <int Q>
+__global__ void __launch_bounds__(128)
+k_post_matrix(int64_t n, int64_t stride, double* __restrict__ fbuf)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    if constexpr (Q <= NB_MRT_MAXQ) {
+        double f[Q];
+#pragma unroll
+        for (int q = 0; q < Q; q++) f[q] = fbuf[(int64_t)q * stride + row];
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; j++) acc += cA[i][j] * f[j];
+            fbuf[(int64_t)i * stride + row] = acc;
+        }
+    }
+}
+
 // Conserved sums: deterministic two-stage reduction.  partial[blk*5 + m].
 template <int D, int Q>
 __global__ void __launch_bounds__(256)

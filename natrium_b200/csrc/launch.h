@@ -24,6 +24,7 @@ struct NbLaunch {
     const NbConst* hc; const void* owner; uint64_t version;
     const NbMrtHost* mrt;   // MRTEntropic tables (D3Q19 unit only)
     const NbMrtStdHost* mrt_std;   // MultipleRelaxationTime tables (D2Q9 / D3Q19 units)
+    const double* post_matrix;     // [19][19] host copy of the post-collision matrix (uploaded with the constants)
     int force;              // external-force hooks (stand-alone collide kernels)
     unsigned grid_override; // staged kernels over a CTA subset (A.cta_map): number of CTAs to launch, 0 = all
     // wall hits (k_wall_hits)
@@ -39,6 +40,7 @@ struct NbStencilOps {
     int (*collide)(const NbLaunch&);     // in-place collide
     int (*conserved)(const NbLaunch&);   // deterministic conserved sums
     int (*wall)(const NbLaunch&);        // wall hits on yf (and yg)
+    int (*post)(const NbLaunch&);        // post-collision matrix on yf; nullptr where the reference has none
 };
 
 const NbStencilOps* nb_ops_d2q9();

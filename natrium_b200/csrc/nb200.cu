@@ -146,6 +146,8 @@ struct nb200_ctx {
     NbMrtHost mrt;                           // MRTEntropic D3Q19 tables
     NbMrtStdHost mrt_std;                    // MultipleRelaxationTime tables (nb200_set_mrt)
     bool mrt_std_set = false;
+    double post_matrix[19][19];              // post-collision matrix (nb200_set_post_collision_matrix)
+    bool post_set = false;
     // halo
     int n_nbr = 0;
     std::vector<int32_t> nbr_rank;
@@ -1282,6 +1284,20 @@ extern "C" int nb200_set_wall_hits(nb200_ctx* c, int64_t n_hits, const int32_t* 
     return NB200_OK;
 }
 
+extern "C" int nb200_set_post_collision_matrix(nb200_ctx* c, int Q, const double* A)
+{
+    if (!c || !c->stencil_set) return fail(c, NB200_ERR_ARG, "set_post_collision_matrix: call set_stencil first");
+    if (!A) { c->post_set = false; c->const_version = ++g_const_stamp; return NB200_OK; }
+    if (Q != c->Q) return fail(c, NB200_ERR_ARG, "set_post_collision_matrix: matrix is for Q=%d, stencil has Q=%d", Q, c->Q);
+    if (!c->ops || !c->ops->post)
+        return fail(c, NB200_ERR_UNSUPPORTED, "PseudoEntropicStabilizer is only defined for D2Q9 and D3Q19 (PseudoEntropicStabilizer.cpp:275-290)");
+    memset(c->post_matrix, 0, sizeof(c->post_matrix));
+    for (int i = 0; i < Q; i++) for (int j = 0; j < Q; j++) c->post_matrix[i][j] = A[i * Q + j];
+    c->post_set = true;
+    c->const_version = ++g_const_stamp;
+    return NB200_OK;
+}
+
 extern "C" int nb200_set_mrt(nb200_ctx* c, int Q, const double* M, const double* T, const double* omega)
 {
     if (!c || !c->stencil_set || !M || !T || !omega) return fail(c, NB200_ERR_ARG, "set_mrt: call set_stencil first / null table");
@@ -1453,6 +1469,7 @@ static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int6
     L.mrt = c->kind == NB_KIND_MRT_ENTROPIC ? &c->mrt : nullptr;
     L.mrt_std = c->kind == NB_KIND_MRT ? &c->mrt_std : nullptr;
     L.force = c->cp.has_external_force ? 1 : 0;
+    L.post_matrix = c->post_set ? &c->post_matrix[0][0] : nullptr;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
     L.fmt = (c->fmt == NB_FMT_DICT && c->staged) ? NB_FMT_STAGED : c->fmt;
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;
@@ -1496,6 +1513,25 @@ static int dispatch_collide(nb200_ctx* c)
     if (rc) return rc;
     c->launches++;
     return NB200_OK;
+}
+
+static int dispatch_post(nb200_ctx* c)
+{
+    if (!c->post_set || c->n_owned == 0) return NB200_OK;
+    NbLaunch L = make_launch(c);
+    L.yf = c->pop[0][c->cur[0]];
+    int rc = cuda_rc(c, c->ops->post(L), "post-collision matrix");
+    if (rc) return rc;
+    c->launches++;
+    return NB200_OK;
+}
+
+extern "C" int nb200_apply_post_collision(nb200_ctx* c)
+{
+    if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "apply_post_collision: call set_layout first");
+    if (!c->post_set) return fail(c, NB200_ERR_ARG, "apply_post_collision: no matrix set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return dispatch_post(c);
 }
 
 // SemiLagrangianBoundaryHandler::apply on the current (just streamed) f and the current g
@@ -1621,6 +1657,7 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             if (!rc) rc = dispatch_wall(c);
             if (!rc && do_g && c->n_slices > 0) rc = launch_stream(c, false, true);
             if (!rc && c->n_owned > 0) rc = dispatch_collide(c);
+            if (!rc) rc = dispatch_post(c);
             if (rc) return rc;
             continue;
         }
@@ -1640,6 +1677,7 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
                 if (!rc) rc = launch_stream(c, true, do_g, c->d_cta_boundary, c->n_cta_boundary, true);
                 if (!rc) rc = dispatch_collide(c);
             }
+            if (!rc) rc = dispatch_post(c);
             if (rc) return rc;
             continue;
         }
@@ -1652,6 +1690,7 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             rc = launch_stream(c, true, do_g);
             if (!rc) rc = dispatch_collide(c);
         }
+        if (!rc) rc = dispatch_post(c);
         if (rc) return rc;
     }
     CUDA_TRY(c, cudaGetLastError());
@@ -1741,7 +1780,7 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     if (c->cp.in_init) return fail(c, NB200_ERR_ARG, "step_host: in_init collisions are only available through nb200_collide");
     CUDA_TRY(c, cudaSetDevice(c->device));
     const bool pipelined = n_chunks > 1 && c->nranks == 1 && c->fmt == NB_FMT_DICT && c->staged && use_fused(c) && !c->cp.with_g
-        && c->n_hit_groups == 0 && n >= (int64_t)n_chunks * 4 * NB_CTA_ROWS;
+        && c->n_hit_groups == 0 && !c->post_set && n >= (int64_t)n_chunks * 4 * NB_CTA_ROWS;
     if (!pipelined) {      // same result, legs in sequence
         rc = copy_all(c, 0, const_cast<double*>(f_in), n, true, false);
         if (!rc) rc = nb200_step(c, 1);

@@ -197,6 +197,23 @@ def selectCollision(configuration, problemDescription, f, *args):
         np.asarray(velocities)[...] = u
 
 
+class PseudoEntropicStabilizer:
+    """Mirror of natrium::PseudoEntropicStabilizer<dim> (L/dataprocessors/PseudoEntropicStabilizer.h:25-66): a
+    DataProcessor appended to the solver; apply() multiplies the populations of every owned DoF by the stabilizer
+    matrix.  On the device the matrix runs after the collision of every step."""
+
+    def __init__(self, solver, with_e=False):
+        self.m_solver, self.m_withE = solver, with_e
+        name = solver.m_stencil.getStencilType()
+        if name not in ("Stencil_D2Q9", "Stencil_D3Q19"):
+            raise CollisionException(_capi.NB200_ERR_UNSUPPORTED, "PseudoEntropicStabilizer is only defined for D2Q9 and D3Q19")
+        self.matrix = mrt.make_stabilizer(name, with_e and name == "Stencil_D2Q9")
+
+    def apply(self):
+        self.m_solver.ctx.set_post_collision_matrix(self.matrix)
+        self.m_solver.ctx.apply_post_collision()
+
+
 class CFDSolver:
     """Time loop owner.  ``run()`` keeps everything on the device (one fused kernel per step);
     ``stream()`` / ``collide()`` are the reference-ordered single operators."""
@@ -240,6 +257,12 @@ class CFDSolver:
     def _configure_collision(self):
         cfg = self.m_configuration
         _apply_collision_setup(self.ctx, cfg, self.m_problem, self.m_stencil, self.m_viscosity, self.getTimeStepSize(), self._with_g)
+
+    def appendDataProcessor(self, proc):
+        """CFDSolver::appendDataProcessor (CFDSolver.h): processors run after collide in every iteration of run()."""
+        self.m_dataProcessors = getattr(self, "m_dataProcessors", []) + [proc]
+        if isinstance(proc, PseudoEntropicStabilizer):
+            self.ctx.set_post_collision_matrix(proc.matrix)      # device-resident run(): part of nb200_step
 
     def stream(self):
         self.m_advectionOperator.stream(self.m_f, self.m_f, self.m_time)

@@ -82,3 +82,35 @@ def make_diag(tau, basis, relax_mode=RELAX_FULL):
             raise ValueError("MRT relaxation not defined")
         return d
     raise ValueError("MRT basis not defined")
+
+
+def make_stabilizer(stencil, with_e=False):
+    """Matrix of PseudoEntropicStabilizer::apply (L/dataprocessors/PseudoEntropicStabilizer.cpp:27-150): in moment space
+    the conserved and second-order moments are kept and every higher moment is replaced by the linear part of its
+    equilibrium closure, A = T C M.
+      D2Q9  (Lallemand basis): qx = -jx, qy = -jy, eps = -(rho + e); with_e: e = -2 rho, eps = rho
+      D3Q19 (d'Humieres basis): eps = -(7 rho + 11 e)/38 (w_eps = 3, w_epsj = -11/2), q = -2/3 j, pi_xx = -1/2 (3 p_xx),
+            pi_ww = -1/2 p_ww, m = 0
+    Tests pin the result to the reference's literals (tests/golden/stabilizer_tables.npz)."""
+    if stencil in ("D2Q9", "Stencil_D2Q9"):
+        M, T = make_M(LALLEMAND_D2Q9), make_T(LALLEMAND_D2Q9)
+        C = np.eye(9)
+        C[6], C[7], C[8] = -C[1], -C[2], 0.0
+        if with_e:
+            C[5] = -2.0 * np.eye(9)[0]
+            C[8] = np.eye(9)[0]
+        else:
+            C[8] = -np.eye(9)[0] - np.eye(9)[5]
+        return np.ascontiguousarray(T @ C @ M)
+    if stencil in ("D3Q19", "Stencil_D3Q19"):
+        if with_e:
+            raise ValueError("the with-e variant exists for D2Q9 only")
+        M, T = make_M(DHUMIERES_D3Q19), make_T(DHUMIERES_D3Q19)
+        I = np.eye(19)
+        C = I.copy()
+        C[2] = -(7.0 * I[0] + 11.0 * I[1]) / 38.0
+        C[4], C[6], C[8] = -2.0 / 3.0 * I[3], -2.0 / 3.0 * I[5], -2.0 / 3.0 * I[7]
+        C[10], C[12] = -0.5 * I[9], -0.5 * I[11]
+        C[16] = C[17] = C[18] = 0.0
+        return np.ascontiguousarray(T @ C @ M)
+    raise ValueError("PseudoEntropicStabilizer is only defined for D2Q9 and D3Q19")

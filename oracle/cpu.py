@@ -196,6 +196,21 @@ def apply_wall_hits(st, f, g, dest_index, dest_dir, kind, value):
                                      kk.ctypes.data_as(_i32p), _d(vv), _d(st.e), _d(st.w), C.c_double(st.scaling), C.c_double(st.cs2))
 
 
+def stabilizer_matrix(name, with_e=False):
+    """The reference's PseudoEntropicStabilizer literals (tests/golden/stabilizer_tables.npz,
+    PseudoEntropicStabilizer.cpp:27-150)."""
+    g = np.load(os.path.join(os.path.dirname(_HERE), "tests", "golden", "stabilizer_tables.npz"))
+    return np.ascontiguousarray(g["d3q19" if name == "D3Q19" else ("d2q9_with_e" if with_e else "d2q9")])
+
+
+def apply_stabilizer(f, A, n=None):
+    """PseudoEntropicStabilizer::apply in place."""
+    Q, stride = f.shape
+    n = stride if n is None else n
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    lib().orc_apply_stabilizer(C.c_int(Q), C.c_int64(n), C.c_int64(stride), _d(f), _d(A))
+
+
 def collide_entropic(st, f, viscosity, dt, scheme, in_init=False, u_init=None, rho_prev=None, n=None):
     """Legacy entropic collideAll in place.  scheme: "KBC_STANDARD" (D2Q9, D3Q15; KBCStandard.cpp:88-1028) or
     "MRT_ENTROPIC" (D3Q19; MRTEntropic.cpp:167-305).  tau is the legacy nu/(dt cs2).  Returns (rho, u_scaled, status)."""

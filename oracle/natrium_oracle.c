@@ -662,6 +662,25 @@ int orc_apply_wall_hits(int D, int Q, int64_t stride, double *f, double *g, int6
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * PseudoEntropicStabilizer::apply (L/dataprocessors/PseudoEntropicStabilizer.cpp:152-262): per owned DoF
+ * f_new[i] = sum_j A[i][j] f[j], j ascending from 0; A = n/d (D2Q9, :27-40), nd_d2q9_with_e (:42-57) or nd_d3q19
+ * (:59-150) -- passed in by the caller (tests use the literals extracted into tests/golden/stabilizer_tables.npz).
+ * ------------------------------------------------------------------------------------------ */
+void orc_apply_stabilizer(int Q, int64_t n, int64_t stride, double *f, const double *A)
+{
+#pragma omp parallel for schedule(static) if (n > 50000)
+    for (int64_t ii = 0; ii < n; ii++) {
+        double fi[ORC_MAXQ], fn[ORC_MAXQ];
+        for (int j = 0; j < Q; j++) fi[j] = f[j * stride + ii];
+        for (int i = 0; i < Q; i++) {
+            fn[i] = 0;
+            for (int j = 0; j < Q; j++) fn[i] += A[i * Q + j] * fi[j];
+        }
+        for (int j = 0; j < Q; j++) f[j * stride + ii] = fn[j];
+    }
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

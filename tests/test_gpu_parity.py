@@ -846,3 +846,68 @@ def test_step_host_equals_device_resident_step(case, ordered, chunks, oracle_lib
     if chunks > 1 and not with_g:
         assert ctx.kernel_launches() - l0 >= 3 * chunks * 3          # scatter, fused, gather per piece
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# pseudo-entropic stabilizer
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,with_e", [("c1_tgv2d_d2q9", False), ("c1_tgv2d_d2q9", True), ("tgv3d_d3q19_small", False)])
+def test_step_with_stabilizer_matches_oracle(case, with_e, oracle_lib):
+    """run() loop body with the PseudoEntropicStabilizer data processor (CFDSolver.cpp:884-891): stream, collide, then
+    f <- A f.  The oracle multiplies by the reference's literal matrix, the product by the host mirror's."""
+    from natrium_b200 import mrt
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case)
+    set_collision(ctx, c, dt)
+    name = c["stencil"]
+    ctx.set_post_collision_matrix(mrt.make_stabilizer(name, with_e))
+    A = oracle_lib.stabilizer_matrix(name, with_e)
+    stepper = oracle_lib.ReferenceOrderStepper(o["st"], o["blocks"], o["dofs"].N, c["nu"], dt)
+    f = o["f"].copy()
+    ctx.upload_populations(0, f)
+    for s in range(5):
+        ctx.step(1)
+        ctx.synchronize()
+        stepper.step(f)
+        oracle_lib.apply_stabilizer(f, A)
+        got = ctx.download_populations(0)
+        assert rel_err(got, f) <= TOL_STEP, (s, rel_err(got, f))
+        ctx.upload_populations(0, f)
+    # explicit application == DataProcessor::apply()
+    ctx.apply_post_collision()
+    oracle_lib.apply_stabilizer(f, A)
+    assert rel_err(ctx.download_populations(0), f) <= TOL_STEP
+    ctx.set_post_collision_matrix(None)
+    l0 = ctx.kernel_launches()
+    ctx.step(1)
+    assert ctx.kernel_launches() - l0 == 1
+    ctx.close()
+
+
+def test_config1_integration_with_stabilizer(oracle_lib):
+    """Integration test #11 (ConvergenceTestSemiLagrangianPeriodic, IntegrationTestCases.cpp:885-961) through the host
+    mirror: CFDSolver + appended PseudoEntropicStabilizer, device-resident run to t = 1/(2 nu);
+    E_kin(t)/E_kin(0) = exp(-2) +- 1e-2."""
+    from natrium_b200 import PseudoEntropicStabilizer, Stencil
+    from natrium_b200 import Context, harness
+    case = "c1_tgv2d_d2q9"
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case)
+    set_collision(ctx, c, dt)
+    from natrium_b200 import mrt
+    ctx.set_post_collision_matrix(mrt.make_stabilizer("D2Q9"))
+    ctx.upload_populations(0, o["f"])
+    ctx.collide()
+    E0 = ctx.conserved()[4]
+    steps = int(round(0.5 / dt))
+    ctx.step(steps)
+    ctx.synchronize()
+    ratio = ctx.conserved()[4] / E0
+    assert abs(ratio - np.exp(-4 * c["nu"] * steps * dt)) < 1e-2, ratio
+    with pytest.raises(Exception):
+        ctx45, *_ = make_ctx("tgv3d_d3q45", with_matrix=False)
+        try:
+            ctx45.set_post_collision_matrix(np.eye(45))
+        finally:
+            ctx45.close()
+    ctx.close()

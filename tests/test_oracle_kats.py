@@ -358,3 +358,49 @@ def test_wall_hits_properties(oracle_lib):
     # thermal hits need D3Q45 and g
     st19 = oracle_lib.Stencil("D3Q19", 1.0)
     assert oracle_lib.apply_wall_hits(st19, np.ones((19, 4)), None, [0], [1], [1], [0.85]) == -3
+
+
+# ---------------------------------------------------------------------------------------------
+# pseudo-entropic stabilizer
+# ---------------------------------------------------------------------------------------------
+def test_stabilizer_tables_and_properties(oracle_lib):
+    """The host mirror rebuilds the three stabilizer matrices from their moment-space definition; they equal the
+    reference's literals (PseudoEntropicStabilizer.cpp:27-150) to round-off.  The matrices are projections that
+    keep density, momentum and the second moments, and leave a BGK equilibrium at rest unchanged."""
+    from natrium_b200 import mrt
+    for name, with_e in [("D2Q9", False), ("D2Q9", True), ("D3Q19", False)]:
+        A = oracle_lib.stabilizer_matrix(name, with_e)
+        assert np.max(np.abs(mrt.make_stabilizer(name, with_e) - A)) <= 2e-16
+        assert np.max(np.abs(A @ A - A)) <= 1e-15
+        st = oracle_lib.Stencil(name, 1.0)
+        f = synthetic_populations(st.Q, 7) * st.w[:, None]
+        g = f.copy()
+        oracle_lib.apply_stabilizer(g, A)
+        assert np.max(np.abs(g.sum(0) - f.sum(0))) <= 1e-15
+        assert np.max(np.abs(st.e.T @ g - st.e.T @ f)) <= 1e-15
+        if not with_e:     # the with-e variant also replaces the energy moment
+            P0 = np.einsum("qa,qb,qn->abn", st.e, st.e, f)
+            P1 = np.einsum("qa,qb,qn->abn", st.e, st.e, g)
+            assert np.max(np.abs(P1 - P0)) <= 1e-15
+        rest = st.w[:, None] * np.ones((st.Q, 1))
+        r2 = rest.copy()
+        oracle_lib.apply_stabilizer(r2, A)
+        assert np.max(np.abs(r2 - rest)) <= 1e-15
+
+
+def test_config1_energy_decay_with_stabilizer(oracle_lib):
+    """Integration test #11 as the reference runs it: with the PseudoEntropicStabilizer appended as data processor
+    (IntegrationTestCases.cpp:924); same bound, E_kin(t)/E_kin(0) = exp(-2) +- 1e-2 at t = 1/(2 nu)."""
+    o = common.oracle_problem("c1_tgv2d_d2q9")
+    st, n, dt, nu = o["st"], o["dofs"].N, o["dt"], 1.0
+    A = oracle_lib.stabilizer_matrix("D2Q9")
+    f = o["f"].copy()
+    stepper = oracle_lib.ReferenceOrderStepper(st, o["blocks"], n, nu, dt)
+    r0, u0, _ = oracle_lib.collide_bgk(st, f, nu, dt)
+    E0 = 0.5 * (r0 * (u0 ** 2).sum(0)).sum()
+    steps = int(round(0.5 / dt))
+    for _ in range(steps):
+        stepper.step(f)
+        oracle_lib.apply_stabilizer(f, A)
+    E = 0.5 * (stepper.rho * (stepper.u ** 2).sum(0)).sum()
+    assert abs(E / E0 - math.exp(-4 * nu * steps * dt)) < 1e-2
