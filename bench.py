@@ -121,7 +121,7 @@ def ncu_traffic(workload_key):
 
 
 # ------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup, layers, target_s=12.0):
+def cpu_reference_run(args, steps, warmup, layers, target_s=12.0, gpu_parity=False):
     """Reference-ordered CPU step (oracle port, OpenMP over rows/DoFs) on a z-slab sample of the workload."""
     from natrium_b200 import harness
     from natrium_b200.stencils import Stencil
@@ -146,6 +146,33 @@ def cpu_reference_run(args, steps, warmup, layers, target_s=12.0):
     rho, u = harness.taylor_green_3d(x, st.getSpeedOfSound())
     f = harness.equilibrium_distributions(st, rho, u)
     stepper = cpu.ReferenceOrderStepper(ost, blocks, n, 2 * math.pi, dt)
+    parity = None
+    if gpu_parity:
+        # parity gate that accompanies the throughput number: the GPU path on this very sample, 10 steps from
+        # the identical state, against the oracle -- max relative error per population value
+        from natrium_b200 import Context
+        ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+        ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+        ctx.set_layout(part.n_owned, part.n_ghost, False)
+        ctx.set_dof_order(part.cell_blocked_order())
+        for (bi, bj), m in blocks.items():
+            ctx.upload_block_csr(bi, bj, m.indptr, m.indices, m.data)
+        ctx.finalize_matrix()
+        ones = np.ones((st.getQ(), n))
+        ctx.upload_populations(0, ones)
+        ctx.stream(0)
+        row_sum_err = float(np.max(np.abs(ctx.download_populations(0) - 1.0)))      # M 1 = 1 (SemiLagrangian_test.cpp:519-596)
+        ctx.set_collision(2 * math.pi, dt)
+        ctx.upload_populations(0, f)
+        ctx.step(10)
+        ctx.synchronize()
+        got = ctx.download_populations(0)
+        fr = f.copy()
+        for _ in range(10):
+            stepper.step(fr)
+        parity = {"steps": 10, "max_rel_err": float(np.max(np.abs(got - fr) / np.abs(fr))), "row_sum_err": row_sum_err,
+                  "staged": bool(ctx.matrix_format_info()["staged"]), "sample": f"{cells[0]}x{cells[1]}x{cells[2]} cells"}
+        ctx.close()
     for _ in range(warmup):
         stepper.step(f)
     if steps <= 0:                       # calibrate: about `target_s` seconds of CPU work
@@ -161,7 +188,7 @@ def cpu_reference_run(args, steps, warmup, layers, target_s=12.0):
     return dict(value=val, unit=UNIT, cores=cpu.num_threads(), kind="port",
                 sample=f"{cells[0]}x{cells[1]}x{cells[2]} cells of the {args.cells}^3 workload ({n} DoFs, "
                        f"{stepper.b.nnz} nnz), {steps} reference-ordered steps (copy + {st.getQ()-1} CSR SpMV + collide), "
-                       f"oracle C port with OpenMP, {el:.1f} s"), el / steps * 1e3
+                       f"oracle C port with OpenMP, {el:.1f} s", parity_vs_gpu=parity), el / steps * 1e3
 
 
 def run_reference(args):
@@ -186,7 +213,7 @@ def workload_config(args, n_gpus):
     nd = args.cells * args.order + 1
     return {"workload": f"TGV3D {args.stencil} BGK semi-Lagrangian p={args.order} {args.cells}^3 cells/GPU "
                         f"({nd}^3 DoFs/GPU) x {n_gpus} GPU slab(s) along z",
-            "cells_per_gpu": args.cells ** 3, "fe_order": args.order, "stencil": args.stencil, "collision": "BGK_STANDARD",
+            "cells_per_gpu": args.cells ** 3, "fe_order": args.order, "stencil": args.stencil, "collision": "BGK_STANDARD" if args.stencil not in ("D2Q25H", "D3Q45") else "BGK_STANDARD f+g quartic Pr=0.71 Sutherland",
             "cfl": 0.4, "mach": 0.05, "parallelism": f"slab x{n_gpus} (NCCL ghost exchange)" if n_gpus > 1 else "single GPU",
             "l2_policy": "inputs_exceed_l2 (matrix stream per step >> 126 MB L2)"}
 
@@ -214,15 +241,16 @@ def run_ours(args):
         uid = box[0]
 
     Ma = 0.05
-    st = Stencil(args.stencil, math.sqrt(3) / Ma)
+    with_g = args.stencil in ("D2Q25H", "D3Q45")      # compressible two-distribution configurations (not the bench line)
+    st = Stencil(args.stencil, 1.0 if with_g else math.sqrt(3) / Ma)
     cells = [args.cells, args.cells, args.cells * world]
     pb = harness.CartesianProblem(3, cells, args.order, length=[2 * math.pi, 2 * math.pi, 2 * math.pi * world])
     dt = pb.timestep(st, 0.4)
-    nu = 2 * math.pi            # Re = 1 as in sl_parallel_benchmark_periodic/benchmark.cpp:58-66
+    nu = 0.01 if with_g else 2 * math.pi            # Re = 1 as in sl_parallel_benchmark_periodic/benchmark.cpp:58-66
     ctx = Context(local, rank, world, uid)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     part = harness.SlabPartition(pb, st, dt, rank, world)
-    ctx.set_layout(part.n_owned, part.n_ghost, False)
+    ctx.set_layout(part.n_owned, part.n_ghost, with_g)
     from natrium_b200 import _capi
     fmt_code = {"dict": _capi.FORMAT_DICT, "dict-unstaged": _capi.FORMAT_DICT_UNSTAGED, "ell": _capi.FORMAT_ELL}[args.format]
     ctx.set_matrix_format(fmt_code, args.dedup_tol if args.format != "ell" else 0.0)
@@ -233,11 +261,17 @@ def run_ours(args):
     t_asm = time.perf_counter() - t0
     if world > 1:
         ctx.set_halo(*part.halo_plan())
-    ctx.set_collision(nu, dt)
     n = part.n_owned
     Q, D = st.getQ(), st.getD()
-    rho, u = harness.taylor_green_3d(part.owned_points(), st.getSpeedOfSound())
-    f0 = harness.equilibrium_distributions(st, rho, u)
+    if with_g:
+        ctx.set_collision(nu, dt, equilibrium=_capi.QUARTIC_EQUILIBRIUM, with_g=True, gamma=1.4, prandtl=0.71, sutherland=True)
+        rho, u = harness.taylor_green_3d(part.owned_points(), st.getSpeedOfSound(), compressible=True, density_numerator=0.1)
+        f0, g0 = harness.quartic_equilibrium_distributions(st, rho, 0.1 * u, np.ones(n), 1.4)
+        ctx.upload_populations(1, g0)
+    else:
+        ctx.set_collision(nu, dt)
+        rho, u = harness.taylor_green_3d(part.owned_points(), st.getSpeedOfSound())
+        f0 = harness.equilibrium_distributions(st, rho, u)
     ctx.upload_populations(0, f0)
     ctx.collide()               # run(): collide once before the loop
 
@@ -290,17 +324,19 @@ def run_ours(args):
     ms_e2e = ctx.timer_stop()
     barrier()
     assert np.isfinite(hmom.numpy()).all() and np.isfinite(bufs[e2e_steps & 1].numpy()).all()
+    if with_g:
+        ms_e2e = 0.0                # g stays on the device in nb200_step_host: no end-to-end number for f+g
     if world > 1:
         t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
-    e2e_val = n_global * Q * e2e_steps / (ms_e2e * 1e-3) / 1e6
+    e2e_val = None if with_g else n_global * Q * e2e_steps / (ms_e2e * 1e-3) / 1e6
     h2d = Q * n * 8
     d2h = Q * n * 8 + (1 + D) * n * 8
 
     # ---- roofline of the dominant kernel (the fused stream+collide kernel: one launch per step per GPU)
     peak, peak_src = measured_peak()
-    bpd = algorithmic_bytes_per_dof(nnz / n, D, Q)
+    bpd = algorithmic_bytes_per_dof(nnz / n, D, Q, with_g)
     alg_bytes = bpd * n
     kern_ms = ms / args.steps          # N=1: the step IS the kernel launch; N>1 includes the halo exchange
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -319,7 +355,13 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            cpu_base, _ = cpu_reference_run(args, 0, 1, args.cpu_sample_layers)
+            cpu_base, _ = cpu_reference_run(args, 0, 1, args.cpu_sample_layers, gpu_parity=True)
+            pg = cpu_base.get("parity_vs_gpu")
+            if pg is not None:
+                pg["tolerance"] = 1e-12
+                pg["ok"] = bool(pg["max_rel_err"] <= 1e-12 and pg["row_sum_err"] <= 1e-12)
+                if not pg["ok"]:
+                    print(f"PARITY GATE FAILED: {pg}", file=sys.stderr, flush=True)
         except Exception as ex:    # the baseline is a reported number, never a reason to lose the bench line
             cpu_base = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
 

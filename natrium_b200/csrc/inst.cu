@@ -234,7 +234,7 @@ const NbStencilOps ops = {D, Q,
 #else
                           nullptr,
 #endif
-                          collide, conserved, wall,
+                          collide, conserved, wall, bind,
 #if NB_HAS_MRT
                           post
 #else

@@ -40,6 +40,7 @@ struct NbStencilOps {
     int (*collide)(const NbLaunch&);     // in-place collide
     int (*conserved)(const NbLaunch&);   // deterministic conserved sums
     int (*wall)(const NbLaunch&);        // wall hits on yf (and yg)
+    int (*bind)(const NbLaunch&);        // uploads the constant block if this context's version is not the bound one
     int (*post)(const NbLaunch&);        // post-collision matrix on yf; nullptr where the reference has none
 };
 

@@ -447,7 +447,10 @@ extern "C" int nb200_create(nb200_ctx** out, int device, int rank, int nranks, c
         return NB200_ERR_CUDA;
     }
     if (nranks > 1) {
-        if (cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // numerically lowest value = highest priority
+        // the exchange (and the boundary CTAs behind it) must not queue behind the interior kernel's ~16k CTAs
+        if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_prev, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess) { delete c; return NB200_ERR_CUDA; }
         {
@@ -1488,9 +1491,10 @@ static int cuda_rc(nb200_ctx* c, int rc, const char* what)
 }
 
 // flip: swap the ping-pong buffers afterwards (false for the first of two partial launches of one step)
-static int dispatch_fused(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0, bool flip = true)
+static int dispatch_fused(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0, bool flip = true, cudaStream_t st = nullptr)
 {
     NbLaunch L = make_launch(c, cta_map, n_cta);
+    if (st) L.stream = st;
     L.xf = c->pop[0][c->cur[0]];
     L.yf = c->pop[0][c->cur[0] ^ 1];
     if (c->cp.with_g) { L.xg = c->pop[1][c->cur[1]]; L.yg = c->pop[1][c->cur[1] ^ 1]; }
@@ -1646,6 +1650,14 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
     // With the staged kernels the exchange runs on its own stream while the CTAs that read no ghost slot work;
     // the CTAs that do are launched behind it ("overlapped with interior-row SpMV").
     const bool do_g = c->cp.with_g != 0;
+    if (c->comm_stream) {
+        // kernels of one step run on two streams: make sure the constant block is in place before either starts
+        NbLaunch L = make_launch(c);
+        CUDA_TRY(c, cudaStreamSynchronize(c->comm_stream));
+        rc = cuda_rc(c, c->ops->bind(L), "constant upload");
+        if (rc) return rc;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     const bool split = c->overlap && c->nranks > 1 && c->n_nbr > 0 && c->fmt == NB_FMT_DICT && c->staged
         && c->n_cta_interior > 0 && c->n_cta_boundary > 0;
     for (int s = 0; s < n_steps; s++) {
@@ -1668,9 +1680,12 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             if (rc) return rc;
             CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
             if (use_fused(c)) {
-                rc = dispatch_fused(c, c->d_cta_interior, c->n_cta_interior, false);
+                // boundary CTAs ride the (high-priority) exchange stream right behind the unpack, so they overlap the
+                // tail of the interior kernel; the context stream joins both before the buffers flip
+                rc = dispatch_fused(c, c->d_cta_boundary, c->n_cta_boundary, false, c->comm_stream);
+                CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+                if (!rc) rc = dispatch_fused(c, c->d_cta_interior, c->n_cta_interior, true);
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-                if (!rc) rc = dispatch_fused(c, c->d_cta_boundary, c->n_cta_boundary, true);
             } else {
                 rc = launch_stream(c, true, do_g, c->d_cta_interior, c->n_cta_interior, false);
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
