@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample-layers", type=int, default=8, help="z cell layers of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="dict", choices=["dict", "dict-unstaged", "ell"], help="device format of the streaming matrix")
-    ap.add_argument("--dof-order", default="cell", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--dof-order", default="none", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--numbering", default="cell", choices=["cell", "lex"],
+                    help="host DoF numbering of the synthetic problem: cell-wise like deal.II (default) or lexicographic")
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     return ap.parse_args()
 
@@ -254,23 +256,25 @@ def run_ours(args):
     from natrium_b200 import _capi
     fmt_code = {"dict": _capi.FORMAT_DICT, "dict-unstaged": _capi.FORMAT_DICT_UNSTAGED, "ell": _capi.FORMAT_ELL}[args.format]
     ctx.set_matrix_format(fmt_code, args.dedup_tol if args.format != "ell" else 0.0)
-    if args.dof_order == "cell":
+    numbering = harness.CellNumbering(part) if args.numbering == "cell" else None
+    host = numbering if numbering is not None else part       # what the host sees: points, halo plan
+    if args.dof_order == "cell" and numbering is None:
         ctx.set_dof_order(part.cell_blocked_order())
     t0 = time.perf_counter()
-    nnz = harness.upload_streaming_matrix(ctx, pb, part, st, dt)
+    nnz = harness.upload_streaming_matrix(ctx, pb, part, st, dt, numbering)
     t_asm = time.perf_counter() - t0
     if world > 1:
-        ctx.set_halo(*part.halo_plan())
+        ctx.set_halo(*host.halo_plan())
     n = part.n_owned
     Q, D = st.getQ(), st.getD()
     if with_g:
         ctx.set_collision(nu, dt, equilibrium=_capi.QUARTIC_EQUILIBRIUM, with_g=True, gamma=1.4, prandtl=0.71, sutherland=True)
-        rho, u = harness.taylor_green_3d(part.owned_points(), st.getSpeedOfSound(), compressible=True, density_numerator=0.1)
+        rho, u = harness.taylor_green_3d(host.owned_points(), st.getSpeedOfSound(), compressible=True, density_numerator=0.1)
         f0, g0 = harness.quartic_equilibrium_distributions(st, rho, 0.1 * u, np.ones(n), 1.4)
         ctx.upload_populations(1, g0)
     else:
         ctx.set_collision(nu, dt)
-        rho, u = harness.taylor_green_3d(part.owned_points(), st.getSpeedOfSound())
+        rho, u = harness.taylor_green_3d(host.owned_points(), st.getSpeedOfSound())
         f0 = harness.equilibrium_distributions(st, rho, u)
     ctx.upload_populations(0, f0)
     ctx.collide()               # run(): collide once before the loop
@@ -341,7 +345,8 @@ def run_ours(args):
     kern_ms = ms / args.steps          # N=1: the step IS the kernel launch; N>1 includes the halo exchange
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     info = ctx.matrix_info()
-    traffic = ncu_traffic(f"{args.stencil}_p{args.order}_{args.cells}_{args.format}") if args.dof_order == "cell" else None
+    cell_rows = args.numbering == "cell" or args.dof_order == "cell"
+    traffic = ncu_traffic(f"{args.stencil}_p{args.order}_{args.cells}_{args.format}") if cell_rows else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "dram_frac_of_peak": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": bpd, "algorithmic_bytes_per_launch": alg_bytes,
@@ -350,7 +355,7 @@ def run_ours(args):
                 "device_format_bytes": info["device_bytes"], "nnz": nnz,
                 "note": "frac is defined on the algorithmic bytes B = 12*nnz + populations (SURVEY 8d); the dictionary format moves ~6x fewer "
                         "DRAM bytes (traffic), so frac > 1; the kernel's actual limiter is the L1/shared-memory data pipe (ncu: "
-                        "l1tex__data_pipe_lsu_wavefronts 84 % of peak, profiles/r01_fused_staged_v5b_ncu_selected.json)", "matrix_format": ctx.matrix_format_info(), "dof_order": args.dof_order}
+                        "l1tex__data_pipe_lsu_wavefronts 84 % of peak, profiles/r01_fused_staged_v5b_ncu_selected.json)", "matrix_format": ctx.matrix_format_info(), "dof_order": args.dof_order, "host_numbering": args.numbering}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

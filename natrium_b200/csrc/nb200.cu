@@ -1816,9 +1816,13 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     for (int k = 0; k < C; k++) {
         const int64_t u0 = H.u_off[(size_t)k], u1 = H.u_off[(size_t)k + 1];
         if (u1 > u0) {
-            CUDA_TRY(c, cudaMemcpy2DAsync(H.d_in + u0, (size_t)n * 8, f_in + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyHostToDevice, H.s_up));
-            k_chunk_scatter<<<dim3(grid_for(u1 - u0, 256), (unsigned)Q), 256, 0, H.s_up>>>(u0, u1, Q, perm, H.d_in, n, x, c->stride);
-            c->launches++;
+            if (perm) {
+                CUDA_TRY(c, cudaMemcpy2DAsync(H.d_in + u0, (size_t)n * 8, f_in + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyHostToDevice, H.s_up));
+                k_chunk_scatter<<<dim3(grid_for(u1 - u0, 256), (unsigned)Q), 256, 0, H.s_up>>>(u0, u1, Q, perm, H.d_in, n, x, c->stride);
+                c->launches++;
+            } else {   // host numbering = device numbering: straight into the population arrays
+                CUDA_TRY(c, cudaMemcpy2DAsync(x + u0, (size_t)c->stride * 8, f_in + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyHostToDevice, H.s_up));
+            }
         }
         CUDA_TRY(c, cudaEventRecord(H.ev_up[(size_t)k], H.s_up));
     }
@@ -1843,6 +1847,12 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
         const int64_t u0 = H.u_off[(size_t)j], u1 = H.u_off[(size_t)j + 1];
         CUDA_TRY(c, cudaStreamWaitEvent(H.s_dn, H.ev_done[(size_t)H.dl_after[(size_t)j]], 0));
         if (u1 <= u0) continue;
+        if (!perm) {
+            CUDA_TRY(c, cudaMemcpy2DAsync(f_out + u0, (size_t)n * 8, y + u0, (size_t)c->stride * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyDeviceToHost, H.s_dn));
+            if (rho) CUDA_TRY(c, cudaMemcpyAsync(rho + u0, c->rho + u0, (size_t)(u1 - u0) * 8, cudaMemcpyDeviceToHost, H.s_dn));
+            if (u) CUDA_TRY(c, cudaMemcpy2DAsync(u + u0, (size_t)n * 8, c->u + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)D, cudaMemcpyDeviceToHost, H.s_dn));
+            continue;
+        }
         k_chunk_gather<<<dim3(grid_for(u1 - u0, 256), (unsigned)Q), 256, 0, H.s_dn>>>(u0, u1, Q, perm, y, c->stride, o_f, n);
         c->launches++;
         CUDA_TRY(c, cudaMemcpy2DAsync(f_out + u0, (size_t)n * 8, o_f + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyDeviceToHost, H.s_dn));

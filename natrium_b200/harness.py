@@ -264,11 +264,51 @@ def assemble_direction(problem, part, stencil, dt, alpha):
     return rowptr, col[keep].astype(np.int32), val[keep]
 
 
-def upload_streaming_matrix(ctx, problem, part, stencil, dt):
-    """Assemble and hand over all diagonal blocks one at a time (peak host memory = one block)."""
+class CellNumbering:
+    """The same partition with the owned DoFs numbered the way deal.II numbers them: cell by cell in the order
+    fillSparseObject walks (SlabPartition.cell_blocked_order).  With it the host's numbering already is the one the
+    staged kernels like, no nb200_set_dof_order hint is needed, and host buffers map 1:1 onto device arrays."""
+
+    def __init__(self, part):
+        self.part = part
+        self.order = part.cell_blocked_order().astype(np.int64)      # new index k <- old index order[k]
+        self.perm = np.empty_like(self.order)
+        self.perm[self.order] = np.arange(len(self.order))
+        self.n_owned, self.n_ghost = part.n_owned, part.n_ghost
+
+    def owned_points(self):
+        return self.part.owned_points()[self.order]
+
+    def halo_plan(self):
+        nbr, send_off, send_idx, recv_off = self.part.halo_plan()
+        return nbr, send_off, self.perm[send_idx].astype(np.int32), recv_off
+
+    def renumber_csr(self, rowptr, col, val):
+        n = self.n_owned
+        lens = np.diff(rowptr)
+        if len(val) and np.all(lens == lens[0]):
+            k = int(lens[0])
+            col2 = col.reshape(n, k)[self.order].reshape(-1)
+            val2 = val.reshape(n, k)[self.order].reshape(-1)
+            rowptr2 = rowptr
+        else:
+            new_lens = lens[self.order]
+            rowptr2 = np.concatenate([[0], np.cumsum(new_lens)]).astype(np.int64)
+            src = np.repeat(rowptr[:-1][self.order] - rowptr2[:-1], new_lens) + np.arange(rowptr2[-1])
+            col2, val2 = col[src], val[src]
+        owned = col2 < n
+        col2 = np.where(owned, self.perm[np.where(owned, col2, 0)], col2).astype(np.int32)
+        return rowptr2, col2, val2
+
+
+def upload_streaming_matrix(ctx, problem, part, stencil, dt, numbering=None):
+    """Assemble and hand over all diagonal blocks one at a time (peak host memory = one block).
+    numbering: a CellNumbering of ``part`` -- rows and owned columns are renumbered before the upload."""
     nnz = 0
     for alpha in range(1, stencil.getQ()):
         rowptr, col, val = assemble_direction(problem, part, stencil, dt, alpha)
+        if numbering is not None:
+            rowptr, col, val = numbering.renumber_csr(rowptr, col, val)
         ctx.upload_block_csr(alpha - 1, alpha - 1, rowptr, col, val)
         nnz += len(val)
     ctx.finalize_matrix()

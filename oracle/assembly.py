@@ -216,6 +216,8 @@ def assemble_semilagrangian(mesh, p, e, dt, numbering=None, opposite=None):
     minus_dt_e = -dt * e
     rows = {}
     tracked = np.zeros(N, dtype=bool)
+    hits = []            # m_boundaryHandler.addHit(el, bi) in call order (SemiLagrangian.cpp:381-383)
+    cell_rank = {c: k for k, c in enumerate(mesh.cells())}
 
     def add(bi, bj, r, c, v):
         rows.setdefault((bi, bj), []).append((r, c, v))
@@ -275,6 +277,9 @@ def assemble_semilagrangian(mesh, p, e, dt, numbering=None, opposite=None):
                     vel = math.sqrt(float(np.dot(ed, ed)))
                     dist = math.sqrt(sum((el["dep"][k] - el["cur"][k]) ** 2 for k in range(dim)))
                     el["dep"] = [el["cur"][k] - ed[k] * dist / vel for k in range(dim)]
+                    # BoundaryHit ctor (BoundaryHit.h:40-56): dtHit = dt - |currentPoint - departurePoint| / |e_cur|
+                    hits.append(dict(index=el["dest"], direction=el["dest_dir"], point=tuple(el["cur"]), cell=cell_rank[tuple(c)],
+                                     boundary=(d, side), dt_hit=dt - dist / vel, seq=len(hits)))
             else:
                 nc = list(c)
                 nc[d] += -1 if side == 0 else 1
@@ -297,4 +302,7 @@ def assemble_semilagrangian(mesh, p, e, dt, numbering=None, opposite=None):
         m = sp.coo_matrix((v, (r, c)), shape=(N, N)).tocsr()   # add() accumulates duplicates
         m.sort_indices()
         blocks[key] = m
+    # HitList iteration order of SemiLagrangianBoundaryHandler::operate (SemiLagrangianBoundaryHandler.cpp:43-109):
+    # std::map over cells, then over hit points, then the hits of a point in insertion order
+    dofs.hits = sorted(hits, key=lambda h: (h["cell"], h["point"], h["seq"]))
     return blocks, dofs

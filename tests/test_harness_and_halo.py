@@ -153,3 +153,31 @@ def test_staging_tables_replay(tmp_path):
                          (("300000", "6", "32", "5", "256", "4"), "OK"), (("777", "3", "1", "40", "4096", "5"), "INFEASIBLE")]:
         out = subprocess.run([exe, *args], check=True, capture_output=True, text=True).stdout
         assert out.startswith(expect), out
+
+
+def test_cell_numbering_renumbers_consistently():
+    """harness.CellNumbering (host numbering = deal.II-like cell-wise order): P A P^T applied to P x equals P (A x),
+    entry order inside a row (= summation order) is untouched, ghost columns keep their slots, the halo plan follows."""
+    st = Stencil("D3Q19", math.sqrt(3) / 0.05)
+    pb = harness.CartesianProblem(3, [3, 2, 4], 2)
+    dt = pb.timestep(st, 0.4)
+    for rank, world in [(0, 1), (1, 2)]:
+        part = harness.SlabPartition(pb, st, dt, rank, world)
+        num = harness.CellNumbering(part)
+        n, ng = part.n_owned, part.n_ghost
+        assert sorted(num.order.tolist()) == list(range(n))
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(n + ng)
+        xp = np.concatenate([x[:n][num.order], x[n:]])
+        for alpha in (1, 7, 12):
+            rp, col, val = harness.assemble_direction(pb, part, st, dt, alpha)
+            rp2, col2, val2 = num.renumber_csr(rp, col, val)
+            A = sp.csr_matrix((val, col, rp), shape=(n, n + ng))
+            B = sp.csr_matrix((val2, col2, rp2), shape=(n, n + ng))
+            assert np.max(np.abs(B @ xp - (A @ x)[num.order])) <= 1e-14
+            assert np.array_equal(val2.reshape(n, -1), val.reshape(n, -1)[num.order])
+        assert np.allclose(num.owned_points(), part.owned_points()[num.order])
+        if world > 1:
+            nbr, so, si, ro = part.halo_plan()
+            nbr2, so2, si2, ro2 = num.halo_plan()
+            assert np.array_equal(num.order[si2], si) and np.array_equal(so, so2) and np.array_equal(ro, ro2)

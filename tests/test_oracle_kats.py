@@ -404,3 +404,28 @@ def test_config1_energy_decay_with_stabilizer(oracle_lib):
         oracle_lib.apply_stabilizer(f, A)
     E = 0.5 * (stepper.rho * (stepper.u ** 2).sum(0)).sum()
     assert abs(E / E0 - math.exp(-4 * nu * steps * dt)) < 1e-2
+
+
+def test_walled_assembly_bounce_blocks_and_hits(oracle_lib):
+    """Wall treatment of fillSparseObject (SemiLagrangian.cpp:358-384): a path that reaches a VelocityNeqBounceBack /
+    ThermalBounceBack wall is reflected with the opposite direction, so its row lands in the off-diagonal block
+    (alpha, opposite(alpha)), rows still sum to one (the property SemiLagrangian*_ConstantStreaming_test pins), and
+    one BoundaryHit per bounced path is recorded with 0 <= dtHit <= dt (BoundaryHit.h:40-56)."""
+    st = oracle_lib.Stencil("D2Q9", 3.0)
+    opp = np.array([int(np.argmin(np.abs(st.e + st.e[i]).sum(1))) for i in range(9)])
+    mesh = assembly.CartesianMesh([np.linspace(0, 2.0, 6), 2.0 * np.array([0, 0.2, 0.45, 0.75, 1.0])], boundary=["periodic", "wall"])
+    dt = assembly.calculate_timestep(mesh, 3, st.max_speed, 0.8)
+    blocks, dofs = assembly.assemble_semilagrangian(mesh, 3, st.e, dt, opposite=opp)
+    ones = np.ones(dofs.N)
+    for a in range(8):
+        y = sum(blocks[k] @ ones for k in blocks if k[0] == a)
+        assert np.max(np.abs(y - 1.0)) <= 1e-12
+    assert {k for k in blocks if k[0] != k[1]} <= {(a - 1, opp[a] - 1) for a in range(1, 9)}
+    assert len(dofs.hits) > 0
+    for h in dofs.hits:
+        a = h["direction"]
+        assert st.e[a][1] != 0                                   # only directions with a wall-normal component bounce
+        assert blocks[(a - 1, opp[a] - 1)][h["index"]].nnz > 0
+        assert -1e-14 <= h["dt_hit"] <= dt + 1e-14
+    keys = [(h["cell"], h["point"]) for h in dofs.hits]
+    assert keys == sorted(keys)                                  # HitList iteration order: cell, then point
