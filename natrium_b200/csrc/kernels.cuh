@@ -144,14 +144,22 @@ k_stream_collide_f_staged(StreamArgs A, const double* __restrict__ x, double* __
         }
         nb_stage_pass<1>(A.stage_col + ps.begin, ps.count, tid, x, x, xs, xs);
         __syncthreads();
+        // Rows t and t + 64 of a CTA are the same position in two neighbouring cells whenever the cells are alike, i.e.
+        // they use the same weight pattern.  Each half of the CTA therefore takes every other direction for BOTH rows:
+        // a weight is loaded once and used twice, which halves the weight traffic through the L1.
+        static_assert(NB_CTA_ROWS == 128, "row pairing assumes two 64-row halves");
+        const int half = tid >> 6, t0 = tid & 63;
 #pragma unroll 1
-        for (int a = ps.a0; a < ps.a1; a++) {
-            const int2 d = reinterpret_cast<const int2*>(&tile[a + 1][tid])[0];
-            double r, dummy;
-            nb_row_dot_staged<1>(A, a, d, xs, xs, r, dummy);
-            tile[a + 1][tid] = r;
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = reinterpret_cast<const int2*>(&tile[a + 1][t0])[0];
+            const int2 d1 = reinterpret_cast<const int2*>(&tile[a + 1][t0 + 64])[0];
+            double r0, r1;
+            nb_row_dot_staged_pair(A, a, d0, d1, xs, r0, r1);
+            tile[a + 1][t0] = r0;
+            tile[a + 1][t0 + 64] = r1;
         }
     }
+    __syncthreads();          // results of a row come from the other half of the CTA
     if (!active) return;
     double f[Q];
 #pragma unroll

@@ -299,6 +299,81 @@ __device__ __forceinline__ void nb_row_dot_staged(const StreamArgs& A, int alpha
     y1 = a1;
 }
 
+// Two rows that share class and weight pattern (the same position in two neighbouring cells): every weight is loaded
+// once and feeds both rows.  Per row the summation order is unchanged (k = 0..K-1), so the results are bit-identical to
+// nb_row_dot_staged.
+template <bool STREAMED, int B2>
+__device__ __forceinline__ void nb_staged_batches_pair(const double2* __restrict__ W2, int K, int64_t P,
+                                                       const double* __restrict__ s0, const double* __restrict__ s1,
+                                                       double& a0, double& a1)
+{
+    const int Kh = (K + 1) >> 1;
+    for (int kk = 0; kk < Kh; kk += B2) {
+        double2 vv[B2];
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int kj = min(kk + j, Kh - 1);
+            vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
+        }
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int k = 2 * (kk + j);
+            if (k < K) {
+                a0 += vv[j].x * s0[k];
+                a1 += vv[j].x * s1[k];
+            }
+            if (k + 1 < K) {
+                a0 += vv[j].y * s0[k + 1];
+                a1 += vv[j].y * s1[k + 1];
+            }
+        }
+    }
+}
+
+// Rows r0 and r1 of one direction (descriptors d0, d1) from the staged values xs: shared-weight path when both rows
+// have the same class and pattern, two independent products otherwise.
+__device__ __forceinline__ void nb_row_dot_staged_pair(const StreamArgs& A, int alpha_m1, int2 d0, int2 d1,
+                                                       const double* __restrict__ xs, double& y0, double& y1)
+{
+    const unsigned x0 = (unsigned)d0.x, x1 = (unsigned)d1.x;
+    if ((x0 >> 16) == (x1 >> 16) && d0.y == d1.y) {
+        const unsigned cls = x0 >> 16;
+        int K, streamed;
+        int64_t P;
+        const double* __restrict__ W;
+        if (cls == 0) {
+            const int kk = A.c0_K[alpha_m1];
+            K = kk & 0x3fffffff;
+            streamed = kk >> 30;
+            P = A.c0_P[alpha_m1];
+            W = A.c0_W[alpha_m1] + 2 * (int64_t)(unsigned)d0.y;
+        } else {
+            const NbDirClass* __restrict__ C = A.cls + alpha_m1 * NB_MAX_CLS + cls;
+            K = C->K;
+            streamed = C->streamed;
+            P = C->P;
+            W = C->W + 2 * (int64_t)(unsigned)d0.y;
+        }
+        const double2* W2 = reinterpret_cast<const double2*>(W);
+        const double* __restrict__ s0 = xs + (x0 & 0xffffu);
+        const double* __restrict__ s1 = xs + (x1 & 0xffffu);
+        double a0 = 0.0, a1 = 0.0;
+        if (streamed) {
+            if (K <= 8) nb_staged_batches_pair<true, 4>(W2, K, P, s0, s1, a0, a1);
+            else nb_staged_batches_pair<true, 7>(W2, K, P, s0, s1, a0, a1);
+        } else {
+            if (K <= 8) nb_staged_batches_pair<false, 4>(W2, K, P, s0, s1, a0, a1);
+            else nb_staged_batches_pair<false, 7>(W2, K, P, s0, s1, a0, a1);
+        }
+        y0 = a0;
+        y1 = a1;
+    } else {
+        double dummy;
+        nb_row_dot_staged<1>(A, alpha_m1, d0, xs, xs, y0, dummy);
+        nb_row_dot_staged<1>(A, alpha_m1, d1, xs, xs, y1, dummy);
+    }
+}
+
 // ---- staging: 8-byte asynchronous copies global -> shared (LDGSTS), so that a thread has all its gathers of a
 // pass in flight at once instead of waiting for each batch to land in registers ----
 __device__ __forceinline__ void nb_cp_async8(double* smem_dst, const double* gmem_src)
