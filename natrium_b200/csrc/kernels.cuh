@@ -153,10 +153,10 @@ k_stream_collide_f_staged(StreamArgs A, const double* __restrict__ x, double* __
         for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
             const int2 d0 = reinterpret_cast<const int2*>(&tile[a + 1][t0])[0];
             const int2 d1 = reinterpret_cast<const int2*>(&tile[a + 1][t0 + 64])[0];
-            double r0, r1;
-            nb_row_dot_staged_pair(A, a, d0, d1, xs, r0, r1);
-            tile[a + 1][t0] = r0;
-            tile[a + 1][t0 + 64] = r1;
+            double r[4];
+            nb_row_dot_staged_pair<1>(A, a, d0, d1, xs, xs, r);
+            tile[a + 1][t0] = r[0];
+            tile[a + 1][t0 + 64] = r[1];
         }
     }
     __syncthreads();          // results of a row come from the other half of the CTA
@@ -204,15 +204,21 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
         }
         nb_stage_pass<2>(A.stage_col + ps.begin, ps.count, tid, xf, xg, xsf, xsg);
         __syncthreads();
+        // row pairing as in k_stream_collide_f_staged: one weight load feeds two rows and two distributions
+        const int half = tid >> 6, t0 = tid & 63;
 #pragma unroll 1
-        for (int a = ps.a0; a < ps.a1; a++) {
-            const int2 d = reinterpret_cast<const int2*>(&tf[a + 1][tid])[0];
-            double r0, r1;
-            nb_row_dot_staged<2>(A, a, d, xsf, xsg, r0, r1);
-            tf[a + 1][tid] = r0;
-            tg[a + 1][tid] = r1;
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = reinterpret_cast<const int2*>(&tf[a + 1][t0])[0];
+            const int2 d1 = reinterpret_cast<const int2*>(&tf[a + 1][t0 + 64])[0];
+            double r[4];
+            nb_row_dot_staged_pair<2>(A, a, d0, d1, xsf, xsg, r);
+            tf[a + 1][t0] = r[0];
+            tf[a + 1][t0 + 64] = r[1];
+            tg[a + 1][t0] = r[2];
+            tg[a + 1][t0 + 64] = r[3];
         }
     }
+    __syncthreads();          // results of a row come from the other half of the CTA
     if (!active) return;
     double f[Q], g[Q];
 #pragma unroll

@@ -346,18 +346,26 @@ k_stream_staged(StreamArgs A, int Q, const double* __restrict__ x0, const double
     for (int p = p0; p < p1; p++) {
         const NbStagePass ps = A.stage_pass[p];
         if (p > p0) __syncthreads();
-        int2 dn = active ? nb_ld_once(A.sdesc + (int64_t)ps.a0 * A.desc_stride + row) : empty;
         nb_stage_pass<NRHS>(A.stage_col + ps.begin, ps.count, tid, x0, x1, xs0, xs1);
         __syncthreads();
+        // row pairing (see k_stream_collide_f_staged): each half of the CTA takes every other direction for rows
+        // t and t + 64, one weight load feeds both
+        const int half = tid >> 6, t0 = tid & 63;
+        const int64_t ra = cta * NB_CTA_ROWS + t0, rb = ra + 64;
+        const bool act_a = ra < A.n_owned, act_b = rb < A.n_owned;
 #pragma unroll 1
-        for (int a = ps.a0; a < ps.a1; a++) {
-            const int2 d = dn;
-            if (a + 1 < ps.a1 && active) dn = nb_ld_once(A.sdesc + (int64_t)(a + 1) * A.desc_stride + row);
-            double r0, r1;
-            nb_row_dot_staged<NRHS>(A, a, d, xs0, xs1, r0, r1);
-            if (active) {
-                y0[(int64_t)(a + 1) * A.stride + row] = r0;
-                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + row] = r1;
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = act_a ? nb_ld_once(A.sdesc + (int64_t)a * A.desc_stride + ra) : empty;
+            const int2 d1 = act_b ? nb_ld_once(A.sdesc + (int64_t)a * A.desc_stride + rb) : empty;
+            double r[4];
+            nb_row_dot_staged_pair<NRHS>(A, a, d0, d1, xs0, xs1, r);
+            if (act_a) {
+                y0[(int64_t)(a + 1) * A.stride + ra] = r[0];
+                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + ra] = r[2];
+            }
+            if (act_b) {
+                y0[(int64_t)(a + 1) * A.stride + rb] = r[1];
+                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + rb] = r[3];
             }
         }
     }

@@ -300,12 +300,13 @@ __device__ __forceinline__ void nb_row_dot_staged(const StreamArgs& A, int alpha
 }
 
 // Two rows that share class and weight pattern (the same position in two neighbouring cells): every weight is loaded
-// once and feeds both rows.  Per row the summation order is unchanged (k = 0..K-1), so the results are bit-identical to
-// nb_row_dot_staged.
-template <bool STREAMED, int B2>
+// once and feeds both rows (and both distributions).  Per row the summation order is unchanged (k = 0..K-1), so the
+// results are bit-identical to nb_row_dot_staged.  acc = { row0 f, row1 f, row0 g, row1 g }.
+template <int NRHS, bool STREAMED, int B2>
 __device__ __forceinline__ void nb_staged_batches_pair(const double2* __restrict__ W2, int K, int64_t P,
                                                        const double* __restrict__ s0, const double* __restrict__ s1,
-                                                       double& a0, double& a1)
+                                                       const double* __restrict__ g0, const double* __restrict__ g1,
+                                                       double (&acc)[4])
 {
     const int Kh = (K + 1) >> 1;
     for (int kk = 0; kk < Kh; kk += B2) {
@@ -319,21 +320,31 @@ __device__ __forceinline__ void nb_staged_batches_pair(const double2* __restrict
         for (int j = 0; j < B2; j++) {
             const int k = 2 * (kk + j);
             if (k < K) {
-                a0 += vv[j].x * s0[k];
-                a1 += vv[j].x * s1[k];
+                acc[0] += vv[j].x * s0[k];
+                acc[1] += vv[j].x * s1[k];
+                if (NRHS == 2) {
+                    acc[2] += vv[j].x * g0[k];
+                    acc[3] += vv[j].x * g1[k];
+                }
             }
             if (k + 1 < K) {
-                a0 += vv[j].y * s0[k + 1];
-                a1 += vv[j].y * s1[k + 1];
+                acc[0] += vv[j].y * s0[k + 1];
+                acc[1] += vv[j].y * s1[k + 1];
+                if (NRHS == 2) {
+                    acc[2] += vv[j].y * g0[k + 1];
+                    acc[3] += vv[j].y * g1[k + 1];
+                }
             }
         }
     }
 }
 
-// Rows r0 and r1 of one direction (descriptors d0, d1) from the staged values xs: shared-weight path when both rows
-// have the same class and pattern, two independent products otherwise.
+// Rows r0 and r1 of one direction (descriptors d0, d1) from the staged values xs0 (f) / xs1 (g): shared-weight path when
+// both rows have the same class and pattern, two independent products otherwise.  y = { row0 f, row1 f, row0 g, row1 g }.
+template <int NRHS>
 __device__ __forceinline__ void nb_row_dot_staged_pair(const StreamArgs& A, int alpha_m1, int2 d0, int2 d1,
-                                                       const double* __restrict__ xs, double& y0, double& y1)
+                                                       const double* __restrict__ xs0, const double* __restrict__ xs1,
+                                                       double (&y)[4])
 {
     const unsigned x0 = (unsigned)d0.x, x1 = (unsigned)d1.x;
     if ((x0 >> 16) == (x1 >> 16) && d0.y == d1.y) {
@@ -355,22 +366,20 @@ __device__ __forceinline__ void nb_row_dot_staged_pair(const StreamArgs& A, int 
             W = C->W + 2 * (int64_t)(unsigned)d0.y;
         }
         const double2* W2 = reinterpret_cast<const double2*>(W);
-        const double* __restrict__ s0 = xs + (x0 & 0xffffu);
-        const double* __restrict__ s1 = xs + (x1 & 0xffffu);
-        double a0 = 0.0, a1 = 0.0;
+        const unsigned o0 = x0 & 0xffffu, o1 = x1 & 0xffffu;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (streamed) {
-            if (K <= 8) nb_staged_batches_pair<true, 4>(W2, K, P, s0, s1, a0, a1);
-            else nb_staged_batches_pair<true, 7>(W2, K, P, s0, s1, a0, a1);
+            if (K <= 8) nb_staged_batches_pair<NRHS, true, 4>(W2, K, P, xs0 + o0, xs0 + o1, xs1 + o0, xs1 + o1, acc);
+            else nb_staged_batches_pair<NRHS, true, 7>(W2, K, P, xs0 + o0, xs0 + o1, xs1 + o0, xs1 + o1, acc);
         } else {
-            if (K <= 8) nb_staged_batches_pair<false, 4>(W2, K, P, s0, s1, a0, a1);
-            else nb_staged_batches_pair<false, 7>(W2, K, P, s0, s1, a0, a1);
+            if (K <= 8) nb_staged_batches_pair<NRHS, false, 4>(W2, K, P, xs0 + o0, xs0 + o1, xs1 + o0, xs1 + o1, acc);
+            else nb_staged_batches_pair<NRHS, false, 7>(W2, K, P, xs0 + o0, xs0 + o1, xs1 + o0, xs1 + o1, acc);
         }
-        y0 = a0;
-        y1 = a1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = acc[i];
     } else {
-        double dummy;
-        nb_row_dot_staged<1>(A, alpha_m1, d0, xs, xs, y0, dummy);
-        nb_row_dot_staged<1>(A, alpha_m1, d1, xs, xs, y1, dummy);
+        nb_row_dot_staged<NRHS>(A, alpha_m1, d0, xs0, xs1, y[0], y[2]);
+        nb_row_dot_staged<NRHS>(A, alpha_m1, d1, xs0, xs1, y[1], y[3]);
     }
 }
 
