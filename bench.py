@@ -355,7 +355,7 @@ def run_ours(args):
                 "device_format_bytes": info["device_bytes"], "nnz": nnz,
                 "note": "frac is defined on the algorithmic bytes B = 12*nnz + populations (SURVEY 8d); the dictionary format moves ~6x fewer "
                         "DRAM bytes (traffic), so frac > 1; the kernel's actual limiter is the L1/shared-memory data pipe (ncu: "
-                        "l1tex__data_pipe_lsu_wavefronts 84 % of peak, profiles/r01_fused_staged_v5b_ncu_selected.json)", "matrix_format": ctx.matrix_format_info(), "dof_order": args.dof_order, "host_numbering": args.numbering}
+                        "l1tex__data_pipe_lsu_wavefronts 80 % of peak, profiles/r01_fused_staged_v6_ncu_selected.json)", "matrix_format": ctx.matrix_format_info(), "dof_order": args.dof_order, "host_numbering": args.numbering}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
