@@ -610,7 +610,7 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
 {
     if (!c || !c->stencil_set || n_owned < 0 || n_ghost < 0) return fail(c, NB200_ERR_ARG, "set_layout: call set_stencil first / bad sizes");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    const int64_t stride = ((n_owned + n_ghost + 31) / 32) * 32;
+    const int64_t stride = std::max<int64_t>(32, ((n_owned + n_ghost + 31) / 32) * 32);     // a rank may own nothing
     if ((int64_t)c->Q * stride >= (int64_t)INT32_MAX) return fail(c, NB200_ERR_UNSUPPORTED, "Q*stride exceeds int32 index range");
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) { cudaFree(c->pop[w][b]); c->pop[w][b] = nullptr; }
     cudaFree(c->rho); cudaFree(c->u); cudaFree(c->T); cudaFree(c->sensor); cudaFree(c->d_partial);
@@ -1082,7 +1082,7 @@ static int copy_all(nb200_ctx* c, int which, double* host, int64_t n, bool up, b
 {
     int rc = check_pop(c, which, n);
     if (rc) return rc;
-    if (!host) return fail(c, NB200_ERR_ARG, "populations: null host pointer");
+    if (!host && n > 0) return fail(c, NB200_ERR_ARG, "populations: null host pointer");
     CUDA_TRY(c, cudaSetDevice(c->device));
     if (n > 0) {
         double* dev = c->pop[which][c->cur[which]];

@@ -25,8 +25,12 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
 #define NB_CTA_ROWS 128
 // Pass capacity in doubles per distribution.  Deliberately small: with 4 CTAs per SM the staged values take
 // 4 x 16 KB, which leaves the L1 large enough to keep the weight patterns resident.
+#ifndef NB_STAGE_CAP
 #define NB_STAGE_CAP 2048          // f only
+#endif
+#ifndef NB_STAGE_CAP_FG
 #define NB_STAGE_CAP_FG 2048       // f and g staged together (two arrays of this size)
+#endif
 #define NB_MAX_DIRS 44             // Q - 1 of the largest stencil on the path (D3Q45)
 
 #define NB_CLS_BITS 6

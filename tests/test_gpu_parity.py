@@ -1075,3 +1075,75 @@ def test_cell_numbering_equals_order_hint(oracle_lib):
     assert np.array_equal(bufs[0].numpy(), want[:, num.order])
     assert ctx.kernel_launches() - l0 == 4 * 4
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# degenerate sizes: a rank that owns nothing, and DoF counts around the warp / CTA boundaries
+# ---------------------------------------------------------------------------------------------
+def test_rank_without_dofs():
+    """More ranks than cell layers leaves ranks without owned DoFs in a p4est partition: every call must be a no-op."""
+    import scipy.sparse as sp
+    from natrium_b200 import Context, Stencil
+    st = Stencil("D2Q9", 1.0)
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+    ctx.set_layout(0, 0, False)
+    empty = sp.csr_matrix((0, 0))
+    for a in range(8):
+        ctx.upload_block_csr(a, a, np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0))
+    ctx.finalize_matrix()
+    ctx.set_collision(0.1, 0.1)
+    ctx.upload_populations(0, np.zeros((9, 0)))
+    ctx.stream(0)
+    ctx.collide()
+    ctx.step(3)
+    ctx.synchronize()
+    assert ctx.download_populations(0).shape == (9, 0)
+    assert np.all(ctx.conserved() == 0.0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("fmt", [None, ("dict-unstaged", 1e-14, False), ("ell", 0.0, False)], ids=["dict", "dict-unstaged", "ell"])
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 257])
+def test_sizes_around_warp_and_cta_boundaries(n, fmt, oracle_lib):
+    """Ragged tails: n_owned not a multiple of 32 / 64 / 128 (the row pairing works on 64-row halves, the ELL on 32-row
+    slices).  Random sparse periodic shift matrices so that every row reads its neighbours; one fused step and one
+    stream against the oracle."""
+    import scipy.sparse as sp
+    from natrium_b200 import Context, Stencil
+    st = Stencil("D2Q9", 1.0)
+    ost = oracle_lib.Stencil("D2Q9", 1.0)
+    rng = np.random.default_rng(n)
+    blocks = {}
+    for a in range(8):
+        k = min(n, 3)
+        cols = (np.arange(n)[:, None] + rng.integers(0, n, size=(1, k))) % n
+        vals = rng.random((n, k)) + 0.1
+        vals /= vals.sum(1, keepdims=True)
+        m = sp.csr_matrix((vals.reshape(-1), cols.reshape(-1), np.arange(n + 1) * k), shape=(n, n))
+        m.sum_duplicates()
+        m.sort_indices()
+        blocks[(a, a)] = m
+    f = (1.0 + 0.1 * rng.random((9, n))) * st.getWeights()[:, None]
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+    ctx.set_layout(n, 0, False)
+    if fmt is not None:
+        ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
+    for (bi, bj), m in blocks.items():
+        ctx.upload_block_csr(bi, bj, m.indptr, m.indices, m.data)
+    ctx.finalize_matrix()
+    ctx.set_collision(0.05, 0.1)
+    ctx.upload_populations(0, f)
+    ctx.stream(0)
+    ref = oracle_lib.stream(blocks, f)
+    assert rel_err(ctx.download_populations(0), ref) <= TOL_STEP
+    ctx.upload_populations(0, f)
+    ctx.step(2)
+    ctx.synchronize()
+    g = f.copy()
+    for _ in range(2):
+        g = oracle_lib.stream(blocks, g)
+        oracle_lib.collide_bgk(ost, g, 0.05, 0.1)
+    assert rel_err(ctx.download_populations(0), g) <= 2 * TOL_STEP
+    ctx.close()
