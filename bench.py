@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", default="dict", choices=["dict", "dict-unstaged", "ell"], help="device format of the streaming matrix")
     ap.add_argument("--dof-order", default="none", choices=["cell", "none"], help="internal DoF order hint (nb200_set_dof_order)")
+    ap.add_argument("--stretch", type=float, default=0.0,
+                    help="side measurement: grade the mesh in y like TurbulentChannelFlow3D (y -> y - s sin(2 pi y)/(2 pi)); 0 = uniform (the bench line)")
     ap.add_argument("--numbering", default="cell", choices=["cell", "lex"],
                     help="host DoF numbering of the synthetic problem: cell-wise like deal.II (default) or lexicographic")
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
@@ -216,7 +218,7 @@ def workload_config(args, n_gpus):
     return {"workload": f"TGV3D {args.stencil} BGK semi-Lagrangian p={args.order} {args.cells}^3 cells/GPU "
                         f"({nd}^3 DoFs/GPU) x {n_gpus} GPU slab(s) along z",
             "cells_per_gpu": args.cells ** 3, "fe_order": args.order, "stencil": args.stencil, "collision": "BGK_STANDARD" if args.stencil not in ("D2Q25H", "D3Q45") else "BGK_STANDARD f+g quartic Pr=0.71 Sutherland",
-            "cfl": 0.4, "mach": 0.05, "parallelism": f"slab x{n_gpus} (NCCL ghost exchange)" if n_gpus > 1 else "single GPU",
+            "cfl": 0.4, "mach": 0.05, "y_stretch": args.stretch, "parallelism": f"slab x{n_gpus} (NCCL ghost exchange)" if n_gpus > 1 else "single GPU",
             "l2_policy": "inputs_exceed_l2 (matrix stream per step >> 126 MB L2)"}
 
 
@@ -246,7 +248,13 @@ def run_ours(args):
     with_g = args.stencil in ("D2Q25H", "D3Q45")      # compressible two-distribution configurations (not the bench line)
     st = Stencil(args.stencil, 1.0 if with_g else math.sqrt(3) / Ma)
     cells = [args.cells, args.cells, args.cells * world]
-    pb = harness.CartesianProblem(3, cells, args.order, length=[2 * math.pi, 2 * math.pi, 2 * math.pi * world])
+    L3 = [2 * math.pi, 2 * math.pi, 2 * math.pi * world]
+    verts = None
+    if args.stretch > 0.0:      # y-graded mesh (TurbulentChannelFlow3D.h:116-123): one weight-pattern set per cell row
+        yy = np.arange(cells[1] + 1) / cells[1]
+        verts = [L3[0] * np.arange(cells[0] + 1) / cells[0], L3[1] * (yy - args.stretch * np.sin(2 * math.pi * yy) / (2 * math.pi)),
+                 L3[2] * np.arange(cells[2] + 1) / cells[2]]
+    pb = harness.CartesianProblem(3, cells, args.order, length=L3, verts=verts)
     dt = pb.timestep(st, 0.4)
     nu = 0.01 if with_g else 2 * math.pi            # Re = 1 as in sl_parallel_benchmark_periodic/benchmark.cpp:58-66
     ctx = Context(local, rank, world, uid)
@@ -295,12 +303,18 @@ def run_ours(args):
     ctx.step(args.steps)
     ms = ctx.timer_stop()
     barrier()
-    clocks = sampler.stop()
     launches = ctx.kernel_launches() - launches0
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    if ms < 400.0:
+        # a short timed region ends before nvidia-smi (50 ms period) delivers samples: keep the same kernel running,
+        # untimed, for ~0.4 s so that the clocks under this load are seen; the step count is derived from the
+        # all-reduced time, i.e. identical on every rank (each step contains a collective)
+        ctx.step(int(math.ceil(400.0 / max(ms / args.steps, 1e-3))))
+        barrier()
+    clocks = sampler.stop()
     n_global = pb.N
     value = n_global * Q * args.steps / (ms * 1e-3) / 1e6
     cons = ctx.conserved()
