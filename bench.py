@@ -150,6 +150,12 @@ def cpu_reference_run(args, steps, warmup, layers, target_s=12.0, gpu_parity=Fal
     rho, u = harness.taylor_green_3d(x, st.getSpeedOfSound())
     f = harness.equilibrium_distributions(st, rho, u)
     stepper = cpu.ReferenceOrderStepper(ost, blocks, n, 2 * math.pi, dt)
+    # all the host threads there are: torchrun exports OMP_NUM_THREADS=1 to its workers, which would turn the CPU arm
+    # into a single-core run
+    try:
+        cpu.set_num_threads(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        cpu.set_num_threads(os.cpu_count() or 1)
     parity = None
     if gpu_parity:
         # parity gate that accompanies the throughput number: the GPU path on this very sample, 10 steps from

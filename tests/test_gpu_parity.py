@@ -1147,3 +1147,34 @@ def test_sizes_around_warp_and_cta_boundaries(n, fmt, oracle_lib):
         oracle_lib.collide_bgk(ost, g, 0.05, 0.1)
     assert rel_err(ctx.download_populations(0), g) <= 2 * TOL_STEP
     ctx.close()
+
+
+def test_collision_selection_table():
+    """CollisionSelection2D/3D_test (test/collision_advanced/CollisionSelection_test.cpp:33-214) for the stencils on the
+    path: every row of selectCollision (CollisionSelection.h:85-91,141-150,179-202,251) is accepted, every other
+    combination throws "Collision model not implemented yet"."""
+    from natrium_b200 import CollisionException, Context, Stencil, _capi, mrt
+    B, R, M = _capi.BGK_STANDARD, _capi.BGK_REGULARIZED, _capi.MRT_STANDARD
+    E, Qe = _capi.BGK_EQUILIBRIUM, _capi.QUARTIC_EQUILIBRIUM
+    rows_f = {"D2Q9": {(B, E), (B, Qe), (R, E), (M, E)}, "D2Q25H": {(B, Qe)}, "D3Q15": {(B, E), (R, E)},
+              "D3Q19": {(B, E), (R, E), (M, E)}, "D3Q45": {(B, E), (B, Qe)}}
+    rows_fg = {"D2Q25H": {(B, E), (B, Qe), (R, E)}, "D3Q45": {(B, Qe)}}
+    for with_g, table in ((False, rows_f), (True, rows_fg)):
+        for name in ("D2Q9", "D2Q25H", "D3Q15", "D3Q19", "D3Q45"):
+            st = Stencil(name, 1.0)
+            ctx = Context(0)
+            ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+            ctx.set_layout(4, 0, with_g)
+            if st.getQ() in (9, 19):
+                b = mrt.DELLAR_D2Q9 if st.getQ() == 9 else mrt.DHUMIERES_D3Q19
+                ctx.set_mrt(mrt.make_M(b), mrt.make_T(b), mrt.make_diag(0.8, b))
+            for scheme in (B, R, M):
+                for eq in (E, Qe):
+                    ok = (scheme, eq) in table.get(name, set())
+                    try:
+                        ctx.set_collision(0.1, 0.1, scheme=scheme, equilibrium=eq, with_g=with_g)
+                        assert ok, (name, scheme, eq, with_g, "accepted but not a row of selectCollision")
+                    except CollisionException as ex:
+                        assert not ok, (name, scheme, eq, with_g, str(ex))
+                        assert "not implemented" in str(ex)
+            ctx.close()
