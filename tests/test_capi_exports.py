@@ -43,3 +43,22 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), fn
                 assert "liboracle" not in txt, fn
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/natrium_b200.h is the FFI surface: it must compile as C99 (no C++ in the signatures) and a C program that
+    takes the address of every declared entry point must link against the library."""
+    import subprocess
+    names = declared_symbols()
+    src = tmp_path / "abi_check.c"
+    body = "\n".join(f"    p[{i}] = (fn)&{n};" for i, n in enumerate(names))
+    src.write_text('#include "natrium_b200.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n'
+                   f"    fn p[{len(names)}];\n{body}\n"
+                   f"    nb200_collision_params cp; cp.force[2] = 0.0; (void)cp;\n"
+                   f'    printf("%d\\n", (int)(sizeof(p) / sizeof(p[0])));\n    return p[0] == 0;\n}}\n')
+    exe = tmp_path / "abi_check"
+    libdir = os.path.join(ROOT, "natrium_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lnatrium_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert int(out) == len(names)
