@@ -1,6 +1,9 @@
 // kernels.cuh -- fused stream+collide and stand-alone collide kernels, templated on the stencil.
 // Instantiated once per (D,Q) by inst.cu (one translation unit per stencil so that the
 // build parallelises and each unit owns its constant-memory block).
+// The production path is k_stream_collide_f_staged / k_stream_collide_fg_staged (staged dictionary format);
+// k_stream_collide_f / _fg<FMT> serve the ELL and unstaged dictionary formats (any CSR, also the fallback when the
+// rows of a CTA share too little for staging).
 #pragma once
 #include "stream_common.cuh"
 #include "collide.cuh"

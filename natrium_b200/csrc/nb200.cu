@@ -1,17 +1,19 @@
-// nb200.cu -- libnatrium_b200: C ABI + CUDA kernels (sm_100a) for NATriuM's hot path.
-//
-// Device data layout (DESIGN.md has the full picture):
-//   populations  f[q*stride + i], q = 0..Q-1 (direction-major SoA, like the reference's one
-//                Trilinos vector per direction, L/solver/DistributionFunctions.h:47-68);
-//                i < n_owned owned DoFs, then ghost slots; two buffers (ping-pong) replace the
-//                reference's per-step full copy f_tmp(m_f) (L/solver/CFDSolver.cpp:671).
-//   matrix       all (Q-1)x(Q-1) blocks of getSystemMatrix() flattened per block-row alpha into
-//                a warp-sliced ELL (slice = 32 rows, column-major inside a slice): value fp64 +
-//                int32 index that already points into the flat population array
-//                (beta*stride + col), so off-diagonal (wall-bounce) blocks cost nothing extra.
-//   kernels      stream_collide_kernel: one thread per DoF walks its Q-1 rows (coalesced
-//                val/idx loads across the warp, gather of x through L1/L2), keeps the Q
-//                post-stream values in registers, collides and writes once.
+// nb200.cu -- libnatrium_b200: the C ABI (include/natrium_b200.h) and everything around the hot kernels for NATriuM's
+// stream + collide path on sm_100a.  DESIGN.md has the full picture; in short:
+//   populations  f[q*stride + i], q = 0..Q-1 (direction-major SoA, like the reference's one Trilinos vector per
+//                direction, L/solver/DistributionFunctions.h:47-68); i < n_owned owned DoFs, then ghost slots; two
+//                buffers (ping-pong) replace the reference's per-step full copy f_tmp(m_f) (L/solver/CFDSolver.cpp:671).
+//   matrix       the (Q-1)x(Q-1) CSR blocks of getSystemMatrix() arrive through nb200_upload_block_csr and become one
+//                of three device formats at nb200_finalize_matrix (stream_common.cuh, dict_build.h): warp-sliced ELL,
+//                dictionary (shared column lists + shared weight patterns), staged dictionary (per-CTA staging
+//                tables).  Column indices always point into the flat population array (beta*stride + col), so
+//                off-diagonal (wall-bounce) blocks cost nothing extra.
+//   kernels      per-stencil units (inst.cu <- kernels.cuh, collide.cuh, entropic.cuh) hold the fused stream+collide,
+//                collide, wall-hit, post-matrix and conserved-sum kernels; this file holds the stencil-independent
+//                ones (stream only, format construction, halo pack/unpack, host-step chunk copies).
+//   this file    context, uploads/downloads (with the optional internal DoF order), halo plans (pruned NCCL neighbour
+//                exchange overlapped with the interior CTAs), step sequencing incl. walls / forces / post-collision
+//                matrix, the chunk-pipelined host-buffer step, diagnostics.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>

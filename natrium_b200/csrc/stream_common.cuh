@@ -1,4 +1,4 @@
-// stream_common.cuh -- the two device formats of the streaming matrix and their row products.
+// stream_common.cuh -- the device formats of the streaming matrix (ELL, dictionary, staged dictionary) and their row products.
 //
 //   NB_FMT_ELL   warp-sliced ELL: 8 B value + 4 B index per stored entry, streamed from HBM.
 //   NB_FMT_DICT  dictionary format: every row is a (column-list id, weight-pattern id) pair; lists
@@ -23,8 +23,9 @@
 enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
 
 #define NB_CTA_ROWS 128
-// Pass capacity in doubles per distribution.  Deliberately small: with 4 CTAs per SM the staged values take
-// 4 x 16 KB, which leaves the L1 large enough to keep the weight patterns resident.
+// Pass capacity in doubles per distribution.  Deliberately small: with 5 CTAs per SM the staged values take
+// 5 x 16 KB (+ 5 x 19.5 KB of result tiles for Q = 19), which leaves the L1 large enough to keep the weight patterns
+// resident (measured: 1536 / 2048 / 3072 doubles -> 0.743 / 0.729 / 0.875 ms per step on configuration 2).
 #ifndef NB_STAGE_CAP
 #define NB_STAGE_CAP 2048          // f only
 #endif
