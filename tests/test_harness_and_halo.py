@@ -181,3 +181,15 @@ def test_cell_numbering_renumbers_consistently():
             nbr, so, si, ro = part.halo_plan()
             nbr2, so2, si2, ro2 = num.halo_plan()
             assert np.array_equal(num.order[si2], si) and np.array_equal(so, so2) and np.array_equal(ro, ro2)
+
+
+def test_dictionary_builder_semantics(tmp_path):
+    """Host-side dictionary builder (natrium_b200/csrc/dict_build.h): tolerance 0 dedups bitwise only and replays the
+    CSR product exactly; the default 1e-14 merges round-off-noisy copies of a weight pattern (error <= K * tol) but
+    keeps values 1e-9 apart separate; more distinct row lengths than exact classes fall into power-of-two classes
+    with zero-weight padding; rows fed by two blocks of a block-row (wall bounce) are concatenated."""
+    import subprocess
+    exe = str(tmp_path / "dict_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "dict_check.cpp")], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("OK"), out
