@@ -165,6 +165,14 @@ def _snap(v):
 
 def _face_crossed_first(mesh, cell, p_in, p_out):
     """SemiLagrangian.cpp:525-699 for a Cartesian cell.  Returns (face_id, p_boundary)."""
+    face, pb, _ = face_crossed_first(mesh, cell, p_in, p_out)
+    return face, pb
+
+
+def face_crossed_first(mesh, cell, p_in, p_out):
+    """SemiLagrangian<dim>::faceCrossedFirst (SemiLagrangian.cpp:525-699) for a Cartesian cell: the face the segment
+    p_in -> p_out leaves the cell through (deal.II numbering 2*d + side, -1: p_out inside), the boundary point and
+    lambda (fraction of the segment up to the face).  Returns (face_id, p_boundary, lambda)."""
     dim = mesh.dim
     x0 = [mesh.verts[d][cell[d]] for d in range(dim)]
     h = [mesh.verts[d][cell[d] + 1] - mesh.verts[d][cell[d]] for d in range(dim)]
@@ -183,9 +191,9 @@ def _face_crossed_first(mesh, cell, p_in, p_out):
             if l < lam:
                 lam, face = l, 2 * d + 1
     if face == -1:
-        return -1, None
+        return -1, None, None
     hb = [_snap(pi[d] + lam * (po[d] - pi[d])) for d in range(dim)]
-    return face, [x0[d] + hb[d] * h[d] for d in range(dim)]
+    return face, [x0[d] + hb[d] * h[d] for d in range(dim)], lam
 
 
 def shape_function_values(mesh, p, nodes, cell, point):

@@ -429,3 +429,56 @@ def test_walled_assembly_bounce_blocks_and_hits(oracle_lib):
         assert -1e-14 <= h["dt_hit"] <= dt + 1e-14
     keys = [(h["cell"], h["point"]) for h in dofs.hits]
     assert keys == sorted(keys)                                  # HitList iteration order: cell, then point
+
+
+def test_face_crossed_first_kats():
+    """SemiLagrangian2D/3D_FaceCrossedFirst_test (test/advection/SemiLagrangian_test.cpp:227-456): rays from the
+    barycentre (0.0625, ...) of the lower-left cell of the 8^dim unit-square / unit-cube test domain; expected face id,
+    lambda and boundary point are the reference's literals."""
+    for dim in (2, 3):
+        mesh = assembly.CartesianMesh.uniform(dim, 8, L=1.0)
+        cell = (0,) * dim
+        c = [0.0625] * dim
+
+        def ray(**kw):
+            p2 = list(c)
+            for k, v in kw.items():
+                p2["xyz".index(k)] = v
+            return assembly.face_crossed_first(mesh, cell, c, p2)
+
+        assert ray()[0] == -1                                        # no face crossed
+        kats = [(dict(x=-0.0625), 0, 0.5, {0: 0.0}), (dict(x=0.1875), 1, 0.5, {0: 0.125}),
+                (dict(y=-0.0625), 2, 0.5, {1: 0.0}), (dict(y=0.1875), 3, 0.5, {1: 0.125})]
+        if dim == 3:
+            kats += [(dict(z=-0.0625), 4, 0.5, {2: 0.0}), (dict(z=0.1875), 5, 0.5, {2: 0.125}),
+                     # three faces crossed, the one hit first wins (:419-452)
+                     (dict(x=0.0625 - 0.25, y=-0.0625, z=-0.0625), 0, 0.25, {0: 0.0, 1: 0.03125, 2: 0.03125}),
+                     (dict(x=-0.0625, y=0.0625 - 0.25, z=-0.0625), 2, 0.25, {0: 0.03125, 1: 0.0, 2: 0.03125}),
+                     (dict(x=-0.0625, y=-0.0625, z=0.0625 - 0.25), 4, 0.25, {0: 0.03125, 1: 0.03125, 2: 0.0})]
+        else:
+            kats += [(dict(x=0.0625 - 0.25, y=-0.0625), 0, 0.25, {0: 0.0, 1: 0.03125}),     # faces 0 and 2, 0 first (:283-290)
+                     (dict(x=-0.0625, y=0.0625 - 0.25), 2, 0.25, {0: 0.03125, 1: 0.0})]     # faces 0 and 2, 2 first (:291-299)
+        for kw, face, lam, pb_expect in kats:
+            f, pb, l = ray(**kw)
+            assert f == face, (dim, kw, f)
+            assert abs(l - lam) <= 1e-13
+            for d in range(dim):
+                assert abs(pb[d] - pb_expect.get(d, 0.0625)) <= 1e-13, (dim, kw, pb)
+
+
+@pytest.mark.parametrize("scaling", [1.0, 5.0])
+def test_bgk_equilibrium_moments(scaling, oracle_lib):
+    """BGKMoments_test / D2Q9IncompressibleModelMoments_Scaled_test (test/collision/BGKStandard_test.cpp:69-152,189-263):
+    rho = 1.45, u = (2.3, -1.14); density, momentum and momentum-flux tensor rho u u + rho cs^2 I of the legacy
+    equilibrium to 1e-14 (the reference's TOLERANCE), unscaled and with stencil scaling 5; and the collision_advanced
+    BGKEquilibrium (unscaled directions, u / scaling) is the same distribution."""
+    st = oracle_lib.Stencil("D2Q9", scaling)
+    rho, u = 1.45, np.array([2.3, -1.14])
+    feq = oracle_lib.legacy_feq(st, rho, u)
+    tol = 1e-14 * max(1.0, scaling * scaling)          # the reference's absolute 1e-14 at scaling 1; entries grow with scaling^2
+    assert abs(feq.sum() - rho) <= 1e-14
+    assert np.max(np.abs(st.e.T @ feq - rho * u)) <= tol
+    P = np.einsum("qa,qb,q->ab", st.e, st.e, feq)
+    assert np.max(np.abs(P - (rho * np.outer(u, u) + rho * st.cs2 * np.eye(2)))) <= tol
+    adv = oracle_lib.equilibrium(st, rho, u / scaling, kind=0)
+    assert np.max(np.abs(adv - feq)) <= 1e-14
