@@ -68,3 +68,51 @@ def oracle_problem(case):
     else:
         f, g = fields.equilibrium_init(st.e, st.w, st.cs2, rho, u), None
     return dict(c=c, st=st, mesh=mesh, dt=dt, blocks=blocks, dofs=dofs, x=x, f=f, g=g, rho=rho, u=u, T=T)
+
+
+def poiseuille_problem(oracle_lib):
+    """SemiLagrangianBoundaryHandler_PoiseuilleBB_test (test/boundaries/SemiLagrangianBoundaryHandler_test.cpp:175-229):
+    PoiseuilleFlow2D (L/benchmarks/PoiseuilleFlow2D.cpp:21-95) on [0,2]x[0,1], refinement 2 (4x4 cells), FE order 2,
+    D2Q9 with scaling sqrt(3)*1.5*u_bulk/Ma, CFL 1.5, Re 10, periodic in x, VelocityNeqBounceBack(zero velocity)
+    walls in y, constant force Fx = 8 u_max nu / h^2 with SHIFTING_VELOCITY forcing, start at rest."""
+    import math
+    from oracle import assembly, fields
+    u_bulk, height, length, Re, Ma, p, cfl = 0.0001 / 1.5, 1.0, 2.0, 10.0, 0.1, 2, 1.5
+    nu = u_bulk * height / Re
+    scaling = math.sqrt(3) * 1.5 * u_bulk / Ma
+    st = oracle_lib.Stencil("D2Q9", scaling)
+    mesh = assembly.CartesianMesh([np.linspace(0, length, 5), np.linspace(0, height, 5)], boundary=["periodic", "wall"])
+    dt = assembly.calculate_timestep(mesh, p, st.max_speed, cfl)
+    opp = np.array([int(np.argmin(np.abs(st.e + st.e[i]).sum(1))) for i in range(9)])
+    blocks, dofs = assembly.assemble_semilagrangian(mesh, p, st.e, dt, opposite=opp)
+    F = np.array([8 * (1.5 * u_bulk) * nu / (height * height), 0.0])
+    hits = dofs.hits
+    idx = np.array([h["index"] for h in hits], dtype=np.int32)
+    dirs = np.array([h["direction"] for h in hits], dtype=np.int32)
+    kinds = np.zeros(len(hits), dtype=np.int32)
+    vals = np.zeros(len(hits))                                   # zero wall velocity: 2 w rho e.u_w / cs2 = 0
+    f0 = fields.equilibrium_init(st.e, st.w, st.cs2, np.ones(dofs.N), np.zeros((2, dofs.N)))
+    return dict(st=st, scaling=scaling, nu=nu, dt=dt, blocks=blocks, dofs=dofs, mesh=mesh, F=F, hits=(idx, dirs, kinds, vals), f0=f0, u_bulk=u_bulk)
+
+
+def integral_mean(dofs, mesh, p, values):
+    """PhysicalProperties<dim>::meanVelocityX (L/solver/PhysicalProperties.cpp:323-365): Gauss-Lobatto quadrature of a
+    nodal field over all cells divided by the domain area (quadrature points = support points)."""
+    from numpy.polynomial import legendre
+    from oracle import assembly
+    nodes = np.asarray(assembly.gll_nodes(p))
+    Pp = legendre.legval(2 * nodes - 1, [0] * p + [1])
+    w1 = 1.0 / (p * (p + 1) * Pp ** 2)                    # GLL weights on [0, 1]
+    total, area = 0.0, 0.0
+    for cell in mesh.cells():
+        h = [mesh.verts[d][cell[d] + 1] - mesh.verts[d][cell[d]] for d in range(mesh.dim)]
+        vol = float(np.prod(h))
+        wq = w1
+        for _ in range(mesh.dim - 1):
+            wq = np.multiply.outer(w1, wq)
+        # cell_dofs is lexicographic with x fastest; outer products above put the LAST axis fastest -> transpose order is
+        # irrelevant because the weights are symmetric under axis permutation
+        ids = dofs.cell_dofs(cell)
+        total += vol * float(np.sum(wq.reshape(-1) * values[ids]))
+        area += vol
+    return total / area

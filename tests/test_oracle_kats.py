@@ -482,3 +482,27 @@ def test_bgk_equilibrium_moments(scaling, oracle_lib):
     assert np.max(np.abs(P - (rho * np.outer(u, u) + rho * st.cs2 * np.eye(2)))) <= tol
     adv = oracle_lib.equilibrium(st, rho, u / scaling, kind=0)
     assert np.max(np.abs(adv - feq)) <= 1e-14
+
+
+def test_poiseuille_bounce_back_with_forcing(oracle_lib):
+    """SemiLagrangianBoundaryHandler_PoiseuilleBB_test (test/boundaries/SemiLagrangianBoundaryHandler_test.cpp:175-229):
+    body-force driven channel between two VelocityNeqBounceBack walls with the SHIFTING_VELOCITY forcing scheme;
+    the converged mean x-velocity lies within 10 % of u_bulk.  Walls (bounce blocks + hit list), forcing and the
+    collision all come from the oracle's restatements."""
+    pb = common.poiseuille_problem(oracle_lib)
+    st, f = pb["st"], pb["f0"].copy()
+    idx, dirs, kinds, vals = pb["hits"]
+    mean_prev, u = None, None
+    for it in range(6000):
+        f = oracle_lib.stream(pb["blocks"], f)
+        assert oracle_lib.apply_wall_hits(st, f, None, idx, dirs, kinds, vals) == 0
+        _, u, rc = oracle_lib.collide_advanced(st, f, pb["nu"], pb["dt"], force=pb["F"], force_type="SHIFTING_VELOCITY")
+        assert rc == 0
+        if it % 100 == 99:
+            mean = common.integral_mean(pb["dofs"], pb["mesh"], 2, u[0])
+            if mean_prev is not None and abs(mean - mean_prev) <= 1e-6 * abs(mean):     # setConvergenceThreshold(1e-6)
+                break
+            mean_prev = mean
+    mean = common.integral_mean(pb["dofs"], pb["mesh"], 2, u[0])          # SolverStats::getMeanVelocityX
+    assert 0.9 * pb["u_bulk"] < mean < 1.1 * pb["u_bulk"], (mean, pb["u_bulk"], it)
+    assert abs(common.integral_mean(pb["dofs"], pb["mesh"], 2, u[1])) < 1e-3 * pb["u_bulk"]
