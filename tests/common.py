@@ -116,3 +116,25 @@ def integral_mean(dofs, mesh, p, values):
         total += vol * float(np.sum(wq.reshape(-1) * values[ids]))
         area += vol
     return total / area
+
+
+def moving_walls_problem(oracle_lib):
+    """WallTest fixture of the reference (test/boundaries/WallFixture.h:44-88, test/problemdescription/WallTestDomain2D.h):
+    unit square, refinement 1 (2x2 cells), FE order 2, D2Q9 (scaling 1), CFL 1, viscosity 0.2, periodic in x, both
+    y-walls VelocityNeqBounceBack moving with u_w = (0.01, 0); start at rest, 100 steps."""
+    from oracle import assembly, fields
+    st = oracle_lib.Stencil("D2Q9", 1.0)
+    mesh = assembly.CartesianMesh([np.linspace(0, 1.0, 3), np.linspace(0, 1.0, 3)], boundary=["periodic", "wall"])
+    p, nu = 2, 0.2
+    dt = assembly.calculate_timestep(mesh, p, st.max_speed, 1.0)
+    opp = np.array([int(np.argmin(np.abs(st.e + st.e[i]).sum(1))) for i in range(9)])
+    blocks, dofs = assembly.assemble_semilagrangian(mesh, p, st.e, dt, opposite=opp)
+    u_w = np.array([0.01, 0.0])
+    hits = dofs.hits
+    idx = np.array([h["index"] for h in hits], dtype=np.int32)
+    dirs = np.array([h["direction"] for h in hits], dtype=np.int32)
+    kinds = np.zeros(len(hits), dtype=np.int32)
+    # VelocityNeqBounceBack::calculateBoundaryValues (VelocityNeqBounceBack.cpp:137-195): 2 w rho (e . u_w) / cs2, rho = 1
+    vals = np.array([2 * st.w[h["direction"]] * 1.0 * float(st.e[h["direction"]] @ u_w) / st.cs2 for h in hits])
+    f0 = fields.equilibrium_init(st.e, st.w, st.cs2, np.ones(dofs.N), np.zeros((2, dofs.N)))
+    return dict(st=st, nu=nu, dt=dt, blocks=blocks, dofs=dofs, mesh=mesh, hits=(idx, dirs, kinds, vals), f0=f0)

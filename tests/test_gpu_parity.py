@@ -1213,3 +1213,32 @@ def test_poiseuille_bounce_back_with_forcing_on_device(oracle_lib):
     mean = common.integral_mean(pb["dofs"], pb["mesh"], 2, u[0])
     assert 0.9 * pb["u_bulk"] < mean < 1.1 * pb["u_bulk"], (mean, pb["u_bulk"])
     ctx.close()
+
+
+def test_moving_walls_on_device(oracle_lib):
+    """WallTest fixture (test/boundaries/WallFixture.h:44-88) on the device: non-zero VelocityNeqBounceBack terms.  Same
+    trajectory as the oracle after 100 steps and the reference's bounds max |u - 0.01| < 1e-3, max |v| < 1e-5."""
+    from natrium_b200 import Context, Stencil
+    pb = common.moving_walls_problem(oracle_lib)
+    ost, n = pb["st"], pb["dofs"].N
+    st = Stencil("D2Q9", 1.0)
+    idx, dirs, kinds, vals = pb["hits"]
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+    ctx.set_layout(n, 0, False)
+    _upload_oracle_blocks(ctx, pb["blocks"])
+    ctx.set_wall_hits(idx, dirs, kinds, vals)
+    ctx.set_collision(pb["nu"], pb["dt"])
+    ctx.upload_populations(0, pb["f0"])
+    ctx.step(100)
+    ctx.synchronize()
+    f = pb["f0"].copy()
+    for _ in range(100):
+        f = oracle_lib.stream(pb["blocks"], f)
+        oracle_lib.apply_wall_hits(ost, f, None, idx, dirs, kinds, vals)
+        oracle_lib.collide_bgk(ost, f, pb["nu"], pb["dt"])
+    assert rel_err(ctx.download_populations(0), f) <= 1e-10
+    rho, u = ctx.download_moments()
+    assert np.max(np.abs(u[0] - 0.01)) < 1e-3 and np.max(np.abs(u[1])) < 1e-5
+    assert abs(np.abs(rho).sum() / n - 1.0) < 1e-10
+    ctx.close()

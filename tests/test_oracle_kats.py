@@ -506,3 +506,21 @@ def test_poiseuille_bounce_back_with_forcing(oracle_lib):
     mean = common.integral_mean(pb["dofs"], pb["mesh"], 2, u[0])          # SolverStats::getMeanVelocityX
     assert 0.9 * pb["u_bulk"] < mean < 1.1 * pb["u_bulk"], (mean, pb["u_bulk"], it)
     assert abs(common.integral_mean(pb["dofs"], pb["mesh"], 2, u[1])) < 1e-3 * pb["u_bulk"]
+
+
+def test_moving_walls_drag_the_fluid(oracle_lib):
+    """VelocityNeqBounceBack2D_SL_BoundaryVelocity_test / _MassConservation_test
+    (test/boundaries/VelocityNeqBounceBack_SL_test.cpp:49-87 with WallFixture.h): after 100 steps every DoF moves with
+    the walls, max |u - 0.01| < 1e-3 and max |v| < 1e-5, and the mean density stays 1 to 1e-10."""
+    pb = common.moving_walls_problem(oracle_lib)
+    st, f = pb["st"], pb["f0"].copy()
+    idx, dirs, kinds, vals = pb["hits"]
+    assert np.count_nonzero(vals) > 0
+    for _ in range(100):
+        f = oracle_lib.stream(pb["blocks"], f)
+        assert oracle_lib.apply_wall_hits(st, f, None, idx, dirs, kinds, vals) == 0
+        rho, u, rc = oracle_lib.collide_bgk(st, f, pb["nu"], pb["dt"])
+        assert rc == 0
+    assert np.max(np.abs(u[0] - 0.01)) < 1e-3
+    assert np.max(np.abs(u[1])) < 1e-5
+    assert abs(np.abs(rho).sum() / pb["dofs"].N - 1.0) < 1e-10
