@@ -50,6 +50,8 @@ def parse():
                     help="side measurement: grade the mesh in y like TurbulentChannelFlow3D (y -> y - s sin(2 pi y)/(2 pi)); 0 = uniform (the bench line)")
     ap.add_argument("--numbering", default="cell", choices=["cell", "lex"],
                     help="host DoF numbering of the synthetic problem: cell-wise like deal.II (default) or lexicographic")
+    ap.add_argument("--grid", default="on", choices=["on", "off"],
+                    help="give the structure hint nb200_set_dof_grid (grid coordinates of the DoFs): TMA box kernels; off = staged dictionary kernels")
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     return ap.parse_args()
 
@@ -274,6 +276,8 @@ def run_ours(args):
     host = numbering if numbering is not None else part       # what the host sees: points, halo plan
     if args.dof_order == "cell" and numbering is None:
         ctx.set_dof_order(part.cell_blocked_order())
+    if args.grid == "on" and args.format == "dict":
+        ctx.set_dof_grid(*host.grid_coords(), fe_order=args.order)
     t0 = time.perf_counter()
     nnz = harness.upload_streaming_matrix(ctx, pb, part, st, dt, numbering)
     t_asm = time.perf_counter() - t0

@@ -111,6 +111,23 @@ int nb200_set_layout(nb200_ctx *ctx, int64_t n_owned, int64_t n_ghost, int with_
  * source cell, and the gathered support values stay in L1. */
 int nb200_set_dof_order(nb200_ctx *ctx, int64_t n_owned, const int32_t *order);
 
+/* Optional structure hint, after nb200_set_layout (and nb200_set_dof_order, if used) and before the first
+ * nb200_upload_block_csr: the local DoFs sit on a tensor-product grid.  coords[(n_owned + n_ghost)][dim] are the integer
+ * grid coordinates of every local DoF (owned first, then the ghost slots), 0 <= coords[.][j] < dims[j]; two DoFs never
+ * share a grid point.  A continuous FE_Q(p) space on any (stretched) hyper-rectangle mesh has such coordinates whatever its
+ * DoF numbering: rank the distinct support-point coordinates of DoFTools::map_dofs_to_support_points per axis
+ * (INTEGRATION.md).  fe_order = p tells the library where cells begin (grid coordinates 0, p, 2p, ... of the local grid are
+ * cell faces; pass the coordinates shifted accordingly) or 0 if unknown.
+ * With the hint the library keeps a second, lexicographic copy of the populations and the fused kernel fetches the
+ * (p+1)^k support points of all rows of a tile as boxes of that grid with TMA tensor copies (cp.async.bulk.tensor);
+ * rows whose columns do not form such a box (bounce-back blocks at walls, truncated rows) are taken from their dictionary
+ * list.  Rows are summed in ascending grid position instead of the uploaded order.  Every other call is unchanged.
+ * dim = 0 / coords = NULL removes the hint. */
+int nb200_set_dof_grid(nb200_ctx *ctx, int dim, const int32_t *dims, const int32_t *coords, int fe_order);
+/* out = { 1 if the grid kernels are in use, #tiles, rows taken from TMA boxes (summed over directions), rows taken from
+ *         their dictionary list, #boxes (TMA copies per step and distribution), #passes, pass capacity (values), grid points } */
+int nb200_grid_info(const nb200_ctx *ctx, int64_t out[8]);
+
 /* One block (bi,bj) of getSystemMatrix() (distributed_sparse_block_matrix, (Q-1)x(Q-1) blocks,
  * SemiLagrangian.cpp:101,116-134) as local CSR: exactly what
  * block(bi,bj).trilinos_matrix().ExtractMyRowView gives row by row (idiom in

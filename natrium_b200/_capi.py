@@ -56,6 +56,8 @@ SIGNATURES = {
     "nb200_set_stencil": (C.c_int, [_vp, C.c_int, C.c_int, _dp, _dp, C.c_double, C.c_double]),
     "nb200_set_layout": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int]),
     "nb200_set_dof_order": (C.c_int, [_vp, C.c_int64, _i32p]),
+    "nb200_set_dof_grid": (C.c_int, [_vp, C.c_int, _i32p, _i32p, C.c_int]),
+    "nb200_grid_info": (C.c_int, [_vp, _i64p]),
     "nb200_upload_block_csr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _i64p, _i32p, _dp]),
     "nb200_finalize_matrix": (C.c_int, [_vp]),
     "nb200_set_matrix_format": (C.c_int, [_vp, C.c_int, C.c_double]),
@@ -176,6 +178,20 @@ class Context:
     def set_dof_order(self, order):
         order = np.ascontiguousarray(order, dtype=np.int32)
         self._check(self.lib.nb200_set_dof_order(self._h, len(order), order.ctypes.data_as(_i32p)))
+
+    def set_dof_grid(self, dims, coords, fe_order=0):
+        """Structure hint: integer grid coordinates [(n_owned + n_ghost), dim] of every local DoF (nb200_set_dof_grid)."""
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        coords = np.ascontiguousarray(coords, dtype=np.int32)
+        assert coords.ndim == 2 and coords.shape[1] == len(dims)
+        self._check(load().nb200_set_dof_grid(self._h, C.c_int(len(dims)), dims.ctypes.data_as(_i32p),
+                                              coords.ctypes.data_as(_i32p), C.c_int(int(fe_order))))
+
+    def grid_info(self):
+        out = np.zeros(8, dtype=np.int64)
+        self._check(load().nb200_grid_info(self._h, out.ctypes.data_as(_i64p)))
+        keys = ("in_use", "tiles", "box_rows", "generic_rows", "boxes", "passes", "pass_capacity", "grid_points")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def upload_block_csr(self, bi, bj, rowptr, col, val):
         rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)

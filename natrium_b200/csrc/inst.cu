@@ -67,9 +67,26 @@ int bind(const NbLaunch& L)
             if (e != cudaSuccess) return (int)e;
         }
 #endif
+        if (L.grid_off && L.grid_off_dirs > 0) {
+            e = cudaMemcpyToSymbolAsync(cGridOff, L.grid_off, sizeof(int16_t) * NB_GRID_MAXK * (size_t)L.grid_off_dirs, 0, cudaMemcpyHostToDevice, L.stream);
+            if (e != cudaSuccess) return (int)e;
+        }
         s_owner = L.owner;
         s_version = L.version;
     }
+    return 0;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: set it whenever the current device has not seen it
+template <class K>
+int set_smem(K kernel, size_t bytes, unsigned* done_mask)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 32 && ((*done_mask >> dev) & 1u)) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 32) *done_mask |= 1u << dev;
     return 0;
 }
 
@@ -93,16 +110,31 @@ int fused(const NbLaunch& L)
         else if (L.eq == NB_KIND_MRT) { NB_IF_MRT(NB_LAUNCH_F(NB_KIND_MRT, FMT)); }              \
         else return -1;                                                                          \
     } while (0)
-        if (L.fmt == NB_FMT_STAGED) {
+        if (L.fmt == NB_FMT_GRID) {
+            const size_t smem_gr = (size_t)(Q * NB_CTA_ROWS + 2 * NB_GRID_CAP) * sizeof(double);
+#define NB_LAUNCH_FGR(EQ)                                                                                                   \
+    do {                                                                                                                   \
+        static unsigned attr_mask = 0;                                                                                     \
+        int e = set_smem(k_stream_collide_f_grid<D, Q, EQ>, smem_gr, &attr_mask);                                          \
+        if (e) return e;                                                                                                   \
+        k_stream_collide_f_grid<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_gr, L.stream>>>(L.A, L.xf, L.yf, L.ygf, L.rho, L.u, L.flag); \
+    } while (0)
+            if (L.eq == NB_EQ_BGK) NB_LAUNCH_FGR(NB_EQ_BGK);
+            else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_FGR(NB_EQ_QUARTIC);
+            else if (L.eq == NB_KIND_KBC) { NB_IF_KBC(NB_LAUNCH_FGR(NB_KIND_KBC)); }
+            else if (L.eq == NB_KIND_MRT_ENTROPIC) { NB_IF_MRTE(NB_LAUNCH_FGR(NB_KIND_MRT_ENTROPIC)); }
+            else if (L.eq == NB_KIND_REGULARIZED) { NB_IF_REG(NB_LAUNCH_FGR(NB_KIND_REGULARIZED)); }
+            else if (L.eq == NB_KIND_MRT) { NB_IF_MRT(NB_LAUNCH_FGR(NB_KIND_MRT)); }
+            else return -1;
+#undef NB_LAUNCH_FGR
+        }
+        else if (L.fmt == NB_FMT_STAGED) {
             const size_t smem_st = (size_t)(Q * NB_CTA_ROWS + NB_STAGE_CAP) * sizeof(double);
 #define NB_LAUNCH_FS(EQ)                                                                                                    \
     do {                                                                                                                   \
-        static bool attr_set = false;                                                                                      \
-        if (!attr_set) {                                                                                                   \
-            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_f_staged<D, Q, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st); \
-            if (e != cudaSuccess) return (int)e;                                                                           \
-            attr_set = true;                                                                                               \
-        }                                                                                                                  \
+        static unsigned attr_mask = 0;                                                                                     \
+        int e = set_smem(k_stream_collide_f_staged<D, Q, EQ>, smem_st, &attr_mask);                                        \
+        if (e) return e;                                                                                                   \
         k_stream_collide_f_staged<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_st, L.stream>>>(L.A, L.xf, L.yf, L.rho, L.u, L.flag); \
     } while (0)
             if (L.eq == NB_EQ_BGK) NB_LAUNCH_FS(NB_EQ_BGK);
@@ -126,24 +158,30 @@ int fused(const NbLaunch& L)
         const size_t smem_fg = (size_t)2 * Q * 128 * sizeof(double);
 #define NB_LAUNCH_FG(EQ, FMT)                                                                                              \
     do {                                                                                                                   \
-        static bool attr_set = false;                                                                                      \
-        if (!attr_set) {                                                                                                   \
-            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_fg<D, Q, EQ, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fg); \
-            if (e != cudaSuccess) return (int)e;                                                                           \
-            attr_set = true;                                                                                               \
-        }                                                                                                                  \
+        static unsigned attr_mask = 0;                                                                                     \
+        int e = set_smem(k_stream_collide_fg<D, Q, EQ, FMT>, smem_fg, &attr_mask);                                         \
+        if (e) return e;                                                                                                   \
         k_stream_collide_fg<D, Q, EQ, FMT><<<grid, 128, smem_fg, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
     } while (0)
-        if (L.fmt == NB_FMT_STAGED) {
+        if (L.fmt == NB_FMT_GRID) {
+            const size_t smem_gr = (size_t)(2 * Q * NB_CTA_ROWS + 4 * NB_GRID_CAP_FG) * sizeof(double);
+#define NB_LAUNCH_FGGR(EQ)                                                                                                  \
+    do {                                                                                                                   \
+        static unsigned attr_mask = 0;                                                                                     \
+        int e = set_smem(k_stream_collide_fg_grid<D, Q, EQ>, smem_gr, &attr_mask);                                         \
+        if (e) return e;                                                                                                   \
+        k_stream_collide_fg_grid<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_gr, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.ygf, L.ygg, L.rho, L.u, L.T, L.sensor, L.flag); \
+    } while (0)
+            if (L.eq == NB_EQ_BGK) NB_LAUNCH_FGGR(NB_EQ_BGK); else NB_LAUNCH_FGGR(NB_EQ_QUARTIC);
+#undef NB_LAUNCH_FGGR
+        }
+        else if (L.fmt == NB_FMT_STAGED) {
             const size_t smem_st = (size_t)(2 * Q * NB_CTA_ROWS + 2 * NB_STAGE_CAP_FG) * sizeof(double);
 #define NB_LAUNCH_FGS(EQ)                                                                                                   \
     do {                                                                                                                   \
-        static bool attr_set = false;                                                                                      \
-        if (!attr_set) {                                                                                                   \
-            cudaError_t e = cudaFuncSetAttribute(k_stream_collide_fg_staged<D, Q, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_st); \
-            if (e != cudaSuccess) return (int)e;                                                                           \
-            attr_set = true;                                                                                               \
-        }                                                                                                                  \
+        static unsigned attr_mask = 0;                                                                                     \
+        int e = set_smem(k_stream_collide_fg_staged<D, Q, EQ>, smem_st, &attr_mask);                                       \
+        if (e) return e;                                                                                                   \
         k_stream_collide_fg_staged<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_st, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
     } while (0)
             if (L.eq == NB_EQ_BGK) NB_LAUNCH_FGS(NB_EQ_BGK); else NB_LAUNCH_FGS(NB_EQ_QUARTIC);
@@ -155,6 +193,32 @@ int fused(const NbLaunch& L)
 #else
         return -1;
 #endif
+    }
+    return (int)cudaGetLastError();
+}
+
+int stream_grid(const NbLaunch& L)
+{
+    int rc = bind(L);
+    if (rc) return rc;
+    const unsigned grid = L.grid_override;
+    if (grid == 0) return 0;
+    if (L.n_rhs == 2) {
+#if NB_WITH_G
+        const size_t sm = (size_t)4 * NB_GRID_CAP_FG * sizeof(double);
+        static unsigned attr_mask = 0;
+        int e = set_smem(k_stream_grid<D, Q, 2>, sm, &attr_mask);
+        if (e) return e;
+        k_stream_grid<D, Q, 2><<<grid, NB_CTA_ROWS, sm, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg);
+#else
+        return -1;
+#endif
+    } else {
+        const size_t sm = (size_t)2 * NB_GRID_CAP * sizeof(double);
+        static unsigned attr_mask = 0;
+        int e = set_smem(k_stream_grid<D, Q, 1>, sm, &attr_mask);
+        if (e) return e;
+        k_stream_grid<D, Q, 1><<<grid, NB_CTA_ROWS, sm, L.stream>>>(L.A, L.xf, nullptr, L.yf, nullptr);
     }
     return (int)cudaGetLastError();
 }
@@ -236,11 +300,11 @@ const NbStencilOps ops = {D, Q,
 #endif
                           collide, conserved, wall, bind,
 #if NB_HAS_MRT
-                          post
+                          post,
 #else
-                          nullptr
+                          nullptr,
 #endif
-};
+                          stream_grid};
 
 }  // namespace
 

@@ -244,6 +244,244 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
     for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// NB_FMT_GRID variants (nb200_set_dof_grid): one CTA = one tile of grid points (two half-tiles of whole cells that are
+// neighbours in x).  Per pass one thread arms an mbarrier with the pass's byte count and issues the TMA tensor copies
+// (boxes of the lexicographic grid copy of the populations) of the NEXT pass into the other staging buffer, then all
+// threads wait for the current pass's barrier and take their rows from shared memory: a class-0 row's k-th support value
+// sits at (row offset + cGridOff[direction][k]).  Results are written to the canonical arrays and to the grid copy that
+// the next step's TMA reads.  Dynamic shared memory: [tile(s)][2 staging buffers (per distribution)].
+// ---------------------------------------------------------------------------------------------
+__constant__ int16_t cGridOff[NB_MAX_DIRS][NB_GRID_MAXK];
+
+#ifndef NB_GRID_OCC_F
+#define NB_GRID_OCC_F 5
+#endif
+
+// issues the TMA copies of pass ps into the staging buffer(s) and arms the barrier (one thread)
+template <int NRHS>
+__device__ __forceinline__ void nb_grid_issue(const StreamArgs& A, const NbGridPass& ps, double* xs0, double* xs1, uint64_t* bar)
+{
+    nb_mbar_expect_tx(bar, (unsigned)ps.bytes * NRHS);
+    for (int b = 0; b < ps.n_box; b++) {
+        const NbGridBox bx = A.gbox[ps.box_begin + b];
+        nb_tma_load_3d(xs0 + bx.smem_off, reinterpret_cast<const char*>(A.tmap_f) + 128 * (int)bx.dir, bx.x, bx.y, bx.z, bar);
+        if (NRHS == 2) nb_tma_load_3d(xs1 + bx.smem_off, reinterpret_cast<const char*>(A.tmap_g) + 128 * (int)bx.dir, bx.x, bx.y, bx.z, bar);
+    }
+}
+
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(NB_CTA_ROWS, NB_GRID_OCC_F)
+k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __restrict__ y, double* __restrict__ ygrid,
+                        double* __restrict__ rho_out, double* __restrict__ u_out, int* __restrict__ flag)
+{
+    extern __shared__ __align__(128) double smem_grid[];
+    __shared__ uint64_t mbar[2];
+    __shared__ int32_t srow[NB_CTA_ROWS];
+    double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);    // [Q][128]
+    double* xs = smem_grid + Q * NB_CTA_ROWS;                                               // [2][NB_GRID_CAP]
+    const int tid = threadIdx.x;
+    const int64_t tl = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t slot = tl * NB_CTA_ROWS + tid;
+    const int32_t row = __ldg(A.tile_row + slot);
+    const bool active = row >= 0;
+    srow[tid] = row;
+    tile[0][tid] = active ? x[row] : 0.0;
+    if (tid == 0) {
+        nb_mbar_init(&mbar[0], 1);
+        nb_mbar_init(&mbar[1], 1);
+        nb_mbar_fence_init();
+    }
+    __syncthreads();
+    const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
+    if (tid == 0 && p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0]);
+    for (int p = p0; p < p1; p++) {
+        const int buf = (p - p0) & 1;
+        const NbGridPass ps = A.gpass[p];
+        // the other buffer was last read in the previous iteration, which ended with a barrier
+        if (tid == 0 && p + 1 < p1) nb_grid_issue<1>(A, A.gpass[p + 1], xs + (buf ^ 1) * NB_GRID_CAP, xs, &mbar[buf ^ 1]);
+        {
+            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.gdesc_stride + slot;
+            for (int a = ps.a0; a < ps.a1; a++, dp += A.gdesc_stride) nb_cp_async8(&tile[a + 1][tid], reinterpret_cast<const double*>(dp));
+            nb_cp_async_wait_all();
+        }
+        nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
+        __syncthreads();          // descriptors of the partner row are in place
+        const double* __restrict__ xb = xs + buf * NB_GRID_CAP;
+        const int half = tid >> 6, t0 = tid & 63;
+        const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
+#pragma unroll 1
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = reinterpret_cast<const int2*>(&tile[a + 1][t0])[0];
+            const int2 d1 = reinterpret_cast<const int2*>(&tile[a + 1][t0 + 64])[0];
+            double r[4];
+            nb_row_dot_grid_pair<1>(A, a, d0, d1, r0, r1, cGridOff[a], xb, xb, x, x, r);
+            tile[a + 1][t0] = r[0];
+            tile[a + 1][t0 + 64] = r[1];
+        }
+        __syncthreads();          // rows are done with this buffer; results of a row come from the other half of the CTA
+    }
+    if (!active) return;
+    double f[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
+    double rho, v[3] = {0.0, 0.0, 0.0};
+    if (nb_collide_f<D, Q, EQ>(f, rho, v, false, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
+    const int64_t gi = __ldg(A.tile_gidx + slot);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        y[(int64_t)q * A.stride + row] = f[q];
+        ygrid[(int64_t)q * A.gstride + gi] = f[q];
+    }
+    rho_out[row] = rho;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = v[j];
+}
+
+// f + g: both distributions staged by the same boxes; [tile f][tile g][2 buffers f][2 buffers g]
+template <int D, int Q, int EQ>
+__global__ void __launch_bounds__(NB_CTA_ROWS, NB_FUSED_OCC_FG)
+k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const double* __restrict__ xg,
+                         double* __restrict__ yf, double* __restrict__ yg, double* __restrict__ yfgrid, double* __restrict__ yggrid,
+                         double* __restrict__ rho_out, double* __restrict__ u_out, double* __restrict__ T_out,
+                         double* __restrict__ s_out, int* __restrict__ flag)
+{
+    extern __shared__ __align__(128) double smem_grid[];
+    __shared__ uint64_t mbar[2];
+    __shared__ int32_t srow[NB_CTA_ROWS];
+    double (*tf)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);
+    double (*tg)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid + Q * NB_CTA_ROWS);
+    double* xsf = smem_grid + 2 * Q * NB_CTA_ROWS;       // [2][NB_GRID_CAP_FG]
+    double* xsg = xsf + 2 * NB_GRID_CAP_FG;
+    const int tid = threadIdx.x;
+    const int64_t tl = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t slot = tl * NB_CTA_ROWS + tid;
+    const int32_t row = __ldg(A.tile_row + slot);
+    const bool active = row >= 0;
+    srow[tid] = row;
+    tf[0][tid] = active ? xf[row] : 0.0;
+    tg[0][tid] = active ? xg[row] : 0.0;
+    if (tid == 0) {
+        nb_mbar_init(&mbar[0], 1);
+        nb_mbar_init(&mbar[1], 1);
+        nb_mbar_fence_init();
+    }
+    __syncthreads();
+    const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
+    if (tid == 0 && p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0]);
+    for (int p = p0; p < p1; p++) {
+        const int buf = (p - p0) & 1;
+        const NbGridPass ps = A.gpass[p];
+        if (tid == 0 && p + 1 < p1)
+            nb_grid_issue<2>(A, A.gpass[p + 1], xsf + (buf ^ 1) * NB_GRID_CAP_FG, xsg + (buf ^ 1) * NB_GRID_CAP_FG, &mbar[buf ^ 1]);
+        {
+            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.gdesc_stride + slot;
+            for (int a = ps.a0; a < ps.a1; a++, dp += A.gdesc_stride) nb_cp_async8(&tf[a + 1][tid], reinterpret_cast<const double*>(dp));
+            nb_cp_async_wait_all();
+        }
+        nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
+        __syncthreads();
+        const double* __restrict__ xbf = xsf + buf * NB_GRID_CAP_FG;
+        const double* __restrict__ xbg = xsg + buf * NB_GRID_CAP_FG;
+        const int half = tid >> 6, t0 = tid & 63;
+        const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
+#pragma unroll 1
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = reinterpret_cast<const int2*>(&tf[a + 1][t0])[0];
+            const int2 d1 = reinterpret_cast<const int2*>(&tf[a + 1][t0 + 64])[0];
+            double r[4];
+            nb_row_dot_grid_pair<2>(A, a, d0, d1, r0, r1, cGridOff[a], xbf, xbg, xf, xg, r);
+            tf[a + 1][t0] = r[0];
+            tf[a + 1][t0 + 64] = r[1];
+            tg[a + 1][t0] = r[2];
+            tg[a + 1][t0 + 64] = r[3];
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    double f[Q], g[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        f[q] = tf[q][tid];
+        g[q] = tg[q][tid];
+    }
+    double rho, u[3], T, sensor;
+    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, nullptr);
+    if (rho < 1e-10) *flag = 1;
+    const int64_t gi = __ldg(A.tile_gidx + slot);
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        yf[(int64_t)q * A.stride + row] = f[q];
+        yg[(int64_t)q * A.stride + row] = g[q];
+        yfgrid[(int64_t)q * A.gstride + gi] = f[q];
+        yggrid[(int64_t)q * A.gstride + gi] = g[q];
+    }
+    rho_out[row] = rho;
+    T_out[row] = T;
+    s_out[row] = sensor;
+#pragma unroll
+    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = u[j] * cP.scaling;
+}
+
+// Stream only over the grid copy (the vmult site and the unfused configurations): canonical output only.
+// (templated on the stencil so that every stencil unit launches its own instance, which reads that unit's cGridOff)
+template <int D, int Q, int NRHS>
+__global__ void __launch_bounds__(NB_CTA_ROWS)
+k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restrict__ x1,
+              double* __restrict__ y0, double* __restrict__ y1)
+{
+    extern __shared__ __align__(128) double smem_grid[];
+    __shared__ uint64_t mbar[2];
+    __shared__ int32_t srow[NB_CTA_ROWS];
+    constexpr int CAP = NRHS == 2 ? NB_GRID_CAP_FG : NB_GRID_CAP;
+    double* xs0 = smem_grid;                         // [2][CAP]
+    double* xs1 = smem_grid + (NRHS == 2 ? 2 * CAP : 0);
+    const int tid = threadIdx.x;
+    const int64_t tl = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
+    const int64_t slot = tl * NB_CTA_ROWS + tid;
+    const int32_t row = __ldg(A.tile_row + slot);
+    srow[tid] = row;
+    if (row >= 0) {
+        y0[row] = x0[row];
+        if (NRHS == 2) y1[row] = x1[row];
+    }
+    if (tid == 0) {
+        nb_mbar_init(&mbar[0], 1);
+        nb_mbar_init(&mbar[1], 1);
+        nb_mbar_fence_init();
+    }
+    __syncthreads();
+    const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
+    if (tid == 0 && p0 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0], xs0, xs1, &mbar[0]);
+    const int half = tid >> 6, t0 = tid & 63;
+    const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
+    for (int p = p0; p < p1; p++) {
+        const int buf = (p - p0) & 1;
+        const NbGridPass ps = A.gpass[p];
+        if (tid == 0 && p + 1 < p1) nb_grid_issue<NRHS>(A, A.gpass[p + 1], xs0 + (buf ^ 1) * CAP, xs1 + (buf ^ 1) * CAP, &mbar[buf ^ 1]);
+        nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
+        const double* __restrict__ xb0 = xs0 + buf * CAP;
+        const double* __restrict__ xb1 = xs1 + buf * CAP;
+#pragma unroll 1
+        for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
+            const int2 d0 = nb_ld_once(A.sdesc + (int64_t)a * A.gdesc_stride + tl * NB_CTA_ROWS + t0);
+            const int2 d1 = nb_ld_once(A.sdesc + (int64_t)a * A.gdesc_stride + tl * NB_CTA_ROWS + t0 + 64);
+            double r[4];
+            nb_row_dot_grid_pair<NRHS>(A, a, d0, d1, r0, r1, cGridOff[a], xb0, xb1, x0, x1, r);
+            if (r0 >= 0) {
+                y0[(int64_t)(a + 1) * A.stride + r0] = r[0];
+                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + r0] = r[2];
+            }
+            if (r1 >= 0) {
+                y0[(int64_t)(a + 1) * A.stride + r1] = r[1];
+                if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + r1] = r[3];
+            }
+        }
+        __syncthreads();          // everybody is done with this buffer before the copy after next lands in it
+    }
+}
+
 // Stand-alone collide (in place), f only.  FORCE: external-force hooks compiled in.
 template <int D, int Q, int EQ, bool FORCE>
 __global__ void __launch_bounds__(128)

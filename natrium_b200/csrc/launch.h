@@ -32,6 +32,11 @@ struct NbLaunch {
     const int32_t* hit_dir; const int32_t* hit_kind; const double* hit_val;
     // conserved sums
     double* partial; int n_partial_blocks; double* out;
+    // grid kernels (NB_FMT_GRID): grid copies the fused kernel writes next to yf / yg, and the host copy of the
+    // per-direction offset table [(Q-1)][NB_GRID_MAXK] (uploaded into the unit's constant memory with the constants)
+    double* ygf; double* ygg;
+    const int16_t* grid_off; int grid_off_dirs;
+    int n_rhs;              // stream_grid: 1 = the distribution in xf/yf, 2 = f and g in one pass
 };
 
 struct NbStencilOps {
@@ -42,6 +47,7 @@ struct NbStencilOps {
     int (*wall)(const NbLaunch&);        // wall hits on yf (and yg)
     int (*bind)(const NbLaunch&);        // uploads the constant block if this context's version is not the bound one
     int (*post)(const NbLaunch&);        // post-collision matrix on yf; nullptr where the reference has none
+    int (*stream_grid)(const NbLaunch&); // stream only over the grid copy (xf[, xg] -> yf[, yg], canonical output)
 };
 
 const NbStencilOps* nb_ops_d2q9();

@@ -14,6 +14,7 @@
 //   this file    context, uploads/downloads (with the optional internal DoF order), halo plans (pruned NCCL neighbour
 //                exchange overlapped with the interior CTAs), step sequencing incl. walls / forces / post-collision
 //                matrix, the chunk-pipelined host-buffer step, diagnostics.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <algorithm>
@@ -29,6 +30,7 @@
 #include "nbconst.h"
 #include "launch.h"
 #include "dict_build.h"
+#include "grid_build.h"
 
 // ---------------------------------------------------------------------------------------------
 // NCCL, bound at run time (dlopen) so that a single-GPU user needs no NCCL at all and a
@@ -139,6 +141,24 @@ struct nb200_ctx {
     int64_t stage_values = 0, stage_passes = 0, stage_max_pass = 0;
     std::vector<NbDirClass> cls0;            // class 0 of every direction (copied into the kernel arguments)
     int stage_cap = 0;
+    // grid (TMA box) path, nb200_set_dof_grid: lexicographic copies of the populations + driving tables (grid_build.h)
+    bool grid_hint = false, grid_ready = false;
+    nbgrid::Grid grid;
+    double* gpop[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [which][buffer], Q * gstride doubles each
+    bool grid_valid[2] = {false, false};     // grid copy of the CURRENT buffer of f / g equals the canonical array
+    int64_t gstride = 0;
+    int32_t* d_gidx_of_int = nullptr;        // [n_owned + n_ghost] canonical internal index -> flat grid index
+    int64_t n_tiles = 0, gdesc_stride = 0;
+    int32_t *d_tile_row = nullptr, *d_tile_gidx = nullptr, *d_tile_pass = nullptr;
+    int2* d_gdesc = nullptr;
+    NbGridPass* d_gpass = nullptr;
+    NbGridBox* d_gbox = nullptr;
+    void* d_tmaps = nullptr;                 // [which][buffer][(Q-1)] CUtensorMap (128 bytes each)
+    std::vector<int16_t> grid_off;           // [(Q-1)][NB_GRID_MAXK] host copy of the offset table (constant memory of the unit)
+    int32_t *d_gtile_interior = nullptr, *d_gtile_boundary = nullptr;
+    int64_t n_gtile_interior = 0, n_gtile_boundary = 0;
+    int64_t grid_rows = 0, grid_generic_rows = 0, grid_boxes = 0, grid_passes = 0;
+    int grid_cap = 0;
     // collision
     const NbStencilOps* ops = nullptr;
     uint64_t const_version = 1;
@@ -403,6 +423,16 @@ __global__ void k_chunk_gather(int64_t u0, int64_t u1, int rows, const int32_t* 
     for (int r = blockIdx.y; r < rows; r += gridDim.y) stage[(int64_t)r * n + u] = dev[(int64_t)r * dev_stride + i];
 }
 
+// canonical -> grid copy of `rows` populations: gdst[r*gstride + gidx[i]] = src[r*stride + i], i over owned and ghost slots
+__global__ void k_to_grid(int64_t n, int rows, const int32_t* __restrict__ gidx, const double* __restrict__ src, int64_t stride,
+                          double* __restrict__ gdst, int64_t gstride)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t g = gidx[i];
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) gdst[(int64_t)r * gstride + g] = src[(int64_t)r * stride + i];
+}
+
 // halo pack / unpack.  A segment = one (neighbour, distribution, population) triple that the receiving rank's
 // matrix actually reads; segments of one neighbour are contiguous in the buffer.
 __global__ void k_halo_pack(const NbHaloSeg* __restrict__ segs, const int32_t* __restrict__ send_idx, int64_t stride,
@@ -414,13 +444,19 @@ __global__ void k_halo_pack(const NbHaloSeg* __restrict__ segs, const int32_t* _
         buf[sg.buf_off + e] = x[send_idx[sg.idx_off + e]];
 }
 
+// gidx != null: the ghost values also go into the grid copies (gxf / gxg, pitch gstride) the TMA kernels read
 __global__ void k_halo_unpack(const NbHaloSeg* __restrict__ segs, int64_t stride, int64_t n_owned,
-                              double* __restrict__ xf, double* __restrict__ xg, const double* __restrict__ buf)
+                              double* __restrict__ xf, double* __restrict__ xg, const double* __restrict__ buf,
+                              const int32_t* __restrict__ gidx, double* __restrict__ gxf, double* __restrict__ gxg, int64_t gstride)
 {
     const NbHaloSeg sg = segs[blockIdx.y];
     double* __restrict__ x = (sg.which ? xg : xf) + (int64_t)sg.pop * stride + n_owned + sg.idx_off;
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < sg.cnt; e += (int64_t)gridDim.x * blockDim.x)
-        x[e] = buf[sg.buf_off + e];
+    double* __restrict__ gx = gidx ? (sg.which ? gxg : gxf) : nullptr;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < sg.cnt; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = buf[sg.buf_off + e];
+        x[e] = v;
+        if (gx) gx[(int64_t)sg.pop * gstride + gidx[n_owned + sg.idx_off + e]] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -508,7 +544,24 @@ static void free_matrix(nb200_ctx* c)
         H = nb200_ctx::HostStep();
     }
     c->cta_max_user.clear();
+    cudaFree(c->d_tile_row); cudaFree(c->d_tile_gidx); cudaFree(c->d_tile_pass); cudaFree(c->d_gdesc); cudaFree(c->d_gpass);
+    cudaFree(c->d_gbox); cudaFree(c->d_tmaps); cudaFree(c->d_gtile_interior); cudaFree(c->d_gtile_boundary);
+    c->d_tile_row = c->d_tile_gidx = c->d_tile_pass = nullptr; c->d_gdesc = nullptr; c->d_gpass = nullptr; c->d_gbox = nullptr;
+    c->d_tmaps = nullptr; c->d_gtile_interior = c->d_gtile_boundary = nullptr;
+    c->grid_ready = false;
+    c->n_tiles = c->gdesc_stride = c->n_gtile_interior = c->n_gtile_boundary = 0;
     c->matrix_ready = false;
+}
+
+static void free_grid(nb200_ctx* c)
+{
+    for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) { cudaFree(c->gpop[w][b]); c->gpop[w][b] = nullptr; }
+    cudaFree(c->d_gidx_of_int);
+    c->d_gidx_of_int = nullptr;
+    c->grid_hint = false;
+    c->grid_valid[0] = c->grid_valid[1] = false;
+    c->grid = nbgrid::Grid();
+    c->gstride = 0;
 }
 
 extern "C" void nb200_destroy(nb200_ctx* c)
@@ -518,6 +571,7 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     cudaStreamSynchronize(c->stream);
     free_blocks(c);
     free_matrix(c);
+    free_grid(c);
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) cudaFree(c->pop[w][b]);
     cudaFree(c->rho); cudaFree(c->u); cudaFree(c->T); cudaFree(c->sensor);
     cudaFree(c->d_flag); cudaFree(c->d_partial);
@@ -641,6 +695,7 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
     c->cur[0] = c->cur[1] = 0;
     free_blocks(c);
     free_matrix(c);
+    free_grid(c);
     cudaFree(c->d_order); cudaFree(c->d_perm); cudaFree(c->d_stage);
     c->d_order = c->d_perm = nullptr; c->d_stage = nullptr;
     c->has_order = false;
@@ -656,7 +711,7 @@ extern "C" int nb200_set_dof_order(nb200_ctx* c, int64_t n, const int32_t* order
 {
     if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "set_dof_order: call set_layout first");
     if (n != c->n_owned || (n > 0 && !order)) return fail(c, NB200_ERR_ARG, "set_dof_order: n=%lld != n_owned=%lld", (long long)n, (long long)c->n_owned);
-    if (!c->blocks.empty() || c->matrix_ready || c->n_nbr) return fail(c, NB200_ERR_ARG, "set_dof_order: call right after set_layout (before matrix / halo uploads)");
+    if (!c->blocks.empty() || c->matrix_ready || c->n_nbr || c->grid_hint) return fail(c, NB200_ERR_ARG, "set_dof_order: call right after set_layout (before set_dof_grid / matrix / halo uploads)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     std::vector<int32_t> perm((size_t)n, -1);
     for (int64_t k = 0; k < n; k++) {
@@ -674,6 +729,52 @@ extern "C" int nb200_set_dof_order(nb200_ctx* c, int64_t n, const int32_t* order
         CUDA_TRY(c, cudaMemcpy(c->d_perm, c->perm.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
     }
     c->has_order = n > 0;
+    return NB200_OK;
+}
+
+extern "C" int nb200_set_dof_grid(nb200_ctx* c, int dim, const int32_t* dims, const int32_t* coords, int fe_order)
+{
+    if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "set_dof_grid: call set_layout first");
+    if (!coords && dim == 0) { free_grid(c); return NB200_OK; }         // removes the hint
+    if ((dim != 2 && dim != 3) || dim != c->D || !dims || !coords || fe_order < 0) return fail(c, NB200_ERR_ARG, "set_dof_grid: bad argument");
+    if (!c->blocks.empty() || c->matrix_ready) return fail(c, NB200_ERR_ARG, "set_dof_grid: call before the first upload_block_csr");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    free_grid(c);
+    nbgrid::Grid& g = c->grid;
+    g.dim = dim;
+    g.fe_order = fe_order;
+    for (int j = 0; j < 3; j++) g.n[j] = j < dim ? dims[j] : 1;
+    for (int j = 0; j < dim; j++) if (g.n[j] < 1 || g.n[j] > 32000) return fail(c, NB200_ERR_ARG, "set_dof_grid: grid dimension %d out of range", (int)g.n[j]);
+    g.nxp = (g.n[0] + 1) & ~1;
+    g.G = g.nxp * g.n[1] * g.n[2];
+    const int64_t nloc = c->n_owned + c->n_ghost;
+    if ((int64_t)c->Q * g.G >= (int64_t)INT32_MAX) return fail(c, NB200_ERR_UNSUPPORTED, "set_dof_grid: Q * grid points exceeds the int32 index range");
+    if (g.G > 4 * std::max<int64_t>(nloc, 1024)) return fail(c, NB200_ERR_UNSUPPORTED, "set_dof_grid: the local DoFs fill less than a quarter of their bounding grid");
+    g.gidx_of_int.assign((size_t)nloc, -1);
+    std::vector<uint8_t> seen((size_t)g.G, 0);
+    for (int64_t u = 0; u < nloc; u++) {
+        int cc[3] = {0, 0, 0};
+        for (int j = 0; j < dim; j++) {
+            cc[j] = coords[u * dim + j];
+            if (cc[j] < 0 || cc[j] >= g.n[j]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: coordinate of DoF %lld outside the grid", (long long)u); }
+        }
+        const int64_t f = g.flat(cc[0], cc[1], cc[2]);
+        if (seen[(size_t)f]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: two DoFs at grid point (%d,%d,%d)", cc[0], cc[1], cc[2]); }
+        seen[(size_t)f] = 1;
+        const int64_t i = (u < c->n_owned && c->has_order) ? c->perm[(size_t)u] : u;      // internal canonical index
+        g.gidx_of_int[(size_t)i] = (int32_t)f;
+    }
+    c->gstride = (g.G + 31) / 32 * 32;
+    const size_t bytes = (size_t)c->Q * c->gstride * sizeof(double);
+    for (int w = 0; w < (c->with_g ? 2 : 1); w++)
+        for (int b = 0; b < 2; b++) {
+            CUDA_TRY(c, cudaMalloc(&c->gpop[w][b], bytes));
+            CUDA_TRY(c, cudaMemsetAsync(c->gpop[w][b], 0, bytes, c->stream));
+        }
+    CUDA_TRY(c, cudaMalloc(&c->d_gidx_of_int, (size_t)std::max<int64_t>(1, nloc) * 4));
+    if (nloc) CUDA_TRY(c, cudaMemcpy(c->d_gidx_of_int, g.gidx_of_int.data(), (size_t)nloc * 4, cudaMemcpyHostToDevice));
+    c->grid_hint = true;
+    c->grid_valid[0] = c->grid_valid[1] = false;
     return NB200_OK;
 }
 
@@ -777,6 +878,14 @@ extern "C" int nb200_upload_block_csr(nb200_ctx* c, int bi, int bj, int64_t n_ro
         col = p_col.data();
         val = p_val.data();
     }
+    if (c->fmt == NB_FMT_DICT && c->grid_hint && nnz > 0) {
+        // grid hint: the entries of every row in ascending grid position (z, y, x), so that the k-th entry of every full row
+        // of a direction has the same offset relative to the first; this is the summation order of all dictionary kernels then
+        if (nbgrid::sort_rows_by_grid(c->grid.gidx_of_int, n_rows, rowptr, col, val, p_col, p_val)) {
+            col = p_col.data();
+            val = p_val.data();
+        }
+    }
     if (c->fmt == NB_FMT_DICT) {
         if (c->dirs.empty()) {
             c->dirs.resize((size_t)(c->Q - 1));
@@ -801,6 +910,87 @@ extern "C" int nb200_upload_block_csr(nb200_ctx* c, int bi, int bj, int64_t n_ro
     }
     c->blocks.push_back(b);
     c->matrix_ready = false;
+    return NB200_OK;
+}
+
+// ---- grid (TMA box) path: device tables and tensor maps ---------------------------------------------
+typedef CUresult (*NbEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int upload_grid_tables(nb200_ctx* c, nbgrid::Tables& T)
+{
+    static_assert(sizeof(NbGridPass) == sizeof(nbgrid::PassHost) && sizeof(NbGridBox) == sizeof(nbgrid::BoxHost), "grid table layout");
+    static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+    const int nb = c->Q - 1;
+    const nbgrid::Grid& g = c->grid;
+    // the driver entry point that encodes tensor maps (no link dependency on libcuda)
+    NbEncodeTiled encode = nullptr;
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+            return fail(c, NB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        encode = (NbEncodeTiled)fn;
+    }
+    const int n_dist = c->with_g ? 2 : 1;
+    std::vector<CUtensorMap> maps((size_t)2 * 2 * nb);
+    memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    for (int w = 0; w < n_dist; w++)
+        for (int b = 0; b < 2; b++)
+            for (int a = 0; a < nb; a++) {
+                const cuuint64_t gdim[3] = {(cuuint64_t)g.nxp, (cuuint64_t)g.n[1], (cuuint64_t)g.n[2]};
+                const cuuint64_t gstr[2] = {(cuuint64_t)g.nxp * 8, (cuuint64_t)g.nxp * g.n[1] * 8};
+                const cuuint32_t box[3] = {(cuuint32_t)T.box_dims[(size_t)a * 3], (cuuint32_t)T.box_dims[(size_t)a * 3 + 1], (cuuint32_t)T.box_dims[(size_t)a * 3 + 2]};
+                const cuuint32_t est[3] = {1, 1, 1};
+                void* base = c->gpop[w][b] + (int64_t)(a + 1) * c->gstride;
+                CUresult r = encode(&maps[(size_t)((w * 2 + b) * nb + a)], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, est,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(c, NB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for direction %d, box %ux%ux%u", (int)r, a, box[0], box[1], box[2]);
+            }
+    CUDA_TRY(c, cudaMalloc(&c->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+    CUDA_TRY(c, cudaMemcpy(c->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    const size_t nslot = (size_t)T.n_tiles * NB_CTA_ROWS;
+    CUDA_TRY(c, cudaMalloc(&c->d_tile_row, nslot * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_tile_gidx, nslot * 4));
+    CUDA_TRY(c, cudaMemcpy(c->d_tile_row, T.tile_row.data(), nslot * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_tile_gidx, T.tile_gidx.data(), nslot * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMalloc(&c->d_tile_pass, T.tile_pass.size() * 4));
+    CUDA_TRY(c, cudaMemcpy(c->d_tile_pass, T.tile_pass.data(), T.tile_pass.size() * 4, cudaMemcpyHostToDevice));
+    {
+        std::vector<int2> hd(T.desc_x.size());
+        for (size_t i = 0; i < hd.size(); i++) hd[i] = make_int2(T.desc_x[i], T.desc_y[i]);
+        std::vector<int32_t>().swap(T.desc_x);
+        std::vector<int32_t>().swap(T.desc_y);
+        CUDA_TRY(c, cudaMalloc(&c->d_gdesc, hd.size() * sizeof(int2)));
+        CUDA_TRY(c, cudaMemcpy(c->d_gdesc, hd.data(), hd.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(c, cudaMalloc(&c->d_gpass, T.passes.size() * sizeof(NbGridPass)));
+    CUDA_TRY(c, cudaMemcpy(c->d_gpass, T.passes.data(), T.passes.size() * sizeof(NbGridPass), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMalloc(&c->d_gbox, std::max<size_t>(1, T.boxes.size()) * sizeof(NbGridBox)));
+    if (!T.boxes.empty()) CUDA_TRY(c, cudaMemcpy(c->d_gbox, T.boxes.data(), T.boxes.size() * sizeof(NbGridBox), cudaMemcpyHostToDevice));
+    {
+        std::vector<int32_t> interior, boundary;
+        for (int64_t b = 0; b < T.n_tiles; b++) (T.tile_reads_ghost[(size_t)b] ? boundary : interior).push_back((int32_t)b);
+        c->n_gtile_interior = (int64_t)interior.size();
+        c->n_gtile_boundary = (int64_t)boundary.size();
+        if (!interior.empty()) {
+            CUDA_TRY(c, cudaMalloc(&c->d_gtile_interior, interior.size() * 4));
+            CUDA_TRY(c, cudaMemcpy(c->d_gtile_interior, interior.data(), interior.size() * 4, cudaMemcpyHostToDevice));
+        }
+        if (!boundary.empty()) {
+            CUDA_TRY(c, cudaMalloc(&c->d_gtile_boundary, boundary.size() * 4));
+            CUDA_TRY(c, cudaMemcpy(c->d_gtile_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    c->grid_off = T.off_table;
+    c->n_tiles = T.n_tiles;
+    c->gdesc_stride = T.desc_stride;
+    c->grid_rows = T.grid_rows; c->grid_generic_rows = T.generic_rows; c->grid_boxes = T.total_boxes; c->grid_passes = (int64_t)T.passes.size();
+    c->grid_ready = true;
+    c->grid_valid[0] = c->grid_valid[1] = false;
+    c->const_version = ++g_const_stamp;          // the offset table travels with the constant block
     return NB200_OK;
 }
 
@@ -831,6 +1021,16 @@ static int finalize_dict(nb200_ctx* c)
         const bool want = c->want_staged && !(env && env[0] == '0') && n > 0;
         c->stage_cap = c->with_g ? NB_STAGE_CAP_FG : NB_STAGE_CAP;
         if (want) staged_ok = nbdict::build_staging(c->dirs, n, c->desc_stride, NB_CTA_ROWS, c->stage_cap, NB_MAX_CLS - 1, SB);
+    }
+    // grid (TMA box) tables: need the host lists as well
+    nbgrid::Tables GT;
+    bool grid_ok = false;
+    if (c->grid_hint && n > 0) {
+        static const char* envg = getenv("NB200_GRID");       // experiments only: NB200_GRID=0 keeps the staged dictionary kernels
+        if (!(envg && envg[0] == '0')) {
+            c->grid_cap = c->with_g ? NB_GRID_CAP_FG : NB_GRID_CAP;
+            grid_ok = nbgrid::build(c->dirs, c->grid, n, c->stride, NB_CTA_ROWS, c->grid_cap, NB_GRID_MAXK, NB_MAX_CLS - 1, GT);
+        }
     }
     for (int a = 0; a < nb; a++) {
         nbdict::DirBuild& d = c->dirs[(size_t)a];
@@ -938,12 +1138,18 @@ static int finalize_dict(nb200_ctx* c)
                 CUDA_TRY(c, cudaMemcpy(c->d_cta_boundary, boundary.data(), boundary.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
             }
         }
-        c->cls0.resize((size_t)nb);
-        for (int a = 0; a < nb; a++) c->cls0[(size_t)a] = hcls[(size_t)a * NB_MAX_CLS];
         c->staged = true;
         c->stage_values = (int64_t)SB.stage_col.size();
         c->stage_passes = (int64_t)SB.passes.size();
         c->stage_max_pass = SB.max_pass_count;
+    }
+    if (staged_ok || grid_ok) {
+        c->cls0.resize((size_t)nb);
+        for (int a = 0; a < nb; a++) c->cls0[(size_t)a] = hcls[(size_t)a * NB_MAX_CLS];
+    }
+    if (grid_ok) {
+        int rc = upload_grid_tables(c, GT);
+        if (rc) return rc;
     }
     free_blocks(c);
     c->matrix_ready = true;
@@ -1064,6 +1270,7 @@ extern "C" int nb200_upload_population(nb200_ctx* c, int which, int q, const dou
     CUDA_TRY(c, cudaSetDevice(c->device));
     rc = copy_rows_in(c, host, 1, c->pop[which][c->cur[which]] + (int64_t)q * c->stride, c->stride);
     if (rc) return rc;
+    c->grid_valid[which] = false;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
 }
@@ -1090,6 +1297,7 @@ static int copy_all(nb200_ctx* c, int which, double* host, int64_t n, bool up, b
         double* dev = c->pop[which][c->cur[which]];
         rc = up ? copy_rows_in(c, host, c->Q, dev, c->stride) : copy_rows_out(c, host, c->Q, dev, c->stride);
         if (rc) return rc;
+        if (up) c->grid_valid[which] = false;
     }
     if (sync) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return NB200_OK;
@@ -1431,7 +1639,17 @@ static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true,
     NCCL_TRY(c, g_nccl.GroupEnd());
     if (!P->recv_segs.empty()) {
         dim3 grid((unsigned)std::min<int64_t>(64, (P->max_recv_cnt + 255) / 256), (unsigned)P->recv_segs.size());
-        k_halo_unpack<<<grid, 256, 0, st>>>(P->d_recv_segs, c->stride, c->n_owned, xf, xg, c->d_recvbuf);
+        // the grid copies of the current buffers get the ghost values too (only where they are in sync with the canonical
+        // arrays; a stale copy is rebuilt as a whole before its next use)
+        const bool gf = c->grid_hint && c->grid_valid[0] && (mask & 1), gg = c->grid_hint && c->with_g && c->grid_valid[1] && (mask & 2);
+        k_halo_unpack<<<grid, 256, 0, st>>>(P->d_recv_segs, c->stride, c->n_owned, xf, xg, c->d_recvbuf,
+                                            (gf || gg) ? c->d_gidx_of_int : nullptr, gf ? c->gpop[0][c->cur[0]] : nullptr,
+                                            gg ? c->gpop[1][c->cur[1]] : nullptr, c->gstride);
+        // a distribution whose copy was not updated here and is marked valid would now be stale in its ghost positions
+        if (c->grid_hint) {
+            if ((mask & 1) && !gf) c->grid_valid[0] = false;
+            if ((mask & 2) && !gg) c->grid_valid[1] = false;
+        }
         c->launches++;
     }
     return NB200_OK;
@@ -1453,12 +1671,15 @@ static StreamArgs stream_args(nb200_ctx* c)
     A.sdesc = c->d_sdesc; A.stage_col = c->d_stage_col; A.stage_pass = c->d_stage_pass; A.stage_cta = c->d_stage_cta;
     A.cta_map = nullptr;
     for (int a = 0; a < NB_MAX_DIRS; a++) {
-        const bool have = c->staged && a < (int)c->cls0.size();
+        const bool have = (c->staged || c->grid_ready) && a < (int)c->cls0.size();
         A.c0_W[a] = have ? c->cls0[(size_t)a].W : nullptr;
         A.c0_P[a] = have ? (int32_t)c->cls0[(size_t)a].P : 32;
         A.c0_K[a] = have ? (c->cls0[(size_t)a].K | (c->cls0[(size_t)a].streamed << 30)) : 0;
     }
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
+    A.tile_row = c->d_tile_row; A.tile_gidx = c->d_tile_gidx; A.gpass = c->d_gpass; A.gbox = c->d_gbox;
+    A.tmap_f = A.tmap_g = nullptr;
+    A.gstride = c->gstride; A.gdesc_stride = c->gdesc_stride;
     return A;
 }
 
@@ -1469,7 +1690,40 @@ static const NbStencilOps* find_ops(int D, int Q)
     return nullptr;
 }
 
-static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0)
+// the grid (TMA box) kernels drive the step when the host gave the grid hint and the tables could be built
+static bool use_grid(const nb200_ctx* c)
+{
+    return c->fmt == NB_FMT_DICT && c->grid_ready;
+}
+
+// switches the staged-table slots of the kernel arguments to the grid tables; tensor maps of the CURRENT buffers
+static void grid_args(const nb200_ctx* c, StreamArgs& A)
+{
+    const size_t nb = (size_t)(c->Q - 1);
+    A.sdesc = c->d_gdesc;
+    A.stage_cta = c->d_tile_pass;
+    A.tmap_f = (const char*)c->d_tmaps + ((size_t)(0 * 2 + c->cur[0]) * nb) * 128;
+    A.tmap_g = c->with_g ? (const char*)c->d_tmaps + ((size_t)(1 * 2 + c->cur[1]) * nb) * 128 : nullptr;
+}
+
+// brings the grid copies of the current buffers in line with the canonical arrays (no-op while they are)
+static int sync_grid(nb200_ctx* c, bool do_f, bool do_g, cudaStream_t st)
+{
+    if (!c->grid_hint) return NB200_OK;
+    const int64_t nloc = c->n_owned + c->n_ghost;
+    for (int w = 0; w < 2; w++) {
+        if (!(w == 0 ? do_f : (do_g && c->with_g)) || c->grid_valid[w]) continue;
+        if (nloc > 0) {
+            k_to_grid<<<dim3((unsigned)((nloc + 255) / 256), (unsigned)c->Q), 256, 0, st>>>(nloc, c->Q, c->d_gidx_of_int, c->pop[w][c->cur[w]], c->stride,
+                                                                                           c->gpop[w][c->cur[w]], c->gstride);
+            c->launches++;
+        }
+        c->grid_valid[w] = true;
+    }
+    return NB200_OK;
+}
+
+static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_t n_cta = 0, bool allow_grid = true)
 {
     NbLaunch L;
     memset(&L, 0, sizeof(L));
@@ -1477,6 +1731,9 @@ static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int6
     L.A = stream_args(c);
     L.A.cta_map = cta_map;
     L.grid_override = cta_map ? (unsigned)n_cta : 0u;
+    L.grid_off = c->grid_ready ? c->grid_off.data() : nullptr;
+    L.grid_off_dirs = c->Q - 1;
+    L.n_rhs = 1;
     L.rho = c->rho; L.u = c->u; L.T = c->T; L.sensor = c->sensor; L.flag = c->d_flag;
     L.eq = c->kind;
     L.mrt = c->kind == NB_KIND_MRT_ENTROPIC ? &c->mrt : nullptr;
@@ -1485,6 +1742,11 @@ static NbLaunch make_launch(nb200_ctx* c, const int32_t* cta_map = nullptr, int6
     L.post_matrix = c->post_set ? &c->post_matrix[0][0] : nullptr;
     L.with_g = c->cp.with_g; L.in_init = c->cp.in_init;
     L.fmt = (c->fmt == NB_FMT_DICT && c->staged) ? NB_FMT_STAGED : c->fmt;
+    if (allow_grid && use_grid(c)) {
+        L.fmt = NB_FMT_GRID;
+        grid_args(c, L.A);
+        if (!cta_map) L.grid_override = (unsigned)c->n_tiles;
+    }
     L.hc = &c->hc; L.owner = c; L.version = c->const_version;
     L.n_hit_groups = c->n_hit_groups; L.hit_group_dof = c->d_hit_group_dof; L.hit_group_off = c->d_hit_group_off;
     L.hit_dir = c->d_hit_dir; L.hit_kind = c->d_hit_kind; L.hit_val = c->d_hit_val;
@@ -1508,6 +1770,13 @@ static int dispatch_fused(nb200_ctx* c, const int32_t* cta_map = nullptr, int64_
     L.xf = c->pop[0][c->cur[0]];
     L.yf = c->pop[0][c->cur[0] ^ 1];
     if (c->cp.with_g) { L.xg = c->pop[1][c->cur[1]]; L.yg = c->pop[1][c->cur[1] ^ 1]; }
+    if (L.fmt == NB_FMT_GRID) {      // the kernel also writes the grid copies of the next buffers (the caller has synced the current ones)
+        L.ygf = c->gpop[0][c->cur[0] ^ 1];
+        if (c->cp.with_g) L.ygg = c->gpop[1][c->cur[1] ^ 1];
+    } else if (flip) {
+        c->grid_valid[0] = false;
+        if (c->cp.with_g) c->grid_valid[1] = false;
+    }
     int rc = cuda_rc(c, c->ops->fused(L), "fused stream+collide");
     if (rc) return rc;
     if (flip) {
@@ -1525,6 +1794,8 @@ static int dispatch_collide(nb200_ctx* c)
     if (c->cp.with_g) L.yg = c->pop[1][c->cur[1]];
     int rc = cuda_rc(c, c->ops->collide(L), "collide");
     if (rc) return rc;
+    c->grid_valid[0] = false;
+    if (c->cp.with_g) c->grid_valid[1] = false;
     c->launches++;
     return NB200_OK;
 }
@@ -1536,6 +1807,7 @@ static int dispatch_post(nb200_ctx* c)
     L.yf = c->pop[0][c->cur[0]];
     int rc = cuda_rc(c, c->ops->post(L), "post-collision matrix");
     if (rc) return rc;
+    c->grid_valid[0] = false;
     c->launches++;
     return NB200_OK;
 }
@@ -1558,6 +1830,7 @@ static int dispatch_wall(nb200_ctx* c)
     L.yg = c->with_g ? c->pop[1][c->cur[1]] : nullptr;
     int rc = cuda_rc(c, c->ops->wall(L), "wall hits");
     if (rc) return rc;
+    c->grid_valid[0] = c->grid_valid[1] = false;
     c->launches++;
     return NB200_OK;
 }
@@ -1567,21 +1840,43 @@ static int launch_stream(nb200_ctx* c, bool do_f, bool do_g, const int32_t* cta_
     StreamArgs A = stream_args(c);
     A.cta_map = cta_map;
     dim3 grid(grid_for(c->n_slices * 32, 128), (unsigned)c->Q);
+    if (use_grid(c) && c->ops && c->ops->stream_grid) {
+        // TMA box kernels; cta_map / n_cta are tile lists then.  Canonical output only: the grid copy of the new buffer is stale.
+        NbLaunch L = make_launch(c, cta_map, n_cta);
+        if (do_f && do_g) {
+            L.n_rhs = 2;
+            L.xf = c->pop[0][c->cur[0]]; L.xg = c->pop[1][c->cur[1]];
+            L.yf = c->pop[0][c->cur[0] ^ 1]; L.yg = c->pop[1][c->cur[1] ^ 1];
+        } else {
+            const int w = do_f ? 0 : 1;
+            L.n_rhs = 1;
+            L.xf = c->pop[w][c->cur[w]]; L.yf = c->pop[w][c->cur[w] ^ 1];
+            if (w == 1) L.A.tmap_f = L.A.tmap_g;
+        }
+        int rc = cuda_rc(c, c->ops->stream_grid(L), "stream (grid)");
+        if (rc) return rc;
+        if (flip) {
+            if (do_f) { c->cur[0] ^= 1; c->grid_valid[0] = false; }
+            if (do_g) { c->cur[1] ^= 1; c->grid_valid[1] = false; }
+        }
+        c->launches++;
+        return NB200_OK;
+    }
+    if (do_f) c->grid_valid[0] = false;
+    if (do_g) c->grid_valid[1] = false;
     // the staged tables are sized for two distributions when the layout has g (NB_STAGE_CAP_FG), which a
     // single-distribution pass can use as well
     if (c->fmt == NB_FMT_DICT && c->staged) {
         const unsigned g1 = cta_map ? (unsigned)n_cta : grid_for(c->n_owned, NB_CTA_ROWS);
         if (do_f && do_g) {
-            static bool attr2 = false;
             const size_t sm = (size_t)2 * NB_STAGE_CAP_FG * sizeof(double);
-            if (!attr2) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr2 = true; }
+            CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   // per device, cheap
             k_stream_staged<2><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[0][c->cur[0]], c->pop[1][c->cur[1]], c->pop[0][c->cur[0] ^ 1], c->pop[1][c->cur[1] ^ 1]);
             if (flip) { c->cur[0] ^= 1; c->cur[1] ^= 1; }
         } else {
             const int w = do_f ? 0 : 1;
-            static bool attr1 = false;
             const size_t sm = (size_t)NB_STAGE_CAP * sizeof(double);
-            if (!attr1) { CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); attr1 = true; }
+            CUDA_TRY(c, cudaFuncSetAttribute(k_stream_staged<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_stream_staged<1><<<g1, NB_CTA_ROWS, sm, c->stream>>>(A, c->Q, c->pop[w][c->cur[w]], nullptr, c->pop[w][c->cur[w] ^ 1], nullptr);
             if (flip) c->cur[w] ^= 1;
         }
@@ -1621,7 +1916,8 @@ extern "C" int nb200_stream(nb200_ctx* c, int which)
     rc = halo_exchange(c, which == 0, which == 1);
     if (rc) return rc;
     if (c->n_slices == 0) return NB200_OK;
-    rc = launch_stream(c, which == 0, which == 1);
+    if (use_grid(c)) rc = sync_grid(c, which == 0, which == 1, c->stream);
+    if (!rc) rc = launch_stream(c, which == 0, which == 1);
     if (!rc && which == 0) rc = dispatch_wall(c);     // m_boundaryHandler.apply(f, f_old, t) / apply(f, f_old, g, t)
     CUDA_TRY(c, cudaGetLastError());
     return rc;
@@ -1668,20 +1964,34 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
         if (rc) return rc;
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
-    const bool split = c->overlap && c->nranks > 1 && c->n_nbr > 0 && c->fmt == NB_FMT_DICT && c->staged
-        && c->n_cta_interior > 0 && c->n_cta_boundary > 0;
+    // CTA lists of the kernels in use: tiles of the grid kernels or 128-row blocks of the staged ones
+    const bool grid = use_grid(c);
+    const int32_t* l_int = grid ? c->d_gtile_interior : c->d_cta_interior;
+    const int32_t* l_bnd = grid ? c->d_gtile_boundary : c->d_cta_boundary;
+    const int64_t n_int = grid ? c->n_gtile_interior : c->n_cta_interior, n_bnd = grid ? c->n_gtile_boundary : c->n_cta_boundary;
+    const bool split = c->overlap && c->nranks > 1 && c->n_nbr > 0 && c->fmt == NB_FMT_DICT && (grid || c->staged)
+        && n_int > 0 && n_bnd > 0;
     for (int s = 0; s < n_steps; s++) {
         if (c->n_hit_groups > 0) {
             // walls: reference order stream(f) -> wall hits (on the new f and the not yet streamed g) -> gStream -> collide
-            // (CompressibleCFDSolver.h:181-314); the hit kernel sits between the two streams, so nothing is fused
-            rc = halo_exchange(c, true, do_g);
+            // (CompressibleCFDSolver.h:181-314); the hit kernel sits between the two streams, so nothing is fused.
+            // g is exchanged AFTER the hits: ThermalBounceBack rewrites g at wall DoFs, and the reference's gStream imports
+            // those post-wall values (CompressibleCFDSolver.h:195,279-291).
+            rc = halo_exchange(c, true, false);
+            if (!rc && grid) rc = sync_grid(c, true, false, c->stream);
             if (!rc && c->n_slices > 0) rc = launch_stream(c, true, false);
             if (!rc) rc = dispatch_wall(c);
+            if (!rc && do_g) rc = halo_exchange(c, false, true);
+            if (!rc && do_g && grid) rc = sync_grid(c, false, true, c->stream);
             if (!rc && do_g && c->n_slices > 0) rc = launch_stream(c, false, true);
             if (!rc && c->n_owned > 0) rc = dispatch_collide(c);
             if (!rc) rc = dispatch_post(c);
             if (rc) return rc;
             continue;
+        }
+        if (grid) {
+            rc = sync_grid(c, true, do_g, c->stream);
+            if (rc) return rc;
         }
         if (split) {
             CUDA_TRY(c, cudaEventRecord(c->ev_prev, c->stream));            // populations of the previous step are final
@@ -1692,14 +2002,14 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             if (use_fused(c)) {
                 // boundary CTAs ride the (high-priority) exchange stream right behind the unpack, so they overlap the
                 // tail of the interior kernel; the context stream joins both before the buffers flip
-                rc = dispatch_fused(c, c->d_cta_boundary, c->n_cta_boundary, false, c->comm_stream);
+                rc = dispatch_fused(c, l_bnd, n_bnd, false, c->comm_stream);
                 CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
-                if (!rc) rc = dispatch_fused(c, c->d_cta_interior, c->n_cta_interior, true);
+                if (!rc) rc = dispatch_fused(c, l_int, n_int, true);
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
             } else {
-                rc = launch_stream(c, true, do_g, c->d_cta_interior, c->n_cta_interior, false);
+                rc = launch_stream(c, true, do_g, l_int, n_int, false);
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
-                if (!rc) rc = launch_stream(c, true, do_g, c->d_cta_boundary, c->n_cta_boundary, true);
+                if (!rc) rc = launch_stream(c, true, do_g, l_bnd, n_bnd, true);
                 if (!rc) rc = dispatch_collide(c);
             }
             if (!rc) rc = dispatch_post(c);
@@ -1841,7 +2151,7 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)H.need_up[(size_t)k]], 0));
         const int64_t b0 = H.cta_off[(size_t)k], b1 = H.cta_off[(size_t)k + 1];
         if (b1 > b0) {
-            NbLaunch L = make_launch(c, H.d_iota + b0, b1 - b0);
+            NbLaunch L = make_launch(c, H.d_iota + b0, b1 - b0, /*allow_grid=*/false);     // chunks are 128-row blocks of the staged tables
             L.xf = x; L.yf = y;
             rc = cuda_rc(c, c->ops->fused(L), "fused stream+collide (host step)");
             if (rc) return rc;
@@ -1878,6 +2188,7 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_dn, 0));      // the context stream is the fence for callers
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)C - 1], 0));
     c->cur[0] ^= 1;
+    c->grid_valid[0] = false;
     CUDA_TRY(c, cudaGetLastError());
     return NB200_OK;
 }
@@ -1975,6 +2286,7 @@ extern "C" int nb200_set_matrix_format(nb200_ctx* c, int format, double value_de
     if (format != NB200_FORMAT_ELL && format != NB200_FORMAT_DICT && format != NB200_FORMAT_DICT_UNSTAGED) return fail(c, NB200_ERR_ARG, "set_matrix_format: unknown format %d", format);
     if (!(value_dedup_tol >= 0.0) || value_dedup_tol > 1e-10) return fail(c, NB200_ERR_ARG, "set_matrix_format: tolerance must be in [0, 1e-10]");
     if (!c->blocks.empty()) return fail(c, NB200_ERR_ARG, "set_matrix_format: call before the first upload_block_csr");
+    if (c->matrix_ready) { CUDA_TRY(c, cudaSetDevice(c->device)); free_matrix(c); }      // the finished matrix belongs to the old format
     c->fmt = format == NB200_FORMAT_ELL ? NB_FMT_ELL : NB_FMT_DICT;
     c->want_staged = format == NB200_FORMAT_DICT;
     c->dedup_tol = value_dedup_tol;
@@ -2002,6 +2314,20 @@ extern "C" int nb200_staging_info(const nb200_ctx* c, int64_t out[5])
     out[2] = c->stage_passes;
     out[3] = c->stage_max_pass;
     out[4] = c->stage_cap;
+    return NB200_OK;
+}
+
+extern "C" int nb200_grid_info(const nb200_ctx* c, int64_t out[8])
+{
+    if (!c || !c->matrix_ready || !out) return NB200_ERR_ARG;
+    out[0] = use_grid(c) ? 1 : 0;
+    out[1] = c->n_tiles;
+    out[2] = c->grid_rows;
+    out[3] = c->grid_generic_rows;
+    out[4] = c->grid_boxes;
+    out[5] = c->grid_passes;
+    out[6] = c->grid_cap;
+    out[7] = c->grid.G;
     return NB200_OK;
 }
 

@@ -20,7 +20,10 @@
 //                NB_STAGE_CAP doubles.  Rows that read the same source cell share the staged copy, so the
 //                gather traffic per CTA drops from rows x K to lists x K loads and the dependent
 //                descriptor -> list -> value chain of NB_FMT_DICT disappears from the inner loop.
-enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
+//   NB_FMT_GRID    the dictionary format driven tile by tile over a lexicographic grid copy of the populations
+//                (nb200_set_dof_grid): the support values of a tile of rows are whole boxes of that grid and arrive by TMA
+//                tensor copies (cp.async.bulk.tensor -> mbarrier), double buffered; see grid_build.h.
+enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2, NB_FMT_GRID = 3 };
 
 #define NB_CTA_ROWS 128
 // Pass capacity in doubles per distribution.  Deliberately small: with 5 CTAs per SM the staged values take
@@ -33,6 +36,15 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2 };
 #define NB_STAGE_CAP_FG 2048       // f and g staged together (two arrays of this size)
 #endif
 #define NB_MAX_DIRS 44             // Q - 1 of the largest stencil on the path (D3Q45)
+// grid kernels: capacity of ONE staging buffer in doubles per distribution (two buffers: the TMA copies of the next
+// pass land while the current one is multiplied), and the longest row the offset table holds ((p+1)^3 for p <= 4)
+#ifndef NB_GRID_CAP
+#define NB_GRID_CAP 1536
+#endif
+#ifndef NB_GRID_CAP_FG
+#define NB_GRID_CAP_FG 1280
+#endif
+#define NB_GRID_MAXK 128
 
 #define NB_CLS_BITS 6
 #define NB_MAX_CLS (1 << NB_CLS_BITS)           // row-length classes per direction
@@ -61,6 +73,18 @@ struct NbStagePass {
     int16_t a0, a1;
 };
 
+// one staging pass of one tile (grid kernels): directions [a0, a1), boxes [box_begin, box_begin + n_box)
+struct NbGridPass {
+    int32_t box_begin;
+    int16_t n_box, a0, a1, pad;
+    int32_t bytes;          // TMA bytes of the pass for one distribution
+};
+// one TMA copy: box of direction dir's population with origin (x, y, z) -> staging buffer + smem_off
+struct NbGridBox {
+    int16_t x, y, z, dir;
+    int32_t smem_off;
+};
+
 struct StreamArgs {
     // NB_FMT_ELL
     const double* __restrict__ ell_val;
@@ -84,6 +108,16 @@ struct StreamArgs {
     int64_t n_slices;
     int64_t n_owned;
     int64_t stride;
+    // NB_FMT_GRID (shares cls / desc / c0_* with the dictionary; sdesc holds the grid descriptors, stage_cta the first pass
+    // of every tile)
+    const int32_t* __restrict__ tile_row;    // [n_tiles][NB_CTA_ROWS] canonical row of every tile thread, -1 = idle
+    const int32_t* __restrict__ tile_gidx;   // [n_tiles][NB_CTA_ROWS] flat index in the grid copy
+    const NbGridPass* __restrict__ gpass;
+    const NbGridBox* __restrict__ gbox;
+    const void* tmap_f;                      // [(Q-1)] CUtensorMap of population a+1 in the current grid copy of f
+    const void* tmap_g;                      //         ... of g
+    int64_t gstride;                         // population pitch of the grid copies
+    int64_t gdesc_stride;                    // pitch of the grid descriptors (sdesc) = n_tiles * NB_CTA_ROWS
 };
 
 // one ELL row dot product for 1 or 2 right-hand sides (f and g share the matrix pass)
@@ -417,6 +451,166 @@ __device__ __forceinline__ void nb_stage_pass(const int32_t* __restrict__ sc, in
             if (NRHS == 2) nb_cp_async8(xs1 + tid + j * NB_CTA_ROWS, x1 + idx[j]);
         }
     nb_cp_async_wait_all();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// NB_FMT_GRID device side: mbarrier + TMA tensor copies, row products with the per-direction offset table
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nb_mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void nb_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void nb_mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nb_mbar_wait(uint64_t* bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NB_DONE_%=;\n"
+        "bra NB_WAIT_%=;\n"
+        "NB_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// box with origin (x, y, z) of the 3-d tensor `tmap` -> shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void nb_tma_load_3d(double* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// Two class-0 rows with the same weight pattern: one weight load feeds both rows (and both distributions).
+// s0/s1: first support value of row 0 / row 1 in the f buffer, g0/g1 in the g buffer.  Summation order k = 0..K-1.
+template <int NRHS, bool STREAMED, int B2>
+__device__ __forceinline__ void nb_grid_batches_pair(const double2* __restrict__ W2, int K, int64_t P, const int16_t* __restrict__ off,
+                                                     const double* __restrict__ s0, const double* __restrict__ s1,
+                                                     const double* __restrict__ g0, const double* __restrict__ g1, double (&acc)[4])
+{
+    const int Kh = (K + 1) >> 1;
+    for (int kk = 0; kk < Kh; kk += B2) {
+        double2 vv[B2];
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int kj = min(kk + j, Kh - 1);
+            vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
+        }
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int k = 2 * (kk + j);
+            if (k < K) {
+                const int o = off[k];
+                acc[0] += vv[j].x * s0[o];
+                acc[1] += vv[j].x * s1[o];
+                if (NRHS == 2) {
+                    acc[2] += vv[j].x * g0[o];
+                    acc[3] += vv[j].x * g1[o];
+                }
+            }
+            if (k + 1 < K) {
+                const int o = off[k + 1];
+                acc[0] += vv[j].y * s0[o];
+                acc[1] += vv[j].y * s1[o];
+                if (NRHS == 2) {
+                    acc[2] += vv[j].y * g0[o];
+                    acc[3] += vv[j].y * g1[o];
+                }
+            }
+        }
+    }
+}
+
+template <int NRHS, bool STREAMED, int B2>
+__device__ __forceinline__ void nb_grid_batches(const double2* __restrict__ W2, int K, int64_t P, const int16_t* __restrict__ off,
+                                                const double* __restrict__ s0, const double* __restrict__ g0, double& a0, double& a1)
+{
+    const int Kh = (K + 1) >> 1;
+    for (int kk = 0; kk < Kh; kk += B2) {
+        double2 vv[B2];
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int kj = min(kk + j, Kh - 1);
+            vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
+        }
+#pragma unroll
+        for (int j = 0; j < B2; j++) {
+            const int k = 2 * (kk + j);
+            if (k < K) {
+                const int o = off[k];
+                a0 += vv[j].x * s0[o];
+                if (NRHS == 2) a1 += vv[j].x * g0[o];
+            }
+            if (k + 1 < K) {
+                const int o = off[k + 1];
+                a0 += vv[j].y * s0[o];
+                if (NRHS == 2) a1 += vv[j].y * g0[o];
+            }
+        }
+    }
+}
+
+// One row of direction a from its grid descriptor d: class 0 rows from the staged boxes, "generic" rows (bit 31) from
+// their dictionary list in global memory, rows of the K = 0 class give 0.
+template <int NRHS>
+__device__ __forceinline__ void nb_row_dot_grid(const StreamArgs& A, int a, int2 d, int32_t row, const int16_t* __restrict__ off,
+                                                const double* __restrict__ xs0, const double* __restrict__ xs1,
+                                                const double* __restrict__ x0, const double* __restrict__ x1, double& y0, double& y1)
+{
+    const unsigned dx = (unsigned)d.x;
+    y0 = y1 = 0.0;
+    if (dx >> 31) {
+        if (row >= 0) nb_row_dot_dict<NRHS>(A, a, row, x0, x1, y0, y1);
+        return;
+    }
+    if ((dx >> 16) != 0) return;
+    const int kk = A.c0_K[a];
+    const int K = kk & 0x3fffffff;
+    const int64_t P = A.c0_P[a];
+    const double2* W2 = reinterpret_cast<const double2*>(A.c0_W[a] + 2 * (int64_t)(unsigned)d.y);
+    const unsigned o = dx & 0xffffu;
+    if (kk >> 30) {
+        if (K <= 8) nb_grid_batches<NRHS, true, 4>(W2, K, P, off, xs0 + o, xs1 + o, y0, y1);
+        else nb_grid_batches<NRHS, true, 7>(W2, K, P, off, xs0 + o, xs1 + o, y0, y1);
+    } else {
+        if (K <= 8) nb_grid_batches<NRHS, false, 4>(W2, K, P, off, xs0 + o, xs1 + o, y0, y1);
+        else nb_grid_batches<NRHS, false, 7>(W2, K, P, off, xs0 + o, xs1 + o, y0, y1);
+    }
+}
+
+// Rows r0 / r1 (descriptors d0 / d1) of direction a; y = { row0 f, row1 f, row0 g, row1 g }.
+template <int NRHS>
+__device__ __forceinline__ void nb_row_dot_grid_pair(const StreamArgs& A, int a, int2 d0, int2 d1, int32_t r0, int32_t r1,
+                                                     const int16_t* __restrict__ off, const double* __restrict__ xs0,
+                                                     const double* __restrict__ xs1, const double* __restrict__ x0,
+                                                     const double* __restrict__ x1, double (&y)[4])
+{
+    const unsigned u0 = (unsigned)d0.x, u1 = (unsigned)d1.x;
+    if (((u0 | u1) >> 16) == 0 && d0.y == d1.y) {        // both class 0 (not generic), same weight pattern
+        const int kk = A.c0_K[a];
+        const int K = kk & 0x3fffffff;
+        const int64_t P = A.c0_P[a];
+        const double2* W2 = reinterpret_cast<const double2*>(A.c0_W[a] + 2 * (int64_t)(unsigned)d0.y);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (kk >> 30) {
+            if (K <= 8) nb_grid_batches_pair<NRHS, true, 4>(W2, K, P, off, xs0 + u0, xs0 + u1, xs1 + u0, xs1 + u1, acc);
+            else nb_grid_batches_pair<NRHS, true, 7>(W2, K, P, off, xs0 + u0, xs0 + u1, xs1 + u0, xs1 + u1, acc);
+        } else {
+            if (K <= 8) nb_grid_batches_pair<NRHS, false, 4>(W2, K, P, off, xs0 + u0, xs0 + u1, xs1 + u0, xs1 + u1, acc);
+            else nb_grid_batches_pair<NRHS, false, 7>(W2, K, P, off, xs0 + u0, xs0 + u1, xs1 + u0, xs1 + u1, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) y[i] = acc[i];
+    } else {
+        nb_row_dot_grid<NRHS>(A, a, d0, r0, off, xs0, xs1, x0, x1, y[0], y[2]);
+        nb_row_dot_grid<NRHS>(A, a, d1, r1, off, xs0, xs1, x0, x1, y[1], y[3]);
+    }
 }
 
 template <int FMT, int NRHS>

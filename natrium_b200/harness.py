@@ -226,6 +226,57 @@ class SlabPartition:
     def owned_global_ids(self):
         return (self.owned_planes[:, None] * self.pb.plane + np.arange(self.pb.plane)[None, :]).reshape(-1)
 
+    def grid_coords(self):
+        """(dims, coords) for nb200_set_dof_grid: integer grid coordinates of every local DoF (owned, then ghosts) in a
+        local tensor grid whose coordinates 0, p, 2p, ... are cell faces.  In a deal.II build the same numbers come from
+        ranking the support-point coordinates per axis.  The last axis is the slab axis: own cells keep their order, the
+        cell above the slab follows directly, cells reached across the periodic boundary sit one empty cell away (the two
+        coincident planes there are distinct DoFs)."""
+        pb, p = self.pb, self.pb.p
+        ax = pb.axes[-1]
+        C = ax.n
+        bounds = [(C * r) // self.nranks for r in range(self.nranks + 1)]
+        b0, b1 = bounds[self.rank], bounds[self.rank + 1]
+        vcell = {}                                     # plane -> (virtual cell, position)
+        for g in self.owned_planes:
+            c = 0 if g == 0 else (g - 1) // p
+            vcell[int(g)] = (c, int(g) - c * p)
+        for g in self.ghost_planes:
+            g = int(g)
+            cands = [min(g // p, C - 1)]
+            if g % p == 0 and g > 0 and g // p <= C - 1:
+                cands.append(g // p - 1)
+            pick = None
+            for c in cands:                            # a cell of this rank, or the neighbour right above / below
+                if b0 <= c < b1:
+                    pick = (c, g - c * p)
+            if pick is None:
+                for c in cands:
+                    if c == b1 or c == b0 - 1:
+                        pick = (c, g - c * p)
+            if pick is None:                           # across the periodic boundary: the top cell below / the bottom cell above
+                below = cands[0] >= b1
+                c = max(cands) if below else min(cands)
+                pick = ((b0 - 2) if below else (b1 + 1), g - c * p)
+            vcell[g] = pick
+        vmin = min(v for v, _ in vcell.values())
+        zloc = {g: (v - vmin) * p + j for g, (v, j) in vcell.items()}
+        nz = max(zloc.values()) + 1
+        planes = np.concatenate([self.owned_planes, self.ghost_planes]).astype(np.int64)
+        zl = np.array([zloc[int(g)] for g in planes], dtype=np.int32)
+        if pb.dim == 2:
+            x = np.arange(pb.nd[0], dtype=np.int32)
+            coords = np.stack([np.tile(x, len(planes)), np.repeat(zl, pb.plane)], axis=1)
+            dims = [pb.nd[0], nz]
+        else:
+            x = np.arange(pb.nd[0], dtype=np.int32)
+            y = np.arange(pb.nd[1], dtype=np.int32)
+            xy = np.stack([np.tile(x, pb.nd[1]), np.repeat(y, pb.nd[0])], axis=1)
+            coords = np.concatenate([np.tile(xy, (len(planes), 1)), np.repeat(zl, pb.plane)[:, None]], axis=1)
+            dims = [pb.nd[0], pb.nd[1], nz]
+        assert len(np.unique(coords, axis=0)) == len(coords)
+        return np.array(dims, dtype=np.int32), np.ascontiguousarray(coords, dtype=np.int32)
+
 
 # ------------------------------------------------------------------------------------------
 # streaming matrix
@@ -278,6 +329,11 @@ class CellNumbering:
 
     def owned_points(self):
         return self.part.owned_points()[self.order]
+
+    def grid_coords(self):
+        dims, coords = self.part.grid_coords()
+        n = self.n_owned
+        return dims, np.ascontiguousarray(np.concatenate([coords[:n][self.order], coords[n:]]))
 
     def halo_plan(self):
         nbr, send_off, send_idx, recv_off = self.part.halo_plan()

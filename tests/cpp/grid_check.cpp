@@ -1,0 +1,198 @@
+// Host-only check of the NB_FMT_GRID driving tables (natrium_b200/csrc/grid_build.h): assembles a semi-Lagrangian-like
+// matrix on a periodic tensor grid (continuous FE_Q(p): cells share their face points, periodic faces are distinct points),
+// with an arbitrary DoF numbering and shuffled row entries, runs the same steps as nb200_upload_block_csr /
+// nb200_finalize_matrix (row sort by grid position -> dictionary -> grid tables) and replays the kernel's access pattern on
+// the CPU: TMA boxes (out-of-range points read 0) -> staging buffer, row = sum_k W[pattern][k] * xs[offset + off_table[k]],
+// rows marked generic from their dictionary list.  Compares with the plain CSR product.
+// Usage: grid_check <dim> <cells_x> <cells_y> <cells_z> <p> <numbering 0=lex 1=random> <cap> <seed> [wall]
+//        wall = 1 adds a few off-diagonal (bounce-back like) entries and truncated rows, which must come out generic.
+#include <cstdio>
+#include <cstdlib>
+#include <array>
+#include <numeric>
+#include <random>
+#include "../../natrium_b200/csrc/grid_build.h"
+
+int main(int argc, char** argv)
+{
+    const int dim = argc > 1 ? atoi(argv[1]) : 3;
+    int nc[3] = {argc > 2 ? atoi(argv[2]) : 3, argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 3};
+    const int p = argc > 5 ? atoi(argv[5]) : 4;
+    const int numbering = argc > 6 ? atoi(argv[6]) : 0;
+    const int cap = argc > 7 ? atoi(argv[7]) : 1536;
+    const unsigned seed = argc > 8 ? (unsigned)atoi(argv[8]) : 1u;
+    const int wall = argc > 9 ? atoi(argv[9]) : 0;
+    if (dim == 2) nc[2] = 0;
+    int nd[3];
+    for (int j = 0; j < 3; j++) nd[j] = j < dim ? nc[j] * p + 1 : 1;
+    const int64_t n = (int64_t)nd[0] * nd[1] * nd[2];
+    const int64_t stride = ((n + 31) / 32) * 32;
+    std::mt19937_64 rng(seed);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    // numbering: user index of lexicographic point
+    std::vector<int32_t> user_of_lex((size_t)n);
+    std::iota(user_of_lex.begin(), user_of_lex.end(), 0);
+    if (numbering) std::shuffle(user_of_lex.begin(), user_of_lex.end(), rng);
+    nbgrid::Grid g;
+    g.dim = dim; g.fe_order = p;
+    for (int j = 0; j < 3; j++) g.n[j] = nd[j];
+    g.nxp = (nd[0] + 1) & ~1;
+    g.G = g.nxp * nd[1] * nd[2];
+    g.gidx_of_int.assign((size_t)n, -1);
+    for (int z = 0; z < nd[2]; z++) for (int y = 0; y < nd[1]; y++) for (int x = 0; x < nd[0]; x++)
+        g.gidx_of_int[(size_t)user_of_lex[(size_t)(((int64_t)z * nd[1] + y) * nd[0] + x)]] = (int32_t)g.flat(x, y, z);
+    // directions: all sign combinations with at least one non-zero component
+    std::vector<std::array<int, 3>> dirs_e;
+    for (int sz = (dim == 3 ? -1 : 0); sz <= (dim == 3 ? 1 : 0); sz++) for (int sy = -1; sy <= 1; sy++) for (int sx = -1; sx <= 1; sx++)
+        if (sx || sy || sz) dirs_e.push_back(std::array<int, 3>{{sx, sy, sz}});
+    const int ndir = (int)dirs_e.size();
+    // 1D interpolation weights per (sign, position in cell, k): arbitrary numbers (the product structure is what matters)
+    std::vector<double> w1((size_t)2 * (p + 1) * (p + 1));
+    for (auto& v : w1) v = U(rng);
+    auto track = [&](int axis, int X, int s, int* cols, double* wts) -> int {
+        if (s == 0) { cols[0] = X; wts[0] = 1.0; return 1; }
+        int c = X > 0 ? (X - 1) / p : 0, loc = X - c * p;
+        if (s > 0 && loc == 0) c = (c + nc[axis] - 1) % nc[axis];       // departure towards -: leaves through the low face
+        if (s < 0 && loc == p) c = (c + 1) % nc[axis];                  // departure towards +
+        for (int k = 0; k <= p; k++) { cols[k] = c * p + k; wts[k] = w1[(size_t)(((s > 0) * (p + 1) + loc) * (p + 1) + k)]; }
+        return p + 1;
+    };
+    std::vector<double> x((size_t)(ndir + 1) * stride);
+    for (auto& v : x) v = U(rng);
+    std::vector<nbdict::DirBuild> dirs((size_t)ndir);
+    std::vector<std::vector<int64_t>> rowptr((size_t)ndir);
+    std::vector<std::vector<int32_t>> col((size_t)ndir);       // user numbering, unsorted
+    std::vector<std::vector<double>> val((size_t)ndir);
+    std::vector<std::vector<int32_t>> wall_col((size_t)ndir);  // extra off-diagonal entries (population of direction (a+1) % ndir)
+    std::vector<std::vector<double>> wall_val((size_t)ndir);
+    std::vector<std::vector<int64_t>> wall_ptr((size_t)ndir);
+    for (int a = 0; a < ndir; a++) {
+        dirs[(size_t)a].init(n);
+        std::vector<std::vector<int32_t>> rc((size_t)n);
+        std::vector<std::vector<double>> rv((size_t)n);
+        for (int Z = 0; Z < nd[2]; Z++) for (int Y = 0; Y < nd[1]; Y++) for (int X = 0; X < nd[0]; X++) {
+            int cx[8], cy[8], cz[8];
+            double wx[8], wy[8], wz[8];
+            const int kx = track(0, X, dirs_e[(size_t)a][0], cx, wx), ky = track(1, Y, dirs_e[(size_t)a][1], cy, wy);
+            const int kz = dim == 3 ? track(2, Z, dirs_e[(size_t)a][2], cz, wz) : (cz[0] = 0, wz[0] = 1.0, 1);
+            const int32_t r = user_of_lex[(size_t)(((int64_t)Z * nd[1] + Y) * nd[0] + X)];
+            for (int c = 0; c < kz; c++) for (int b = 0; b < ky; b++) for (int aa = 0; aa < kx; aa++) {
+                rc[(size_t)r].push_back(user_of_lex[(size_t)(((int64_t)cz[c] * nd[1] + cy[b]) * nd[0] + cx[aa])]);
+                rv[(size_t)r].push_back(wx[aa] * wy[b] * wz[c]);
+            }
+            if (wall && (r % 13) == 4 && rc[(size_t)r].size() > 2) { rc[(size_t)r].resize(rc[(size_t)r].size() - 2); rv[(size_t)r].resize(rv[(size_t)r].size() - 2); }
+            // shuffled entry order: the library sorts by grid position
+            std::vector<size_t> o(rc[(size_t)r].size());
+            std::iota(o.begin(), o.end(), 0);
+            std::shuffle(o.begin(), o.end(), rng);
+            std::vector<int32_t> c2(o.size());
+            std::vector<double> v2(o.size());
+            for (size_t i = 0; i < o.size(); i++) { c2[i] = rc[(size_t)r][o[i]]; v2[i] = rv[(size_t)r][o[i]]; }
+            rc[(size_t)r].swap(c2); rv[(size_t)r].swap(v2);
+        }
+        auto& rp = rowptr[(size_t)a];
+        rp.push_back(0);
+        wall_ptr[(size_t)a].push_back(0);
+        for (int64_t r = 0; r < n; r++) {
+            col[(size_t)a].insert(col[(size_t)a].end(), rc[(size_t)r].begin(), rc[(size_t)r].end());
+            val[(size_t)a].insert(val[(size_t)a].end(), rv[(size_t)r].begin(), rv[(size_t)r].end());
+            rp.push_back((int64_t)col[(size_t)a].size());
+            if (wall && (r % 17) == 3) { wall_col[(size_t)a].push_back((int32_t)((r * 7 + 1) % n)); wall_val[(size_t)a].push_back(0.25); }
+            wall_ptr[(size_t)a].push_back((int64_t)wall_col[(size_t)a].size());
+        }
+        // what nb200_upload_block_csr does: sort by grid position, then the dictionary
+        std::vector<int32_t> sc;
+        std::vector<double> sv;
+        const int32_t* cp = col[(size_t)a].data();
+        const double* vp = val[(size_t)a].data();
+        if (nbgrid::sort_rows_by_grid(g.gidx_of_int, n, rp.data(), cp, vp, sc, sv)) { cp = sc.data(); vp = sv.data(); }
+        const char* msg = "";
+        if (!nbdict::add_block(dirs[(size_t)a], n, rp.data(), cp, vp, (int64_t)(a + 1) * stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block %s\n", msg); return 1; }
+        if (wall) {
+            const int b = (a + 1) % ndir;
+            if (!nbdict::add_block(dirs[(size_t)a], n, wall_ptr[(size_t)a].data(), wall_col[(size_t)a].data(), wall_val[(size_t)a].data(),
+                                   (int64_t)(b + 1) * stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block wall %s\n", msg); return 1; }
+        }
+    }
+    nbgrid::Tables T;
+    const int max_k = 128;
+    if (!nbgrid::build(dirs, g, n, stride, 128, cap, max_k, 63, T)) { printf("INFEASIBLE\n"); return 0; }
+    // grid copy of x
+    const int64_t gstride = (g.G + 31) / 32 * 32;
+    std::vector<double> xg((size_t)(ndir + 1) * gstride, 0.0);
+    for (int q = 0; q <= ndir; q++) for (int64_t i = 0; i < n; i++) xg[(size_t)(q * gstride + g.gidx_of_int[(size_t)i])] = x[(size_t)(q * stride + i)];
+    double max_err = 0.0, max_ref = 0.0;
+    int64_t checked = 0, seen_rows = 0;
+    std::vector<double> xs((size_t)cap);
+    std::vector<uint8_t> row_seen((size_t)n, 0);
+    for (int64_t b = 0; b < T.n_tiles; b++) {
+        int next_dir = 0;
+        for (int t = 0; t < 128; t++) {
+            const int32_t r = T.tile_row[(size_t)(b * 128 + t)];
+            if (r >= 0) {
+                if (row_seen[(size_t)r]) { printf("FAIL row %d in two tiles\n", r); return 1; }
+                row_seen[(size_t)r] = 1; seen_rows++;
+                if (T.tile_gidx[(size_t)(b * 128 + t)] != g.gidx_of_int[(size_t)r]) { printf("FAIL tile_gidx\n"); return 1; }
+            }
+        }
+        for (int pi = T.tile_pass[(size_t)b]; pi < T.tile_pass[(size_t)b + 1]; pi++) {
+            const auto& ps = T.passes[(size_t)pi];
+            if (ps.a0 != next_dir) { printf("FAIL pass table\n"); return 1; }
+            next_dir = ps.a1;
+            std::fill(xs.begin(), xs.end(), 1e300);      // poison: values outside the boxes must never be used
+            int64_t bytes = 0;
+            for (int bi = 0; bi < ps.n_box; bi++) {
+                const auto& bx = T.boxes[(size_t)(ps.box_begin + bi)];
+                const int32_t* bd = T.box_dims.data() + (size_t)bx.dir * 3;
+                if (bx.smem_off % 16 || bx.smem_off + (int64_t)bd[0] * bd[1] * bd[2] > cap || bx.dir < ps.a0 || bx.dir >= ps.a1) { printf("FAIL box placement\n"); return 1; }
+                for (int z = 0; z < bd[2]; z++) for (int y = 0; y < bd[1]; y++) for (int xx = 0; xx < bd[0]; xx++) {
+                    const int gx = bx.x + xx, gy = bx.y + y, gz = bx.z + z;
+                    double v = 0.0;
+                    if (gx >= 0 && gx < g.nxp && gy >= 0 && gy < g.n[1] && gz >= 0 && gz < g.n[2]) v = xg[(size_t)((bx.dir + 1) * gstride + g.flat(gx, gy, gz))];
+                    xs[(size_t)(bx.smem_off + (z * bd[1] + y) * bd[0] + xx)] = v;
+                }
+                bytes += (int64_t)bd[0] * bd[1] * bd[2] * 8;
+                if (bx.x & 1) { printf("FAIL odd box origin in x (TMA needs 16-byte aligned inner coordinates)\n"); return 1; }
+            }
+            if (bytes != ps.bytes) { printf("FAIL pass bytes %lld != %d\n", (long long)bytes, ps.bytes); return 1; }
+            for (int a = ps.a0; a < ps.a1; a++)
+                for (int t = 0; t < 128; t++) {
+                    const int32_t r = T.tile_row[(size_t)(b * 128 + t)];
+                    const uint32_t dx = (uint32_t)T.desc_x[(size_t)a * T.desc_stride + (size_t)(b * 128 + t)];
+                    if (r < 0) { if ((dx >> 16) != 63) { printf("FAIL idle thread descriptor\n"); return 1; } continue; }
+                    const auto& d = dirs[(size_t)a];
+                    double ref = 0.0, aref = 0.0;
+                    for (int64_t k = rowptr[(size_t)a][(size_t)r]; k < rowptr[(size_t)a][(size_t)r + 1]; k++) {
+                        const double tt = val[(size_t)a][(size_t)k] * x[(size_t)((int64_t)(a + 1) * stride + col[(size_t)a][(size_t)k])];
+                        ref += tt; aref += std::fabs(tt);
+                    }
+                    if (wall) for (int64_t k = wall_ptr[(size_t)a][(size_t)r]; k < wall_ptr[(size_t)a][(size_t)r + 1]; k++) {
+                        const double tt = wall_val[(size_t)a][(size_t)k] * x[(size_t)((int64_t)((a + 1) % ndir + 1) * stride + wall_col[(size_t)a][(size_t)k])];
+                        ref += tt; aref += std::fabs(tt);
+                    }
+                    double got = 0.0;
+                    const int ci = d.row_cls[(size_t)r];
+                    if (dx >> 31) {          // generic: dictionary list
+                        const auto& C = d.cls[(size_t)ci];
+                        const double* W = C.pats.data() + (size_t)d.row_pat[(size_t)r] * C.K;
+                        const int32_t* L = C.lists.data() + (size_t)d.row_lst[(size_t)r] * C.K;
+                        for (int k = 0; k < C.K; k++) got += W[k] * x[(size_t)L[k]];
+                    } else if ((dx >> 16) == 0) {
+                        if (ci != 0) { printf("FAIL box row of class %d\n", ci); return 1; }
+                        const auto& C = d.cls[0];
+                        const double* W = C.pats.data() + (size_t)T.desc_y[(size_t)a * T.desc_stride + (size_t)(b * 128 + t)] * C.K;
+                        for (int k = 0; k < C.K; k++) got += W[k] * xs[(size_t)((dx & 0xffffu) + T.off_table[(size_t)a * max_k + k])];
+                    } else if (ci >= 0) { printf("FAIL non-empty row with the empty descriptor\n"); return 1; }
+                    max_err = std::max(max_err, std::fabs(got - ref));
+                    max_ref = std::max(max_ref, aref);
+                    checked++;
+                }
+        }
+        if (next_dir != ndir) { printf("FAIL passes do not cover all directions\n"); return 1; }
+    }
+    if (seen_rows != n) { printf("FAIL %lld of %lld rows in tiles\n", (long long)seen_rows, (long long)n); return 1; }
+    if (!(max_err <= 1e-13 * max_ref)) { printf("FAIL max_err %g (scale %g)\n", max_err, max_ref); return 1; }
+    printf("OK rows=%lld checked=%lld tiles=%lld boxes=%lld passes=%zu box_rows=%lld generic=%lld max_pass=%lld err=%.2e\n", (long long)n, (long long)checked,
+           (long long)T.n_tiles, (long long)T.total_boxes, T.passes.size(), (long long)T.grid_rows, (long long)T.generic_rows, (long long)T.max_pass_doubles, max_err);
+    return 0;
+}

@@ -19,9 +19,23 @@ TOL_CONS = 1e-13      # conserved sums vs oracle
 # device formats of the streaming matrix: library default (dictionary, value tolerance 1e-14), bit-faithful
 # dictionary (tolerance 0) and the generic warp-sliced ELL
 # (format, value tolerance, cell-blocked internal DoF order)
+# a 4th element "grid": the host also gives the structure hint nb200_set_dof_grid -> TMA box kernels (NB_FMT_GRID)
 FORMATS = [None, ("dict", 1e-14, True), ("dict", 0.0, False), ("ell", 0.0, False), ("ell", 0.0, True),
-           ("dict-unstaged", 1e-14, False), ("dict-unstaged", 1e-14, True)]
-FORMAT_IDS = ["dict-default", "dict-cellorder", "dict-exact", "ell", "ell-cellorder", "dict-unstaged", "dict-unstaged-cellorder"]
+           ("dict-unstaged", 1e-14, False), ("dict-unstaged", 1e-14, True), ("dict", 1e-14, False, "grid"), ("dict", 0.0, True, "grid")]
+FORMAT_IDS = ["dict-default", "dict-cellorder", "dict-exact", "ell", "ell-cellorder", "dict-unstaged", "dict-unstaged-cellorder",
+              "grid", "grid-cellorder-exact"]
+
+
+def fake_grid_hint(ctx, n, dim=2):
+    """A grid hint for DoFs that sit on no mesh at all (random CSR inputs): any injective placement is valid input, the
+    rows then match no box template and the grid kernels take every row from its dictionary list."""
+    nx = int(np.ceil(n ** (1.0 / dim)))
+    i = np.arange(n)
+    if dim == 2:
+        coords, dims = np.stack([i % nx, i // nx], axis=1), [nx, (n + nx - 1) // nx]
+    else:
+        coords, dims = np.stack([i % nx, (i // nx) % nx, i // (nx * nx)], axis=1), [nx, nx, (n + nx * nx - 1) // (nx * nx)]
+    ctx.set_dof_grid(dims, coords, 0)
 
 
 def _fmt_code(name):
@@ -40,6 +54,8 @@ def make_ctx(case, with_matrix=True, fmt=None):
         ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
         if fmt[2]:
             ctx.set_dof_order(part.cell_blocked_order())
+        if len(fmt) > 3:
+            ctx.set_dof_grid(*part.grid_coords(), fe_order=pb.p)
     if with_matrix:
         harness.upload_streaming_matrix(ctx, pb, part, st, dt)
     return ctx, c, st, pb, dt, part
@@ -376,6 +392,8 @@ def test_ragged_and_offdiagonal_blocks(fmt, oracle_lib):
         ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
         if fmt[2]:
             ctx.set_dof_order(rng.permutation(n))
+        if len(fmt) > 3:
+            fake_grid_hint(ctx, n)
     for (bi, bj), m in blocks.items():
         ctx.upload_block_csr(bi, bj, m.indptr, m.indices, m.data)
     ctx.finalize_matrix()
@@ -930,14 +948,26 @@ def _walled_problem(oracle_lib, name, scaling, verts, boundary, p, cfl):
     return ost, mesh, dt, blocks, dofs
 
 
+def dofmap_grid_coords(dofs):
+    """(dims, coords) for nb200_set_dof_grid from the oracle's DofMap (lexicographic tensor grid, optional renumbering)."""
+    nd = list(dofs.nd)
+    i = np.arange(dofs.N)
+    lexc = np.stack([i % nd[0], i // nd[0]] if len(nd) == 2 else [i % nd[0], (i // nd[0]) % nd[1], i // (nd[0] * nd[1])], axis=1)
+    if dofs.numbering is None:
+        return nd, lexc
+    coords = np.empty_like(lexc)
+    coords[dofs.numbering] = lexc
+    return nd, coords
+
+
 def _upload_oracle_blocks(ctx, blocks):
     for (bi, bj), m in sorted(blocks.items()):
         ctx.upload_block_csr(bi, bj, m.indptr, m.indices, m.data)
     ctx.finalize_matrix()
 
 
-@pytest.mark.parametrize("fmt", [None, ("dict", 1e-14, True), ("dict-unstaged", 0.0, False), ("ell", 0.0, False)],
-                         ids=["dict-default", "dict-permuted", "dict-unstaged", "ell"])
+@pytest.mark.parametrize("fmt", [None, ("dict", 1e-14, True), ("dict-unstaged", 0.0, False), ("ell", 0.0, False), ("dict", 1e-14, False, "grid")],
+                         ids=["dict-default", "dict-permuted", "dict-unstaged", "ell", "grid"])
 def test_lid_driven_walled_stretched_2d(fmt, oracle_lib):
     """C4-like: D2Q9 on a y-stretched mesh with VelocityNeqBounceBack walls in y (moving lid) and periodic x.  The
     matrix (off-diagonal bounce blocks, SemiLagrangian.cpp:358-384) and the hit list (addHit, :381-383) come from the
@@ -964,6 +994,8 @@ def test_lid_driven_walled_stretched_2d(fmt, oracle_lib):
         ctx.set_matrix_format(_fmt_code(fmt[0]), fmt[1])
         if fmt[2]:
             ctx.set_dof_order(np.random.default_rng(9).permutation(n))
+        if len(fmt) > 3:
+            ctx.set_dof_grid(*dofmap_grid_coords(dofs), fe_order=p)
     _upload_oracle_blocks(ctx, blocks)
     ctx.set_wall_hits(idx, dirs, kinds, vals)
     nu = 0.05
@@ -1242,3 +1274,131 @@ def test_moving_walls_on_device(oracle_lib):
     assert np.max(np.abs(u[0] - 0.01)) < 1e-3 and np.max(np.abs(u[1])) < 1e-5
     assert abs(np.abs(rho).sum() / n - 1.0) < 1e-10
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# grid (TMA box) kernels, nb200_set_dof_grid
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["c1_tgv2d_d2q9", "tgv2d_small", "tgv3d_d3q19_small", "tgv3d_d3q19_p2", "tgv3d_d3q15", "tgv2d_d2q25", "tgv3d_d3q45"])
+@pytest.mark.parametrize("numbering", ["lex", "cell"])
+def test_grid_kernels_selected_and_rows_come_from_boxes(case, numbering):
+    """With the grid hint the TMA box kernels drive the step; on the periodic meshes of the path every row is a box row
+    (none falls back to its dictionary list), whatever the host numbering."""
+    from natrium_b200 import Context, harness
+    c, st, pb, dt = common.product_problem(case)
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
+    part = harness.SlabPartition(pb, st, dt)
+    ctx.set_layout(part.n_owned, part.n_ghost, bool(c.get("with_g")))
+    num = harness.CellNumbering(part) if numbering == "cell" else None
+    ctx.set_dof_grid(*(num or part).grid_coords(), fe_order=pb.p)
+    nnz = harness.upload_streaming_matrix(ctx, pb, part, st, dt, num)
+    info = ctx.grid_info()
+    assert info["in_use"] == 1, info
+    # every (row, direction) is either a box row or taken from its dictionary list; on these tiny periodic meshes the
+    # corner tiles would need up to 2^dim boxes per direction, beyond the buffer: those rows fall back, the others do not
+    assert info["box_rows"] + info["generic_rows"] == (st.getQ() - 1) * part.n_owned, info
+    assert info["box_rows"] >= 0.5 * (st.getQ() - 1) * part.n_owned, info
+    if case in ("c1_tgv2d_d2q9", "tgv2d_d2q25"):
+        assert info["generic_rows"] == 0, info
+    assert info["boxes"] >= info["tiles"] and info["passes"] >= info["tiles"]
+    # M 1 = 1 through the boxes (SemiLagrangian_test.cpp:519-596)
+    ones = np.ones((st.getQ(), part.n_owned))
+    ctx.upload_populations(0, ones)
+    ctx.stream(0)
+    assert np.max(np.abs(ctx.download_populations(0) - 1.0)) <= 1e-13
+    ctx.close()
+
+
+def test_grid_hint_errors():
+    from natrium_b200 import Context, Stencil, NatriumB200Error
+    st = Stencil("D2Q9", 1.0)
+    ctx = Context(0)
+    ctx.set_stencil(st.getDirections(), st.getWeights(), 1.0, st.getSpeedOfSoundSquare())
+    with pytest.raises(NatriumB200Error):
+        ctx.set_dof_grid([4, 4], np.zeros((16, 2)), 0)                      # before set_layout
+    ctx.set_layout(16, 0, False)
+    with pytest.raises(NatriumB200Error):
+        ctx.set_dof_grid([4, 4], np.zeros((16, 2)), 0)                      # two DoFs at one grid point
+    with pytest.raises(NatriumB200Error):
+        ctx.set_dof_grid([4, 4, 1], np.zeros((16, 3)), 0)                   # dimension differs from the stencil's
+    i = np.arange(16)
+    with pytest.raises(NatriumB200Error):
+        ctx.set_dof_grid([4, 3], np.stack([i % 4, i // 4], axis=1), 0)      # coordinate outside the grid
+    ctx.set_dof_grid([4, 4], np.stack([i % 4, i // 4], axis=1), 0)
+    with pytest.raises(NatriumB200Error):
+        ctx.set_dof_order(np.arange(16))                                    # the order hint comes first
+    ctx.close()
+
+
+@pytest.mark.parametrize("case,with_grid", [("tgv3d_d3q19_small", False), ("tgv3d_d3q19_small", True), ("tgv3d_d3q45", False), ("tgv3d_d3q45", True)])
+def test_conserved_moments_1000_steps_3d(case, with_grid, oracle_lib):
+    """north_star: conserved moments (mass, momentum, energy) agree with the reference-ordered CPU run to machine precision
+    over 1000 steps -- D3Q19 BGK and D3Q45 f+g (quartic, Pr 0.71, Sutherland), staged and grid kernels."""
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=("dict", 1e-14, False, "grid") if with_grid else None)
+    with_g = bool(c.get("with_g"))
+    set_collision(ctx, c, dt)
+    stepper = oracle_lib.ReferenceOrderStepper(o["st"], o["blocks"], o["dofs"].N, c["nu"], dt, equilibrium=1 if with_g else 0,
+                                               with_g=with_g, gamma=1.4, prandtl=0.71 if with_g else None, sutherland=with_g)
+    f = o["f"].copy()
+    g = o["g"].copy() if with_g else None
+    ctx.upload_populations(0, f)
+    if with_g:
+        ctx.upload_populations(1, g)
+    e, cs2 = o["st"].e, o["st"].cs2
+
+    def sums(fa, ga):
+        rho = fa.sum(axis=0)
+        m = e.T @ fa
+        if ga is None:
+            en = (0.5 * (m ** 2).sum(axis=0) / rho).sum()
+        else:      # 0.5 * (sum_i |e_i|^2 f_i / cs2 + sum_i g_i): kinetic + internal energy carried by f and g (nb200_conserved)
+            en = 0.5 * (((e ** 2).sum(axis=1) @ fa) / cs2 + ga.sum(axis=0)).sum()
+        return np.array([rho.sum(), m[0].sum(), m[1].sum(), m[2].sum(), en])
+
+    done = 0
+    for target in (1, 10, 100, 1000):
+        ctx.step(target - done)
+        for _ in range(target - done):
+            assert stepper.step(f, g) == 0
+        done = target
+        got, ref = ctx.conserved(), sums(f, g)
+        assert abs(got[0] - ref[0]) <= TOL_CONS * abs(ref[0]), (target, got, ref)
+        assert abs(got[4] - ref[4]) <= 1e-11 * abs(ref[4]), (target, got, ref)
+        scale = np.abs(e).max() * ref[0]
+        assert np.max(np.abs(got[1:4] - ref[1:4])) <= TOL_CONS * scale, (target, got, ref)
+        assert rel_err(ctx.download_populations(0), f) <= 1e-9, target
+    ctx.synchronize()
+    if with_grid:
+        assert ctx.grid_info()["in_use"] == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("case", ["c1_tgv2d_d2q9", "tgv3d_d3q19_small"])
+def test_grid_step_host_and_mixed_calls(case, oracle_lib):
+    """The grid copies follow every way the populations can change: uploads, stream-only, collide-only, fused steps and
+    host-buffer steps in any order give what the same calls give without the hint."""
+    o = common.oracle_problem(case)
+    res = []
+    for fmt in (None, ("dict", 1e-14, False, "grid")):
+        ctx, c, st, pb, dt, part = make_ctx(case, fmt=fmt)
+        set_collision(ctx, c, dt)
+        ctx.upload_populations(0, o["f"])
+        ctx.step(2)
+        ctx.stream(0)
+        ctx.collide()
+        ctx.step(1)
+        n, Q = part.n_owned, st.getQ()
+        fin, fout = np.ascontiguousarray(ctx.download_populations(0)), np.zeros((Q, n))
+        rho, u = np.zeros(n), np.zeros((st.getD(), n))
+        ctx.step_host(fin.ctypes.data, fout.ctypes.data, rho.ctypes.data, u.ctypes.data, 4)
+        ctx.synchronize()
+        ctx.step(2)
+        ctx.upload_population(0, 1, np.ascontiguousarray(fout[1]))
+        ctx.step(1)
+        ctx.synchronize()
+        res.append((ctx.download_populations(0), fout, rho))
+        ctx.close()
+    for a, b in zip(res[0], res[1]):
+        assert rel_err(b, a) <= 1e-12

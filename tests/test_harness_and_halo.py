@@ -155,6 +155,35 @@ def test_staging_tables_replay(tmp_path):
         assert out.startswith(expect), out
 
 
+def test_grid_tables_replay(tmp_path):
+    """Host-side builder of the grid (TMA box) driving tables (natrium_b200/csrc/grid_build.h): a CPU replay of the kernel's
+    access pattern -- boxes of the lexicographic grid copy (out-of-range points read 0, everything outside the boxes is
+    poisoned), rows from (offset + per-direction offset table), generic rows from their dictionary list -- equals the CSR
+    product for 2-d / 3-d periodic tensor grids, lexicographic and random DoF numbering, shuffled row entries, FE orders
+    1-4, and walls (off-diagonal entries and truncated rows must come out generic)."""
+    import subprocess
+    exe = str(tmp_path / "grid_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "grid_check.cpp")], check=True)
+    for args in ["3 3 3 3 4 0 1536 1", "3 3 2 4 4 1 1536 2", "2 5 4 0 4 1 1536 3", "3 4 3 3 2 1 1536 4", "3 2 3 2 3 1 1536 5",
+                 "2 4 4 0 2 0 1536 6 1", "3 3 3 2 4 1 1536 7 1", "3 2 2 2 1 0 1536 8", "3 6 5 4 4 1 1280 9", "2 9 7 0 4 1 1536 11"]:
+        out = subprocess.run([exe, *args.split()], check=True, capture_output=True, text=True).stdout
+        assert out.startswith("OK"), (args, out)
+    # the harness' own grid coordinates: one grid point per local DoF, cell faces at multiples of p, for every rank
+    from natrium_b200 import harness
+    from natrium_b200.stencils import Stencil
+    st = Stencil("D3Q19", 3.0)
+    pb = harness.CartesianProblem(3, [2, 2, 8], 4)
+    dt = pb.timestep(st, 0.4)
+    for r in range(4):
+        part = harness.SlabPartition(pb, st, dt, r, 4)
+        dims, coords = part.grid_coords()
+        assert coords.shape == (part.n_owned + part.n_ghost, 3) and (coords >= 0).all() and (coords < dims[None, :]).all()
+        assert len(np.unique(coords, axis=0)) == len(coords)
+        num = harness.CellNumbering(part)
+        d2, c2 = num.grid_coords()
+        assert np.array_equal(c2[:part.n_owned], coords[:part.n_owned][num.order]) and np.array_equal(c2[part.n_owned:], coords[part.n_owned:])
+
+
 def test_cell_numbering_renumbers_consistently():
     """harness.CellNumbering (host numbering = deal.II-like cell-wise order): P A P^T applied to P x equals P (A x),
     entry order inside a row (= summation order) is untouched, ghost columns keep their slots, the halo plan follows."""
