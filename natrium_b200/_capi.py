@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnatrium_b200.so")
+# NB200_LIB selects another build of the same library (tuning experiments: variants compiled with other -D flags)
+LIB_PATH = os.environ.get("NB200_LIB") or os.path.join(_HERE, "libnatrium_b200.so")
 
 NB200_OK = 0
 NB200_ERR_ARG = -1

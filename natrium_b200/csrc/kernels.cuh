@@ -253,7 +253,8 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
 // sits at (row offset + cGridOff[direction][k]).  Results are written to the canonical arrays and to the grid copy that
 // the next step's TMA reads.  Dynamic shared memory: [tile(s)][2 staging buffers (per distribution)].
 // ---------------------------------------------------------------------------------------------
-__constant__ int16_t cGridOff[NB_MAX_DIRS][NB_GRID_MAXK];
+// two 16-bit offsets per word: entries 2j (low half) and 2j+1 (high half) of a class-0 row of the direction
+__constant__ unsigned cGridOff[NB_MAX_DIRS][NB_GRID_MAXK / 2];
 
 #ifndef NB_GRID_OCC_F
 #define NB_GRID_OCC_F 5
@@ -271,6 +272,26 @@ __device__ __forceinline__ void nb_grid_issue(const StreamArgs& A, const NbGridP
     }
 }
 
+// A warp is done with staging buffer `buf` of pass p: the last of the CTA's warps to say so issues the copies of pass
+// p + 2 into it (nobody waits for anybody: fast warps run ahead into the other buffer).  cnt: per-buffer arrival counter.
+template <int NRHS>
+__device__ __forceinline__ void nb_grid_release(const StreamArgs& A, int p, int p1, int buf, int lane, int* cnt, double* xs0, double* xs1,
+                                                int cap, uint64_t* mbar)
+{
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();                      // this warp's reads of the buffer are done before the count says so
+        const int old = atomicAdd(&cnt[buf], 1);
+        if (old == NB_CTA_ROWS / 32 - 1) {
+            cnt[buf] = 0;
+            if (p + 2 < p1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy reads before the async-proxy writes
+                nb_grid_issue<NRHS>(A, A.gpass[p + 2], xs0 + buf * cap, xs1 + buf * cap, &mbar[buf]);
+            }
+        }
+    }
+}
+
 template <int D, int Q, int EQ>
 __global__ void __launch_bounds__(NB_CTA_ROWS, NB_GRID_OCC_F)
 k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __restrict__ y, double* __restrict__ ygrid,
@@ -278,6 +299,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
 {
     extern __shared__ __align__(128) double smem_grid[];
     __shared__ uint64_t mbar[2];
+    __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
     double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);    // [Q][128]
     double* xs = smem_grid + Q * NB_CTA_ROWS;                                               // [2][NB_GRID_CAP]
@@ -287,30 +309,33 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     const int32_t row = __ldg(A.tile_row + slot);
     const bool active = row >= 0;
     srow[tid] = row;
+    {   // the descriptors of all directions: each parks in the tile slot its result will overwrite
+        const int2* __restrict__ dp = A.sdesc + slot;
+#pragma unroll 1
+        for (int a = 0; a < Q - 1; a++, dp += A.gdesc_stride) nb_cp_async8(&tile[a + 1][tid], reinterpret_cast<const double*>(dp));
+    }
     tile[0][tid] = active ? x[row] : 0.0;
     if (tid == 0) {
         nb_mbar_init(&mbar[0], 1);
         nb_mbar_init(&mbar[1], 1);
+        cnt[0] = cnt[1] = 0;
         nb_mbar_fence_init();
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0 && p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0]);
+    if (tid == 0) {      // both buffers are free: the first two passes start right away
+        if (p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0]);
+        if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + NB_GRID_CAP, xs, &mbar[1]);
+    }
+    nb_cp_async_wait_all();
+    __syncthreads();          // descriptors of the partner rows are in place
+    const int half = tid >> 6, t0 = tid & 63;
+    const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
     for (int p = p0; p < p1; p++) {
         const int buf = (p - p0) & 1;
         const NbGridPass ps = A.gpass[p];
-        // the other buffer was last read in the previous iteration, which ended with a barrier
-        if (tid == 0 && p + 1 < p1) nb_grid_issue<1>(A, A.gpass[p + 1], xs + (buf ^ 1) * NB_GRID_CAP, xs, &mbar[buf ^ 1]);
-        {
-            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.gdesc_stride + slot;
-            for (int a = ps.a0; a < ps.a1; a++, dp += A.gdesc_stride) nb_cp_async8(&tile[a + 1][tid], reinterpret_cast<const double*>(dp));
-            nb_cp_async_wait_all();
-        }
         nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
-        __syncthreads();          // descriptors of the partner row are in place
         const double* __restrict__ xb = xs + buf * NB_GRID_CAP;
-        const int half = tid >> 6, t0 = tid & 63;
-        const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
 #pragma unroll 1
         for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
             const int2 d0 = reinterpret_cast<const int2*>(&tile[a + 1][t0])[0];
@@ -320,8 +345,9 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
             tile[a + 1][t0] = r[0];
             tile[a + 1][t0 + 64] = r[1];
         }
-        __syncthreads();          // rows are done with this buffer; results of a row come from the other half of the CTA
+        nb_grid_release<1>(A, p, p1, buf, tid & 31, cnt, xs, xs, NB_GRID_CAP, mbar);
     }
+    __syncthreads();          // results of a row come from the other half of the CTA
     if (!active) return;
     double f[Q];
 #pragma unroll
@@ -349,6 +375,7 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
 {
     extern __shared__ __align__(128) double smem_grid[];
     __shared__ uint64_t mbar[2];
+    __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
     double (*tf)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);
     double (*tg)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid + Q * NB_CTA_ROWS);
@@ -360,32 +387,35 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     const int32_t row = __ldg(A.tile_row + slot);
     const bool active = row >= 0;
     srow[tid] = row;
+    {
+        const int2* __restrict__ dp = A.sdesc + slot;
+#pragma unroll 1
+        for (int a = 0; a < Q - 1; a++, dp += A.gdesc_stride) nb_cp_async8(&tf[a + 1][tid], reinterpret_cast<const double*>(dp));
+    }
     tf[0][tid] = active ? xf[row] : 0.0;
     tg[0][tid] = active ? xg[row] : 0.0;
     if (tid == 0) {
         nb_mbar_init(&mbar[0], 1);
         nb_mbar_init(&mbar[1], 1);
+        cnt[0] = cnt[1] = 0;
         nb_mbar_fence_init();
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0 && p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0]);
+    if (tid == 0) {
+        if (p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0]);
+        if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FG, xsg + NB_GRID_CAP_FG, &mbar[1]);
+    }
+    nb_cp_async_wait_all();
+    __syncthreads();
+    const int half = tid >> 6, t0 = tid & 63;
+    const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
     for (int p = p0; p < p1; p++) {
         const int buf = (p - p0) & 1;
         const NbGridPass ps = A.gpass[p];
-        if (tid == 0 && p + 1 < p1)
-            nb_grid_issue<2>(A, A.gpass[p + 1], xsf + (buf ^ 1) * NB_GRID_CAP_FG, xsg + (buf ^ 1) * NB_GRID_CAP_FG, &mbar[buf ^ 1]);
-        {
-            const int2* __restrict__ dp = A.sdesc + (int64_t)ps.a0 * A.gdesc_stride + slot;
-            for (int a = ps.a0; a < ps.a1; a++, dp += A.gdesc_stride) nb_cp_async8(&tf[a + 1][tid], reinterpret_cast<const double*>(dp));
-            nb_cp_async_wait_all();
-        }
         nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
-        __syncthreads();
         const double* __restrict__ xbf = xsf + buf * NB_GRID_CAP_FG;
         const double* __restrict__ xbg = xsg + buf * NB_GRID_CAP_FG;
-        const int half = tid >> 6, t0 = tid & 63;
-        const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
 #pragma unroll 1
         for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
             const int2 d0 = reinterpret_cast<const int2*>(&tf[a + 1][t0])[0];
@@ -397,8 +427,9 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
             tg[a + 1][t0] = r[2];
             tg[a + 1][t0 + 64] = r[3];
         }
-        __syncthreads();
+        nb_grid_release<2>(A, p, p1, buf, tid & 31, cnt, xsf, xsg, NB_GRID_CAP_FG, mbar);
     }
+    __syncthreads();
     if (!active) return;
     double f[Q], g[Q];
 #pragma unroll
@@ -433,6 +464,7 @@ k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restr
 {
     extern __shared__ __align__(128) double smem_grid[];
     __shared__ uint64_t mbar[2];
+    __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
     constexpr int CAP = NRHS == 2 ? NB_GRID_CAP_FG : NB_GRID_CAP;
     double* xs0 = smem_grid;                         // [2][CAP]
@@ -449,17 +481,20 @@ k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restr
     if (tid == 0) {
         nb_mbar_init(&mbar[0], 1);
         nb_mbar_init(&mbar[1], 1);
+        cnt[0] = cnt[1] = 0;
         nb_mbar_fence_init();
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0 && p0 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0], xs0, xs1, &mbar[0]);
+    if (tid == 0) {
+        if (p0 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0], xs0, xs1, &mbar[0]);
+        if (p0 + 1 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0 + 1], xs0 + CAP, xs1 + CAP, &mbar[1]);
+    }
     const int half = tid >> 6, t0 = tid & 63;
     const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
     for (int p = p0; p < p1; p++) {
         const int buf = (p - p0) & 1;
         const NbGridPass ps = A.gpass[p];
-        if (tid == 0 && p + 1 < p1) nb_grid_issue<NRHS>(A, A.gpass[p + 1], xs0 + (buf ^ 1) * CAP, xs1 + (buf ^ 1) * CAP, &mbar[buf ^ 1]);
         nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
         const double* __restrict__ xb0 = xs0 + buf * CAP;
         const double* __restrict__ xb1 = xs1 + buf * CAP;
@@ -478,7 +513,7 @@ k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restr
                 if (NRHS == 2) y1[(int64_t)(a + 1) * A.stride + r1] = r[3];
             }
         }
-        __syncthreads();          // everybody is done with this buffer before the copy after next lands in it
+        nb_grid_release<NRHS>(A, p, p1, buf, tid & 31, cnt, xs0, xs1, CAP, mbar);
     }
 }
 

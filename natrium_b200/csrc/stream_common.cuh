@@ -487,26 +487,39 @@ __device__ __forceinline__ void nb_tma_load_3d(double* smem_dst, const void* tma
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// Offsets of a batch of entries: the table holds two 16-bit offsets per word (entries 2j, 2j+1), read from constant
+// memory up front with the weights (asm volatile keeps them at the head of the batch, so their latency overlaps the
+// weight loads' instead of sitting in front of every shared-memory load).
+__device__ __forceinline__ unsigned nb_ldc_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("{\n.reg .u64 t;\ncvta.to.const.u64 t, %1;\nld.const.u32 %0, [t];\n}" : "=r"(v) : "l"(p));
+    return v;
+}
+
 // Two class-0 rows with the same weight pattern: one weight load feeds both rows (and both distributions).
 // s0/s1: first support value of row 0 / row 1 in the f buffer, g0/g1 in the g buffer.  Summation order k = 0..K-1.
 template <int NRHS, bool STREAMED, int B2>
-__device__ __forceinline__ void nb_grid_batches_pair(const double2* __restrict__ W2, int K, int64_t P, const int16_t* __restrict__ off,
+__device__ __forceinline__ void nb_grid_batches_pair(const double2* __restrict__ W2, int K, int64_t P, const unsigned* __restrict__ off2,
                                                      const double* __restrict__ s0, const double* __restrict__ s1,
                                                      const double* __restrict__ g0, const double* __restrict__ g1, double (&acc)[4])
 {
     const int Kh = (K + 1) >> 1;
     for (int kk = 0; kk < Kh; kk += B2) {
         double2 vv[B2];
+        unsigned oo[B2];
 #pragma unroll
         for (int j = 0; j < B2; j++) {
             const int kj = min(kk + j, Kh - 1);
             vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
         }
 #pragma unroll
+        for (int j = 0; j < B2; j++) oo[j] = nb_ldc_u32(off2 + min(kk + j, Kh - 1));
+#pragma unroll
         for (int j = 0; j < B2; j++) {
             const int k = 2 * (kk + j);
             if (k < K) {
-                const int o = off[k];
+                const int o = (int)(oo[j] & 0xffffu);
                 acc[0] += vv[j].x * s0[o];
                 acc[1] += vv[j].x * s1[o];
                 if (NRHS == 2) {
@@ -515,7 +528,7 @@ __device__ __forceinline__ void nb_grid_batches_pair(const double2* __restrict__
                 }
             }
             if (k + 1 < K) {
-                const int o = off[k + 1];
+                const int o = (int)(oo[j] >> 16);
                 acc[0] += vv[j].y * s0[o];
                 acc[1] += vv[j].y * s1[o];
                 if (NRHS == 2) {
@@ -528,27 +541,30 @@ __device__ __forceinline__ void nb_grid_batches_pair(const double2* __restrict__
 }
 
 template <int NRHS, bool STREAMED, int B2>
-__device__ __forceinline__ void nb_grid_batches(const double2* __restrict__ W2, int K, int64_t P, const int16_t* __restrict__ off,
+__device__ __forceinline__ void nb_grid_batches(const double2* __restrict__ W2, int K, int64_t P, const unsigned* __restrict__ off2,
                                                 const double* __restrict__ s0, const double* __restrict__ g0, double& a0, double& a1)
 {
     const int Kh = (K + 1) >> 1;
     for (int kk = 0; kk < Kh; kk += B2) {
         double2 vv[B2];
+        unsigned oo[B2];
 #pragma unroll
         for (int j = 0; j < B2; j++) {
             const int kj = min(kk + j, Kh - 1);
             vv[j] = STREAMED ? nb_ld_stream2(W2 + (int64_t)kj * P) : nb_ld_keep2(W2 + (int64_t)kj * P);
         }
 #pragma unroll
+        for (int j = 0; j < B2; j++) oo[j] = nb_ldc_u32(off2 + min(kk + j, Kh - 1));
+#pragma unroll
         for (int j = 0; j < B2; j++) {
             const int k = 2 * (kk + j);
             if (k < K) {
-                const int o = off[k];
+                const int o = (int)(oo[j] & 0xffffu);
                 a0 += vv[j].x * s0[o];
                 if (NRHS == 2) a1 += vv[j].x * g0[o];
             }
             if (k + 1 < K) {
-                const int o = off[k + 1];
+                const int o = (int)(oo[j] >> 16);
                 a0 += vv[j].y * s0[o];
                 if (NRHS == 2) a1 += vv[j].y * g0[o];
             }
@@ -559,7 +575,7 @@ __device__ __forceinline__ void nb_grid_batches(const double2* __restrict__ W2, 
 // One row of direction a from its grid descriptor d: class 0 rows from the staged boxes, "generic" rows (bit 31) from
 // their dictionary list in global memory, rows of the K = 0 class give 0.
 template <int NRHS>
-__device__ __forceinline__ void nb_row_dot_grid(const StreamArgs& A, int a, int2 d, int32_t row, const int16_t* __restrict__ off,
+__device__ __forceinline__ void nb_row_dot_grid(const StreamArgs& A, int a, int2 d, int32_t row, const unsigned* __restrict__ off,
                                                 const double* __restrict__ xs0, const double* __restrict__ xs1,
                                                 const double* __restrict__ x0, const double* __restrict__ x1, double& y0, double& y1)
 {
@@ -587,7 +603,7 @@ __device__ __forceinline__ void nb_row_dot_grid(const StreamArgs& A, int a, int2
 // Rows r0 / r1 (descriptors d0 / d1) of direction a; y = { row0 f, row1 f, row0 g, row1 g }.
 template <int NRHS>
 __device__ __forceinline__ void nb_row_dot_grid_pair(const StreamArgs& A, int a, int2 d0, int2 d1, int32_t r0, int32_t r1,
-                                                     const int16_t* __restrict__ off, const double* __restrict__ xs0,
+                                                     const unsigned* __restrict__ off, const double* __restrict__ xs0,
                                                      const double* __restrict__ xs1, const double* __restrict__ x0,
                                                      const double* __restrict__ x1, double (&y)[4])
 {
