@@ -260,12 +260,14 @@ __constant__ unsigned cGridOff[NB_MAX_DIRS][NB_GRID_MAXK / 2];
 #define NB_GRID_OCC_F 5
 #endif
 
-// issues the TMA copies of pass ps into the staging buffer(s) and arms the barrier (one thread)
+// Issues the TMA copies of pass ps into the staging buffer(s) and arms the barrier.  Called by ALL lanes of one warp:
+// lane 0 arms the barrier with the pass's byte count, lane l fetches box l (l + 32, ...) and issues its copy, so the
+// table reads of the boxes are in flight together instead of one load latency per box.
 template <int NRHS>
-__device__ __forceinline__ void nb_grid_issue(const StreamArgs& A, const NbGridPass& ps, double* xs0, double* xs1, uint64_t* bar)
+__device__ __forceinline__ void nb_grid_issue(const StreamArgs& A, const NbGridPass& ps, double* xs0, double* xs1, uint64_t* bar, int lane)
 {
-    nb_mbar_expect_tx(bar, (unsigned)ps.bytes * NRHS);
-    for (int b = 0; b < ps.n_box; b++) {
+    if (lane == 0) nb_mbar_expect_tx(bar, (unsigned)ps.bytes * NRHS);
+    for (int b = lane; b < ps.n_box; b += 32) {
         const NbGridBox bx = A.gbox[ps.box_begin + b];
         nb_tma_load_3d(xs0 + bx.smem_off, reinterpret_cast<const char*>(A.tmap_f) + 128 * (int)bx.dir, bx.x, bx.y, bx.z, bar);
         if (NRHS == 2) nb_tma_load_3d(xs1 + bx.smem_off, reinterpret_cast<const char*>(A.tmap_g) + 128 * (int)bx.dir, bx.x, bx.y, bx.z, bar);
@@ -279,16 +281,19 @@ __device__ __forceinline__ void nb_grid_release(const StreamArgs& A, int p, int 
                                                 int cap, uint64_t* mbar)
 {
     __syncwarp();
+    int last = 0;
     if (lane == 0) {
         __threadfence_block();                      // this warp's reads of the buffer are done before the count says so
         const int old = atomicAdd(&cnt[buf], 1);
         if (old == NB_CTA_ROWS / 32 - 1) {
             cnt[buf] = 0;
-            if (p + 2 < p1) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy reads before the async-proxy writes
-                nb_grid_issue<NRHS>(A, A.gpass[p + 2], xs0 + buf * cap, xs1 + buf * cap, &mbar[buf]);
-            }
+            last = 1;
         }
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && p + 2 < p1) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy reads before the async-proxy writes
+        nb_grid_issue<NRHS>(A, A.gpass[p + 2], xs0 + buf * cap, xs1 + buf * cap, &mbar[buf], lane);
     }
 }
 
@@ -323,9 +328,9 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0) {      // both buffers are free: the first two passes start right away
-        if (p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0]);
-        if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + NB_GRID_CAP, xs, &mbar[1]);
+    if (tid < 32) {      // both buffers are free: the first two passes start right away (warp 0 issues the copies)
+        if (p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0], tid);
+        if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + NB_GRID_CAP, xs, &mbar[1], tid);
     }
     nb_cp_async_wait_all();
     __syncthreads();          // descriptors of the partner rows are in place
@@ -402,9 +407,9 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0) {
-        if (p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0]);
-        if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FG, xsg + NB_GRID_CAP_FG, &mbar[1]);
+    if (tid < 32) {
+        if (p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0], tid);
+        if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FG, xsg + NB_GRID_CAP_FG, &mbar[1], tid);
     }
     nb_cp_async_wait_all();
     __syncthreads();
@@ -486,9 +491,9 @@ k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restr
     }
     __syncthreads();
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
-    if (tid == 0) {
-        if (p0 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0], xs0, xs1, &mbar[0]);
-        if (p0 + 1 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0 + 1], xs0 + CAP, xs1 + CAP, &mbar[1]);
+    if (tid < 32) {
+        if (p0 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0], xs0, xs1, &mbar[0], tid);
+        if (p0 + 1 < p1) nb_grid_issue<NRHS>(A, A.gpass[p0 + 1], xs0 + CAP, xs1 + CAP, &mbar[1], tid);
     }
     const int half = tid >> 6, t0 = tid & 63;
     const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
