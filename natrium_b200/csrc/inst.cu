@@ -249,8 +249,8 @@ int collide(const NbLaunch& L)
 #if NB_WITH_G
 #define NB_LAUNCH_CG(EQ)                                                                                              \
     do {                                                                                                              \
-        if (L.force) k_collide_fg<D, Q, EQ, true><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);  \
-        else k_collide_fg<D, Q, EQ, false><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag);         \
+        if (L.force) k_collide_fg<D, Q, EQ, true><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag, L.gidx, L.ygf, L.ygg, L.A.gstride);  \
+        else k_collide_fg<D, Q, EQ, false><<<grid, 128, 0, L.stream>>>(n, L.A.stride, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.in_init, L.flag, L.gidx, L.ygf, L.ygg, L.A.gstride);         \
     } while (0)
         if (L.eq == NB_EQ_BGK) NB_LAUNCH_CG(NB_EQ_BGK);
         else NB_LAUNCH_CG(NB_EQ_QUARTIC);

@@ -553,33 +553,65 @@ k_collide_f(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __rest
     }
 }
 
-// Stand-alone collide (in place), f and g.
+// Stand-alone collide (in place), f and g.  gidx != null: the new populations also go into the grid copies (fgrid / ggrid,
+// pitch gstride) the TMA kernels read, so that no separate canonical -> grid copy is needed before the next stream.
+// Q > 25 takes the looping form (collide.cuh: nb_collide_fg_loops), which keeps no population array in registers.
 template <int D, int Q, int EQ, bool FORCE>
 __global__ void __launch_bounds__(128)
-k_collide_fg(int64_t n, int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf,
+k_collide_fg(int64_t n, int64_t stride, double* fbuf, double* gbuf,
              double* __restrict__ rho_out, double* __restrict__ u_out, double* __restrict__ T_out,
-             double* __restrict__ s_out, int in_init, int* __restrict__ flag)
+             double* __restrict__ s_out, int in_init, int* __restrict__ flag,
+             const int32_t* __restrict__ gidx, double* __restrict__ fgrid, double* __restrict__ ggrid, int64_t gstride)
 {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    double f[Q], g[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        f[q] = fbuf[(int64_t)q * stride + row];
-        g[q] = gbuf[(int64_t)q * stride + row];
+    __shared__ double ctab[Q > 25 ? Q * NB_CT_PITCH : 1];
+    if constexpr (Q > 25) {
+        nb_ct_fill<D, Q>(ctab, threadIdx.x, blockDim.x);
+        __syncthreads();
     }
+    if (row >= n) return;
     double rho, u[3], uo[3], T, sensor, vf[3] = {0.0, 0.0, 0.0};
     if (in_init) {
 #pragma unroll
         for (int j = 0; j < D; j++) uo[j] = u_out[(int64_t)j * n + row];
     }
-    nb_collide_bgk_fg<D, Q, EQ, FORCE>(f, g, rho, u, T, sensor, in_init ? uo : nullptr, vf);
-    if (rho < 1e-10) *flag = 1;
+    const int64_t gi = gidx ? (int64_t)gidx[row] : 0;
+    if constexpr (Q > 25) {
+        double* fp = fbuf + row;
+        double* gp = gbuf + row;
+        auto ldf = [&](int i) { return fp[(int64_t)i * stride]; };
+        auto ldg = [&](int i) { return gp[(int64_t)i * stride]; };
+        auto st = [&](int i, double fv, double gv) {
+            fp[(int64_t)i * stride] = fv;
+            gp[(int64_t)i * stride] = gv;
+            if (gidx && !(FORCE && cP.force_type == 2)) fgrid[(int64_t)i * gstride + gi] = fv;
+            if (gidx) ggrid[(int64_t)i * gstride + gi] = gv;
+        };
+        auto stf = [&](int i, double df) {
+            const double fv = fp[(int64_t)i * stride] + df;
+            fp[(int64_t)i * stride] = fv;
+            if (gidx) fgrid[(int64_t)i * gstride + gi] = fv;
+        };
+        nb_collide_fg_loops<D, Q, EQ, FORCE>(ctab, ldf, ldg, st, stf, rho, u, T, sensor, in_init ? uo : nullptr, vf);
+    } else {
+        double f[Q], g[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-        fbuf[(int64_t)q * stride + row] = f[q];
-        gbuf[(int64_t)q * stride + row] = g[q];
+        for (int q = 0; q < Q; q++) {
+            f[q] = fbuf[(int64_t)q * stride + row];
+            g[q] = gbuf[(int64_t)q * stride + row];
+        }
+        nb_collide_bgk_fg<D, Q, EQ, FORCE>(f, g, rho, u, T, sensor, in_init ? uo : nullptr, vf);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            fbuf[(int64_t)q * stride + row] = f[q];
+            gbuf[(int64_t)q * stride + row] = g[q];
+            if (gidx) {
+                fgrid[(int64_t)q * gstride + gi] = f[q];
+                ggrid[(int64_t)q * gstride + gi] = g[q];
+            }
+        }
     }
+    if (rho < 1e-10) *flag = 1;
     rho_out[row] = rho;
     T_out[row] = T;
     s_out[row] = sensor;

@@ -35,6 +35,7 @@ struct NbLaunch {
     // grid kernels (NB_FMT_GRID): grid copies the fused kernel writes next to yf / yg, and the host copy of the
     // per-direction offset table [(Q-1)][NB_GRID_MAXK] (uploaded into the unit's constant memory with the constants)
     double* ygf; double* ygg;
+    const int32_t* gidx;    // collide with grid dual write: canonical row -> flat grid index (null = canonical only)
     const int16_t* grid_off; int grid_off_dirs;
     int n_rhs;              // stream_grid: 1 = the distribution in xf/yf, 2 = f and g in one pass
 };

@@ -1792,10 +1792,14 @@ static int dispatch_collide(nb200_ctx* c)
     NbLaunch L = make_launch(c);
     L.yf = c->pop[0][c->cur[0]];
     if (c->cp.with_g) L.yg = c->pop[1][c->cur[1]];
+    // f + g with the grid hint: the collide kernel writes the grid copies as well (no canonical -> grid pass before the
+    // next stream); the ghost positions of the copies are stale until the next exchange, which rewrites them
+    const bool dual = c->cp.with_g && use_grid(c) && c->nranks == 1;
+    if (dual) { L.gidx = c->d_gidx_of_int; L.ygf = c->gpop[0][c->cur[0]]; L.ygg = c->gpop[1][c->cur[1]]; }
     int rc = cuda_rc(c, c->ops->collide(L), "collide");
     if (rc) return rc;
-    c->grid_valid[0] = false;
-    if (c->cp.with_g) c->grid_valid[1] = false;
+    c->grid_valid[0] = dual;
+    if (c->cp.with_g) c->grid_valid[1] = dual;
     c->launches++;
     return NB200_OK;
 }
