@@ -247,6 +247,12 @@ int nb200_apply_post_collision(nb200_ctx *ctx);
  * wall hits, f+g or a non-staged matrix format run the same legs in sequence.  Results are identical either way. */
 int nb200_step_host(nb200_ctx *ctx, const double *f_in, double *f_out, double *rho, double *u, int64_t n, int n_chunks);
 
+/* The same for the compressible solver's two distributions (CompressibleCFDSolver::stream / gStream / collide,
+ * L/solver/CompressibleCFDSolver.h:181-314): f_in, g_in [Q][n] -> device, one step, f_out, g_out [Q][n], rho [n], u [D][n],
+ * T [n] -> host (rho / u / T may be NULL).  The legs run in sequence on the context stream. */
+int nb200_step_host_fg(nb200_ctx *ctx, const double *f_in, const double *g_in, double *f_out, double *g_out, double *rho,
+                       double *u, double *T, int64_t n);
+
 /* ---- results ----------------------------------------------------------------------------- */
 
 /* rho [n], u [D][n] (scaled, as written to m_velocity), T [n], sensor [n]; any pointer may be NULL. */

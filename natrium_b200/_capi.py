@@ -83,6 +83,7 @@ SIGNATURES = {
     "nb200_collide": (C.c_int, [_vp]),
     "nb200_step": (C.c_int, [_vp, C.c_int]),
     "nb200_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int]),
+    "nb200_step_host_fg": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64]),
     "nb200_download_moments": (C.c_int, [_vp, _dp, _dp, _dp, _dp, C.c_int64]),
     "nb200_conserved": (C.c_int, [_vp, _dp]),
     "nb200_synchronize": (C.c_int, [_vp]),
@@ -314,6 +315,9 @@ class Context:
     def step_host(self, f_in_ptr, f_out_ptr, rho_ptr, u_ptr, n_chunks=16):
         """One step with host buffers given as raw addresses (page-locked for true overlap); fence with synchronize()."""
         self._check(self.lib.nb200_step_host(self._h, f_in_ptr, f_out_ptr, rho_ptr, u_ptr, self.n_owned, n_chunks))
+
+    def step_host_fg(self, f_in_ptr, g_in_ptr, f_out_ptr, g_out_ptr, rho_ptr, u_ptr, T_ptr):
+        self._check(self.lib.nb200_step_host_fg(self._h, f_in_ptr, g_in_ptr, f_out_ptr, g_out_ptr, rho_ptr, u_ptr, T_ptr, self.n_owned))
 
     def synchronize(self):
         self._check(self.lib.nb200_synchronize(self._h))

@@ -164,7 +164,7 @@ int fused(const NbLaunch& L)
         k_stream_collide_fg<D, Q, EQ, FMT><<<grid, 128, smem_fg, L.stream>>>(L.A, L.xf, L.xg, L.yf, L.yg, L.rho, L.u, L.T, L.sensor, L.flag); \
     } while (0)
         if (L.fmt == NB_FMT_GRID) {
-            const size_t smem_gr = (size_t)(2 * Q * NB_CTA_ROWS + 4 * NB_GRID_CAP_FG) * sizeof(double);
+            const size_t smem_gr = (size_t)(2 * Q * NB_CTA_ROWS + 4 * NB_GRID_CAP_FGF) * sizeof(double);
 #define NB_LAUNCH_FGGR(EQ)                                                                                                  \
     do {                                                                                                                   \
         static unsigned attr_mask = 0;                                                                                     \
@@ -205,7 +205,7 @@ int stream_grid(const NbLaunch& L)
     if (grid == 0) return 0;
     if (L.n_rhs == 2) {
 #if NB_WITH_G
-        const size_t sm = (size_t)4 * NB_GRID_CAP_FG * sizeof(double);
+        const size_t sm = (size_t)4 * NB_GRID_CAP_OF(Q, 2) * sizeof(double);
         static unsigned attr_mask = 0;
         int e = set_smem(k_stream_grid<D, Q, 2>, sm, &attr_mask);
         if (e) return e;
@@ -277,7 +277,7 @@ int wall(const NbLaunch& L)
     if (rc) return rc;
     if (L.n_hit_groups <= 0) return 0;
     k_wall_hits<D, Q><<<grid_for(L.n_hit_groups, 64), 64, 0, L.stream>>>(L.n_hit_groups, L.hit_group_dof, L.hit_group_off, L.hit_dir,
-                                                                         L.hit_kind, L.hit_val, L.A.stride, L.yf, L.yg);
+                                                                         L.hit_kind, L.hit_val, L.A.stride, L.yf, L.yg, L.gidx, L.ygg, L.A.gstride);
     return (int)cudaGetLastError();
 }
 

@@ -259,6 +259,9 @@ __constant__ unsigned cGridOff[NB_MAX_DIRS][NB_GRID_MAXK / 2];
 #ifndef NB_GRID_OCC_F
 #define NB_GRID_OCC_F 5
 #endif
+#ifndef NB_GRID_OCC_FG
+#define NB_GRID_OCC_FG 3
+#endif
 
 // Issues the TMA copies of pass ps into the staging buffer(s) and arms the barrier.  Called by ALL lanes of one warp:
 // lane 0 arms the barrier with the pass's byte count, lane l fetches box l (l + 32, ...) and issues its copy, so the
@@ -372,7 +375,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
 
 // f + g: both distributions staged by the same boxes; [tile f][tile g][2 buffers f][2 buffers g]
 template <int D, int Q, int EQ>
-__global__ void __launch_bounds__(NB_CTA_ROWS, NB_FUSED_OCC_FG)
+__global__ void __launch_bounds__(NB_CTA_ROWS, NB_GRID_OCC_FG)
 k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const double* __restrict__ xg,
                          double* __restrict__ yf, double* __restrict__ yg, double* __restrict__ yfgrid, double* __restrict__ yggrid,
                          double* __restrict__ rho_out, double* __restrict__ u_out, double* __restrict__ T_out,
@@ -382,10 +385,12 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     __shared__ uint64_t mbar[2];
     __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
+    __shared__ double ctab[Q * NB_CT_PITCH];
+    nb_ct_fill<D, Q>(ctab, threadIdx.x, NB_CTA_ROWS);       // visible after the barriers below
     double (*tf)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);
     double (*tg)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid + Q * NB_CTA_ROWS);
-    double* xsf = smem_grid + 2 * Q * NB_CTA_ROWS;       // [2][NB_GRID_CAP_FG]
-    double* xsg = xsf + 2 * NB_GRID_CAP_FG;
+    double* xsf = smem_grid + 2 * Q * NB_CTA_ROWS;       // [2][NB_GRID_CAP_FGF]
+    double* xsg = xsf + 2 * NB_GRID_CAP_FGF;
     const int tid = threadIdx.x;
     const int64_t tl = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
     const int64_t slot = tl * NB_CTA_ROWS + tid;
@@ -409,7 +414,7 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
     if (tid < 32) {
         if (p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0], tid);
-        if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FG, xsg + NB_GRID_CAP_FG, &mbar[1], tid);
+        if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FGF, xsg + NB_GRID_CAP_FGF, &mbar[1], tid);
     }
     nb_cp_async_wait_all();
     __syncthreads();
@@ -419,8 +424,8 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
         const int buf = (p - p0) & 1;
         const NbGridPass ps = A.gpass[p];
         nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
-        const double* __restrict__ xbf = xsf + buf * NB_GRID_CAP_FG;
-        const double* __restrict__ xbg = xsg + buf * NB_GRID_CAP_FG;
+        const double* __restrict__ xbf = xsf + buf * NB_GRID_CAP_FGF;
+        const double* __restrict__ xbg = xsg + buf * NB_GRID_CAP_FGF;
 #pragma unroll 1
         for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
             const int2 d0 = reinterpret_cast<const int2*>(&tf[a + 1][t0])[0];
@@ -432,27 +437,24 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
             tg[a + 1][t0] = r[2];
             tg[a + 1][t0 + 64] = r[3];
         }
-        nb_grid_release<2>(A, p, p1, buf, tid & 31, cnt, xsf, xsg, NB_GRID_CAP_FG, mbar);
+        nb_grid_release<2>(A, p, p1, buf, tid & 31, cnt, xsf, xsg, NB_GRID_CAP_FGF, mbar);
     }
     __syncthreads();
     if (!active) return;
-    double f[Q], g[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        f[q] = tf[q][tid];
-        g[q] = tg[q][tid];
-    }
+    // collision straight from the tiles (collide.cuh: nb_collide_fg_loops): no population arrays in registers
     double rho, u[3], T, sensor;
-    nb_collide_bgk_fg<D, Q, EQ>(f, g, rho, u, T, sensor, nullptr);
-    if (rho < 1e-10) *flag = 1;
     const int64_t gi = __ldg(A.tile_gidx + slot);
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        yf[(int64_t)q * A.stride + row] = f[q];
-        yg[(int64_t)q * A.stride + row] = g[q];
-        yfgrid[(int64_t)q * A.gstride + gi] = f[q];
-        yggrid[(int64_t)q * A.gstride + gi] = g[q];
-    }
+    auto ldf = [&](int i) { return tf[i][tid]; };
+    auto ldg = [&](int i) { return tg[i][tid]; };
+    auto st = [&](int i, double fv, double gv) {
+        yf[(int64_t)i * A.stride + row] = fv;
+        yg[(int64_t)i * A.stride + row] = gv;
+        yfgrid[(int64_t)i * A.gstride + gi] = fv;
+        yggrid[(int64_t)i * A.gstride + gi] = gv;
+    };
+    auto stf = [&](int, double) {};
+    nb_collide_fg_loops<D, Q, EQ, false>(ctab, ldf, ldg, st, stf, rho, u, T, sensor, nullptr, nullptr);
+    if (rho < 1e-10) *flag = 1;
     rho_out[row] = rho;
     T_out[row] = T;
     s_out[row] = sensor;
@@ -471,7 +473,7 @@ k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restr
     __shared__ uint64_t mbar[2];
     __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
-    constexpr int CAP = NRHS == 2 ? NB_GRID_CAP_FG : NB_GRID_CAP;
+    constexpr int CAP = NB_GRID_CAP_OF(Q, NRHS);
     double* xs0 = smem_grid;                         // [2][CAP]
     double* xs1 = smem_grid + (NRHS == 2 ? 2 * CAP : 0);
     const int tid = threadIdx.x;
@@ -638,7 +640,8 @@ template <int D, int Q>
 __global__ void __launch_bounds__(64)
 k_wall_hits(int64_t n_groups, const int32_t* __restrict__ group_dof, const int64_t* __restrict__ group_off,
             const int32_t* __restrict__ hit_dir, const int32_t* __restrict__ hit_kind, const double* __restrict__ hit_val,
-            int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf)
+            int64_t stride, double* __restrict__ fbuf, double* __restrict__ gbuf,
+            const int32_t* __restrict__ gidx, double* __restrict__ ggrid, int64_t gstride)
 {
     const int64_t grp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (grp >= n_groups) return;
@@ -685,6 +688,7 @@ k_wall_hits(int64_t n_groups, const int32_t* __restrict__ group_dof, const int64
                 for (int i = 0; i < Q; i++) {
                     fbuf[(int64_t)i * stride + idx] = fd[i] + feq[i];
                     gbuf[(int64_t)i * stride + idx] = feq[i] * gfac;
+                    if (gidx) ggrid[(int64_t)i * gstride + gidx[idx]] = feq[i] * gfac;
                 }
             }
         }

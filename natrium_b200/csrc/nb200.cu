@@ -1028,7 +1028,7 @@ static int finalize_dict(nb200_ctx* c)
     if (c->grid_hint && n > 0) {
         static const char* envg = getenv("NB200_GRID");       // experiments only: NB200_GRID=0 keeps the staged dictionary kernels
         if (!(envg && envg[0] == '0')) {
-            c->grid_cap = c->with_g ? NB_GRID_CAP_FG : NB_GRID_CAP;
+            c->grid_cap = NB_GRID_CAP_OF(c->Q, c->with_g ? 2 : 1);
             grid_ok = nbgrid::build(c->dirs, c->grid, n, c->stride, NB_CTA_ROWS, c->grid_cap, NB_GRID_MAXK, NB_MAX_CLS - 1, GT);
         }
     }
@@ -1477,9 +1477,17 @@ extern "C" int nb200_set_wall_hits(nb200_ctx* c, int64_t n_hits, const int32_t* 
     c->d_hit_group_dof = c->d_hit_dir = c->d_hit_kind = nullptr; c->d_hit_group_off = nullptr; c->d_hit_val = nullptr;
     c->n_hits = n_hits; c->n_hit_groups = 0; c->hits_thermal = thermal;
     if (n_hits == 0) return NB200_OK;
+    // A VelocityNeqBounceBack hit adds value = 2 w rho (e . u_wall) / cs2 to one population; at a wall at rest that is + 0.0,
+    // which leaves the population as it is.  Such hits are not kept: a problem whose walls all rest (Riemann2D, lid-less
+    // cavities) then has no hit kernel between streaming and collision and runs the fused step.
+    std::vector<int64_t> ord;
+    ord.reserve((size_t)n_hits);
+    for (int64_t h = 0; h < n_hits; h++)
+        if (!(kind[h] == NB200_WALL_VELOCITY_NEQ_BOUNCE_BACK && value[h] == 0.0)) ord.push_back(h);
+    n_hits = (int64_t)ord.size();
+    c->n_hits = n_hits;
+    if (n_hits == 0) return NB200_OK;
     // group by destination DoF (internal numbering), keeping the list order inside a group
-    std::vector<int64_t> ord((size_t)n_hits);
-    for (int64_t h = 0; h < n_hits; h++) ord[(size_t)h] = h;
     auto dof_of = [&](int64_t h) { return c->has_order ? c->perm[(size_t)dest_index[h]] : dest_index[h]; };
     std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return dof_of(a) < dof_of(b); });
     std::vector<int32_t> gdof, hdir((size_t)n_hits), hkind((size_t)n_hits);
@@ -1832,9 +1840,13 @@ static int dispatch_wall(nb200_ctx* c)
     NbLaunch L = make_launch(c);
     L.yf = c->pop[0][c->cur[0]];
     L.yg = c->with_g ? c->pop[1][c->cur[1]] : nullptr;
+    // thermal hits rewrite g at wall DoFs: a grid copy of g that is in sync follows (the next kernel, the stream of g, reads it)
+    const bool dual_g = c->hits_thermal && c->with_g && use_grid(c) && c->grid_valid[1];
+    if (dual_g) { L.gidx = c->d_gidx_of_int; L.ygg = c->gpop[1][c->cur[1]]; }
     int rc = cuda_rc(c, c->ops->wall(L), "wall hits");
     if (rc) return rc;
-    c->grid_valid[0] = c->grid_valid[1] = false;
+    c->grid_valid[0] = false;
+    if (c->hits_thermal && !dual_g) c->grid_valid[1] = false;
     c->launches++;
     return NB200_OK;
 }
@@ -2195,6 +2207,27 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     c->grid_valid[0] = false;
     CUDA_TRY(c, cudaGetLastError());
     return NB200_OK;
+}
+
+// The same call for the compressible solver (CompressibleCFDSolver::stream / gStream / collide, CompressibleCFDSolver.h:181-314):
+// f and g in, f, g, rho, u, T out.  Legs in sequence on the context stream (uploads, step, downloads).
+extern "C" int nb200_step_host_fg(nb200_ctx* c, const double* f_in, const double* g_in, double* f_out, double* g_out, double* rho,
+                                  double* u, double* T, int64_t n)
+{
+    int rc = ready(c, true, true);
+    if (rc) return rc;
+    if (!f_in || !g_in || !f_out || !g_out || n != c->n_owned) return fail(c, NB200_ERR_ARG, "step_host_fg: bad argument");
+    if (!c->with_g || !c->cp.with_g) return fail(c, NB200_ERR_ARG, "step_host_fg: the layout / collision has no g distribution");
+    if (c->cp.in_init) return fail(c, NB200_ERR_ARG, "step_host_fg: in_init collisions are only available through nb200_collide");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    rc = copy_all(c, 0, const_cast<double*>(f_in), n, true, false);
+    if (!rc) rc = copy_all(c, 1, const_cast<double*>(g_in), n, true, false);
+    if (!rc) rc = nb200_step(c, 1);
+    if (!rc) rc = copy_all(c, 0, f_out, n, false, false);
+    if (!rc && c->has_order) CUDA_TRY(c, cudaStreamSynchronize(c->stream));     // the permuted path shares one staging buffer
+    if (!rc) rc = copy_all(c, 1, g_out, n, false, false);
+    if (!rc && (rho || u || T)) rc = nb200_download_moments(c, rho, u, T, nullptr, n);
+    return rc;
 }
 
 // ---- results -------------------------------------------------------------------------------------

@@ -42,8 +42,13 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2, NB_FMT_GRID = 3 };
 #define NB_GRID_CAP 1536
 #endif
 #ifndef NB_GRID_CAP_FG
-#define NB_GRID_CAP_FG 1280
+#define NB_GRID_CAP_FG 1280        // f + g, large stencils (D3Q45: a 3-d box of 14 x 9 x 9 values per distribution)
 #endif
+#ifndef NB_GRID_CAP_FGF
+#define NB_GRID_CAP_FGF 512        // f + g, stencils that run the fused kernel (Q <= 25, D2Q25H: small 2-d boxes)
+#endif
+// capacity of one staging buffer per distribution for a stencil with Q directions and n_rhs distributions
+#define NB_GRID_CAP_OF(Q, n_rhs) ((n_rhs) == 2 ? ((Q) <= 25 ? NB_GRID_CAP_FGF : NB_GRID_CAP_FG) : NB_GRID_CAP)
 #define NB_GRID_MAXK 128
 
 #define NB_CLS_BITS 6

@@ -281,9 +281,8 @@ class SlabPartition:
 # ------------------------------------------------------------------------------------------
 # streaming matrix
 # ------------------------------------------------------------------------------------------
-def assemble_direction(problem, part, stencil, dt, alpha):
-    """Local CSR (rowptr int64, col int32, val f64) of block (alpha-1, alpha-1): rows = owned DoFs
-    of ``part`` in local order, columns in local numbering (owned, then ghosts)."""
+def _dense_direction(problem, part, stencil, dt, alpha):
+    """(col, val) of shape (owned rows, k): the periodic tensor-product row of every owned DoF, entries in (z, y, x) order."""
     e = stencil.getDirection(alpha)
     dim = problem.dim
     tr = [problem.axes[d].track(float(-dt * e[d])) for d in range(dim)]
@@ -307,12 +306,157 @@ def assemble_direction(problem, part, stencil, dt, alpha):
     rows = int(np.prod(col.shape[:dim]))
     col = np.ascontiguousarray(np.broadcast_to(col, val.shape).reshape(rows, k))
     val = np.ascontiguousarray(val.reshape(rows, k))
+    return col, val
+
+
+def _csr_from_pieces(n_rows, pieces):
+    """CSR (rowptr int64, col int32, val f64) from pieces (rows ascending and unique over all pieces, col (m, K), val (m, K));
+    entries below the reference's 1e-10 drop threshold are left out (SemiLagrangian.cpp:483)."""
+    lens = np.zeros(n_rows, dtype=np.int64)
+    oks = []
+    for rr, c, v in pieces:
+        ok = np.abs(v) >= 1e-10
+        lens[rr] = ok.sum(axis=1)
+        oks.append(ok)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    oc = np.empty(rp[-1], dtype=np.int32)
+    ov = np.empty(rp[-1])
+    for (rr, c, v), ok in zip(pieces, oks):
+        if len(rr) == 0:
+            continue
+        k = ok.sum(axis=1)
+        pos = np.repeat(rp[rr], k) + (np.arange(int(k.sum())) - np.repeat(np.cumsum(k) - k, k))
+        oc[pos] = c[ok]
+        ov[pos] = v[ok]
+    return rp, oc, ov
+
+
+def assemble_direction(problem, part, stencil, dt, alpha):
+    """Local CSR (rowptr int64, col int32, val f64) of block (alpha-1, alpha-1): rows = owned DoFs
+    of ``part`` in local order, columns in local numbering (owned, then ghosts)."""
+    col, val = _dense_direction(problem, part, stencil, dt, alpha)
+    rows, k = val.shape
     keep = np.abs(val) >= 1e-10
     if keep.all():
         rowptr = np.arange(rows + 1, dtype=np.int64) * k
         return rowptr, col.reshape(-1).astype(np.int32), val.reshape(-1)
     rowptr = np.concatenate([[0], np.cumsum(keep.sum(axis=1))]).astype(np.int64)
     return rowptr, col[keep].astype(np.int32), val[keep]
+
+
+def opposite_directions(stencil):
+    e = stencil.getDirections()
+    return np.array([int(np.argmin(np.abs(e + e[i]).sum(1))) for i in range(len(e))])
+
+
+def assemble_direction_walled(problem, part, stencil, dt, alpha, walls, opposite=None):
+    """Direction ``alpha`` on a mesh whose axes with ``walls[d]`` end in bounce-back walls (VelocityNeqBounceBack /
+    ThermalBounceBack; the other axes are periodic): what fillSparseObject does when a path reaches such a wall
+    (L/advection/SemiLagrangian.cpp:358-384) -- the direction is reversed and the rest of the path runs back from the hit
+    point.  Along the line x + t (-dt e_alpha) the walls bound t to [t_lo, t_hi] (t_lo <= 0 <= t_hi); a path of length 1
+    folds at t_hi (first bounce: the row reads population opposite(alpha) at t = 2 t_hi - 1 and lands in the off-diagonal
+    block) and, in a corner, once more at t_lo (second bounce: population alpha again, t = 2 t_lo - 2 t_hi + 1); one
+    BoundaryHit per bounce.  Vectorised: the bounced rows are grouped by their distinct end points t (a handful: only
+    the DoFs of the wall layer bounce), each group is a tensor product of 1-d tracks like the regular rows.
+    Returns ({(bi, bj): (rowptr, col, val)}, hit_rows): local CSR blocks over the owned rows of ``part`` and the local
+    index of the destination row of every hit (a twice-bounced row appears twice); the hit direction is alpha."""
+    opposite = opposite_directions(stencil) if opposite is None else opposite
+    e = stencil.getDirection(alpha)
+    dim = problem.dim
+    delta = [float(-dt * e[d]) for d in range(dim)]
+    own = part.owned_planes
+    idx = [np.arange(problem.nd[d]) for d in range(dim - 1)] + [own]
+    shape = tuple(len(i) for i in idx[::-1])                         # (z, y, x) / (y, x): last axis slowest
+    t_hi = np.full(shape, np.inf)
+    t_lo = np.full(shape, -np.inf)
+    for d in range(dim):
+        if not walls[d] or delta[d] == 0.0:
+            continue
+        ax = problem.axes[d]
+        xs = ax.x[idx[d]]
+        lo, hi = ax.v[0], ax.v[-1]
+        fwd, bwd = (lo, hi) if delta[d] < 0 else (hi, lo)           # wall met moving along +delta / -delta
+        th = (fwd - xs) / delta[d]
+        tl = (bwd - xs) / delta[d]
+        th = np.where(np.abs(th) < 1e-14, 0.0, th)
+        tl = np.where(np.abs(tl) < 1e-14, 0.0, tl)
+        sh = [1] * dim
+        sh[dim - 1 - d] = len(xs)
+        t_hi = np.minimum(t_hi, th.reshape(sh))
+        t_lo = np.maximum(t_lo, tl.reshape(sh))
+    t_hi, t_lo = np.broadcast_to(t_hi, shape).reshape(-1), np.broadcast_to(t_lo, shape).reshape(-1)
+    n_rows = int(np.prod(shape))
+    # crossing: the end point t = 1 lies beyond the wall by more than the reference's snap tolerance (1e-10 of a cell)
+    tol = 1e-10
+    one = t_hi < 1.0 - tol
+    t1 = np.where(one, 2.0 * t_hi - 1.0, 1.0)
+    two = one & (t1 < t_lo - tol)
+    t_end = np.where(two, 2.0 * t_lo - 2.0 * t_hi + 1.0, t1)
+    # a DoF in a corner whose path leaves through one wall and whose reflection leaves through the other never gets
+    # anywhere: the reference's tracker gives up after 50 rounds and puts 1.0 on the diagonal (SemiLagrangian.cpp:252-268)
+    stuck = one & (t_hi - t_lo < tol)
+    assert not (two & ~stuck & (t_end > t_hi + tol)).any(), "third wall hit"
+    one_sp = one & ~stuck
+    dense_c, dense_v = _dense_direction(problem, part, stencil, dt, alpha)
+    diag = [(np.nonzero(~one)[0], dense_c[~one], dense_v[~one])]
+    if stuck.any():
+        rs = np.nonzero(stuck)[0]
+        diag.append((rs, rs[:, None].astype(np.int64), np.ones((len(rs), 1))))
+    off = []
+    special = np.nonzero(one_sp)[0]
+    coords = np.unravel_index(special, shape)[::-1]               # per axis (x, y[, z]) positions into idx[d]
+    t_sp = t_end[special]
+    for t in np.unique(t_sp):
+        sel = t_sp == t
+        rr = special[sel]
+        tr = [problem.axes[d].track(delta[d] * t) for d in range(dim)]
+        gl = [idx[d][coords[d][sel]] for d in range(dim)]            # global 1-d DoF index per axis
+        zc, zw = tr[-1][0][gl[-1]], tr[-1][1][gl[-1]]
+        zbase = part.base[zc]
+        if (zbase < 0).any():
+            raise RuntimeError("reflected departure point outside owned + ghost planes")
+        xc, xw = tr[0][0][gl[0]], tr[0][1][gl[0]]
+        if dim == 2:
+            c = zbase[:, :, None] + xc[:, None, :]
+            v = zw[:, :, None] * xw[:, None, :]
+        else:
+            yc, yw = tr[1][0][gl[1]], tr[1][1][gl[1]]
+            ndx = problem.nd[0]
+            c = zbase[:, :, None, None] + yc[:, None, :, None] * ndx + xc[:, None, None, :]
+            v = (xw[:, None, None, :] * yw[:, None, :, None]) * zw[:, :, None, None]
+        m = len(rr)
+        c = np.broadcast_to(c, v.shape).reshape(m, -1)
+        v = v.reshape(m, -1)
+        tw = two[rr]
+        if tw.any():
+            diag.append((rr[tw], c[tw], v[tw]))
+        if (~tw).any():
+            off.append((rr[~tw], c[~tw], v[~tw]))
+    blocks = {(alpha - 1, alpha - 1): _csr_from_pieces(n_rows, diag)}
+    if off:
+        blocks[(alpha - 1, int(opposite[alpha]) - 1)] = _csr_from_pieces(n_rows, off)
+    hit_rows = np.sort(np.concatenate([np.nonzero(one)[0], np.nonzero(two & ~stuck)[0]]))
+    return blocks, hit_rows
+
+
+def upload_streaming_matrix_walled(ctx, problem, part, stencil, dt, walls, numbering=None):
+    """upload_streaming_matrix for a mesh with bounce-back walls.  Returns (nnz, hit_index, hit_direction): the hit list
+    in the caller's numbering (one hit per bounced path), for nb200_set_wall_hits."""
+    nnz = 0
+    hi, hd = [], []
+    opp = opposite_directions(stencil)
+    for alpha in range(1, stencil.getQ()):
+        blocks, rows_hit = assemble_direction_walled(problem, part, stencil, dt, alpha, walls, opp)
+        for (bi, bj), (rowptr, col, val) in blocks.items():
+            if numbering is not None:
+                rowptr, col, val = numbering.renumber_csr(rowptr, col, val)
+            ctx.upload_block_csr(bi, bj, rowptr, col, val)
+            nnz += len(val)
+        idx = rows_hit if numbering is None else numbering.perm[rows_hit]
+        hi.append(np.asarray(idx, dtype=np.int32))
+        hd.append(np.full(len(rows_hit), alpha, dtype=np.int32))
+    ctx.finalize_matrix()
+    return nnz, np.concatenate(hi), np.concatenate(hd)
 
 
 class CellNumbering:

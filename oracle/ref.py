@@ -132,3 +132,20 @@ def thermal_wall_point(scaling, wall_temperature, f, g):
     """One destination DoF of ThermalBounceBack<3>::calculateBoundaryValues (call sequence restated in ref_driver.cpp,
     arithmetic from the reference's headers).  f, g: (45,) arrays, modified in place; returns True if re-equilibrated."""
     return bool(lib().ref_thermal_wall_point(C.c_double(scaling), C.c_double(wall_temperature), _d(f), _d(g)))
+
+
+def select_collision_range(name, scaling, f, a, b, viscosity, dt, rho_scratch, u_scratch, scheme="BGK_STANDARD",
+                           equilibrium="BGK_EQUILIBRIUM"):
+    """selectCollision(f) on the DoF range [a, b) of f (Q, stride), in place: what one MPI rank of the reference does on its
+    owned DoFs.  rho_scratch (b-a), u_scratch (D, b-a): per-rank outputs.  Thread-safe (ctypes releases the GIL); returns
+    the status code.  Used by bench.py's CPU baseline."""
+    Q, stride = f.shape
+    n = b - a
+    fv = np.zeros(3)
+    err = C.create_string_buffer(256)
+    base = f.ctypes.data + 8 * a
+    return lib().ref_select_collision(
+        name.encode(), C.c_double(scaling), C.c_int(SCHEMES[scheme]), C.c_int(EQUILIBRIA[equilibrium]), C.c_int(0), C.c_int(0), _d(fv),
+        C.c_int(0), C.c_int(0), C.c_double(viscosity), C.c_double(dt), C.c_int(0), C.c_int(0), C.c_double(1.4), C.c_int(0),
+        C.c_double(1.0), C.c_int(0), C.c_int64(n), C.c_int64(stride), C.cast(base, _dp), None, _d(rho_scratch), _d(u_scratch),
+        None, None, err, C.c_int(256))

@@ -184,6 +184,43 @@ def test_grid_tables_replay(tmp_path):
         assert np.array_equal(c2[:part.n_owned], coords[:part.n_owned][num.order]) and np.array_equal(c2[part.n_owned:], coords[part.n_owned:])
 
 
+@pytest.mark.parametrize("name,scaling,boundary,p,cfl,stretch", [
+    ("D2Q9", 3.0, ["periodic", "wall"], 3, 0.8, True), ("D2Q25H", 1.0, ["wall", "wall"], 2, 1.0, False),
+    ("D3Q45", 1.0, ["periodic", "wall", "periodic"], 2, 0.4, True), ("D3Q19", 2.0, ["periodic", "wall", "periodic"], 3, 0.4, True),
+    ("D2Q9", 2.0, ["wall", "wall"], 4, 0.4, True)])
+def test_walled_assembly_equals_oracle(name, scaling, boundary, p, cfl, stretch):
+    """harness.assemble_direction_walled (vectorised input generator for the walled bench configurations: Riemann 2D with
+    walls all around, the channel with walls in y) against the oracle's restatement of fillSparseObject with bounce-back
+    walls (path reversal at the wall, off-diagonal blocks, double bounce and stuck paths in corners, one hit per bounce)."""
+    import scipy.sparse as sp
+    from oracle import assembly, cpu
+    from natrium_b200 import harness
+    from natrium_b200.stencils import Stencil
+    ost, st = cpu.Stencil(name, scaling), Stencil(name, scaling)
+    opp = harness.opposite_directions(st)
+    dim = len(boundary)
+    y = np.linspace(0, 1, 4)
+    ys = y - 0.8 * np.sin(2 * np.pi * y) / (2 * np.pi) if stretch else np.linspace(0, 2, 5)
+    verts = [np.linspace(0, 1, 3) if stretch else np.linspace(0, 2, 5), ys] + ([np.linspace(0, 1, 4)] if dim == 3 else [])
+    mesh = assembly.CartesianMesh(verts, boundary=boundary)
+    dt = assembly.calculate_timestep(mesh, p, ost.max_speed, cfl)
+    blocks, dofs = assembly.assemble_semilagrangian(mesh, p, ost.e, dt, opposite=opp)
+    pb = harness.CartesianProblem(dim, [len(v) - 1 for v in verts], p, verts=verts)
+    assert pb.timestep(st, cfl) == dt
+    part = harness.SlabPartition(pb, st, dt)
+    mine, hits = {}, set()
+    for a in range(1, st.getQ()):
+        bl, rh = harness.assemble_direction_walled(pb, part, st, dt, a, [b == "wall" for b in boundary], opp)
+        for k, (rp, c, v) in bl.items():
+            m = sp.csr_matrix((v, c, rp), shape=(part.n_owned, part.n_owned))
+            if m.nnz:
+                mine[k] = m
+        hits |= {(int(r), a) for r in rh}
+    assert set(mine) == set(blocks)
+    assert max(abs(mine[k] - blocks[k]).max() for k in blocks) <= 1e-14
+    assert hits == {(h["index"], h["direction"]) for h in dofs.hits}
+
+
 def test_cell_numbering_renumbers_consistently():
     """harness.CellNumbering (host numbering = deal.II-like cell-wise order): P A P^T applied to P x equals P (A x),
     entry order inside a row (= summation order) is untouched, ghost columns keep their slots, the halo plan follows."""
