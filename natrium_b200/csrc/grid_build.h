@@ -206,45 +206,65 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
         const int K = C0.K;
         if (K > max_k) return false;
         const int64_t lo = (int64_t)(a + 1) * stride, hi = lo + stride;      // columns of population a + 1 only
-        bool have = false;
         std::vector<int>& tp = tmpl[(size_t)a];
-        // lists are shared by many rows: classify each list once
-        std::vector<int32_t> list_origin((size_t)C0.n_lists(), -2);
-        for (int64_t r = 0; r < n_owned; r++) {
-            if (d.row_cls[(size_t)r] != 0) continue;
-            const int32_t li = d.row_lst[(size_t)r];
-            int32_t& lo_ = list_origin[(size_t)li];
-            if (lo_ == -2) {
-                lo_ = -1;
-                const int32_t* L = C0.lists.data() + (size_t)li * K;
-                bool ok = true;
-                int c0[3];
-                for (int k = 0; k < K && ok; k++) {
-                    if (L[k] < lo || L[k] >= hi) { ok = false; break; }
-                    const int64_t gi = g.gidx_of_int[(size_t)(L[k] - lo)];
-                    if (gi < 0) { ok = false; break; }
-                    int c[3];
-                    g.unflat(gi, c);
-                    if (k == 0) { c0[0] = c[0]; c0[1] = c[1]; c0[2] = c[2]; }
-                    const int rel[3] = {c[0] - c0[0], c[1] - c0[1], c[2] - c0[2]};
-                    if (!have) {
-                        tp.push_back(rel[0]); tp.push_back(rel[1]); tp.push_back(rel[2]);
-                    } else if (tp[(size_t)k * 3] != rel[0] || tp[(size_t)k * 3 + 1] != rel[1] || tp[(size_t)k * 3 + 2] != rel[2]) {
-                        ok = false;
-                    }
+        // relative grid coordinates of the K entries of every class-0 list; the template of the direction is the pattern
+        // most lists have (a first-come choice could pick an oddity, e.g. a list that straddles a periodic seam)
+        const int64_t nl = C0.n_lists();
+        std::vector<int16_t> rel((size_t)nl * K * 3, 0);
+        std::vector<uint8_t> lok((size_t)nl, 0), lused((size_t)nl, 0);
+        for (int64_t r = 0; r < n_owned; r++) if (d.row_cls[(size_t)r] == 0) lused[(size_t)d.row_lst[(size_t)r]] = 1;
+        std::vector<uint64_t> lhash((size_t)nl, 0);
+        for (int64_t li = 0; li < nl; li++) {
+            if (!lused[(size_t)li]) continue;
+            const int32_t* L = C0.lists.data() + (size_t)li * K;
+            bool ok = true;
+            int c0[3] = {0, 0, 0};
+            uint64_t hsh = 0x9e3779b97f4a7c15ull;
+            for (int k = 0; k < K && ok; k++) {
+                if (L[k] < lo || L[k] >= hi) { ok = false; break; }
+                const int64_t gi = g.gidx_of_int[(size_t)(L[k] - lo)];
+                if (gi < 0) { ok = false; break; }
+                int c[3];
+                g.unflat(gi, c);
+                if (k == 0) { c0[0] = c[0]; c0[1] = c[1]; c0[2] = c[2]; }
+                for (int j = 0; j < 3; j++) {
+                    const int rj = c[j] - c0[j];
+                    if (rj < 0 || rj > 64) ok = false;
+                    rel[((size_t)li * K + k) * 3 + j] = (int16_t)rj;
+                    hsh = nbdict::mix64(hsh, (uint64_t)(rj + 1));
                 }
-                if (!have) {
-                    // the first full row defines the template; it must be a box that starts at its first entry
-                    if (ok) {
-                        for (int k = 0; k < K && ok; k++)
-                            for (int j = 0; j < 3; j++) if (tp[(size_t)k * 3 + j] < 0 || tp[(size_t)k * 3 + j] > 64) ok = false;
-                    }
-                    if (ok) have = true; else tp.clear();
-                }
-                if (ok) lo_ = (int32_t)g.gidx_of_int[(size_t)(L[0] - lo)];
             }
-            origin[(size_t)a][(size_t)r] = lo_;
+            lok[(size_t)li] = ok ? 1 : 0;
+            lhash[(size_t)li] = hsh;
         }
+        // majority pattern
+        int64_t best = -1;
+        {
+            std::vector<std::pair<uint64_t, int64_t>> hs;
+            for (int64_t li = 0; li < nl; li++) if (lok[(size_t)li]) hs.emplace_back(lhash[(size_t)li], li);
+            std::sort(hs.begin(), hs.end());
+            int64_t best_cnt = 0;
+            for (size_t i0 = 0; i0 < hs.size();) {
+                size_t i1 = i0;
+                while (i1 < hs.size() && hs[i1].first == hs[i0].first) i1++;
+                if ((int64_t)(i1 - i0) > best_cnt) { best_cnt = (int64_t)(i1 - i0); best = hs[i0].second; }
+                i0 = i1;
+            }
+        }
+        const bool have = best >= 0;
+        if (have) {
+            tp.resize((size_t)K * 3);
+            for (int k = 0; k < K * 3; k++) tp[(size_t)k] = rel[(size_t)best * K * 3 + k];
+        }
+        std::vector<int32_t> list_origin((size_t)nl, -1);
+        for (int64_t li = 0; li < nl && have; li++) {
+            if (!lok[(size_t)li]) continue;
+            bool same = true;
+            for (int k = 0; k < K * 3 && same; k++) same = rel[(size_t)li * K * 3 + k] == rel[(size_t)best * K * 3 + k];
+            if (same) list_origin[(size_t)li] = (int32_t)g.gidx_of_int[(size_t)(C0.lists[(size_t)li * K] - lo)];
+        }
+        for (int64_t r = 0; r < n_owned; r++)
+            if (d.row_cls[(size_t)r] == 0) origin[(size_t)a][(size_t)r] = list_origin[(size_t)d.row_lst[(size_t)r]];
         if (have)
             for (int k = 0; k < K; k++)
                 for (int j = 0; j < 3; j++) ext[(size_t)a * 3 + j] = std::max(ext[(size_t)a * 3 + j], tp[(size_t)k * 3 + j] + 1);

@@ -6,15 +6,97 @@
 // rows marked generic from their dictionary list.  Compares with the plain CSR product.
 // Usage: grid_check <dim> <cells_x> <cells_y> <cells_z> <p> <numbering 0=lex 1=random> <cap> <seed> [wall]
 //        wall = 1 adds a few off-diagonal (bounce-back like) entries and truncated rows, which must come out generic.
+//        grid_check file <path> <cap>: the problem comes from a dump (tests/test_harness_and_halo.py: any rank of a partitioned
+//        harness problem, ghost slots included): int64 header {dim, p, n_owned, n_ghost, ndir, dims[3]}, int32 coords[nloc][dim],
+//        then per direction int64 nnz, int64 rowptr[n_owned + 1], int32 col[nnz], double val[nnz].
 #include <cstdio>
 #include <cstdlib>
 #include <array>
 #include <numeric>
 #include <random>
+#include <string>
+#include <cmath>
 #include "../../natrium_b200/csrc/grid_build.h"
+
+struct Problem {
+    int dim = 3, p = 4, ndir = 0, wall = 0;
+    int64_t n = 0, nloc = 0, stride = 0;          // rows (owned), owned + ghost, population pitch
+    nbgrid::Grid g;
+    std::vector<double> x;
+    std::vector<nbdict::DirBuild> dirs;
+    std::vector<std::vector<int64_t>> rowptr, wall_ptr;
+    std::vector<std::vector<int32_t>> col, wall_col;
+    std::vector<std::vector<double>> val, wall_val;
+};
+
+static bool add_direction(Problem& P, int a)
+{
+    // what nb200_upload_block_csr does: sort by grid position, then the dictionary
+    std::vector<int32_t> sc;
+    std::vector<double> sv;
+    const int32_t* cp = P.col[(size_t)a].data();
+    const double* vp = P.val[(size_t)a].data();
+    if (nbgrid::sort_rows_by_grid(P.g.gidx_of_int, P.n, P.rowptr[(size_t)a].data(), cp, vp, sc, sv)) { cp = sc.data(); vp = sv.data(); }
+    const char* msg = "";
+    if (!nbdict::add_block(P.dirs[(size_t)a], P.n, P.rowptr[(size_t)a].data(), cp, vp, (int64_t)(a + 1) * P.stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block %s\n", msg); return false; }
+    if (P.wall) {
+        const int b = (a + 1) % P.ndir;
+        if (!nbdict::add_block(P.dirs[(size_t)a], P.n, P.wall_ptr[(size_t)a].data(), P.wall_col[(size_t)a].data(), P.wall_val[(size_t)a].data(),
+                               (int64_t)(b + 1) * P.stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block wall %s\n", msg); return false; }
+    }
+    return true;
+}
+
+static bool load_file(const char* path, Problem& P)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    int64_t h[8];
+    if (fread(h, 8, 8, f) != 8) return false;
+    P.dim = (int)h[0]; P.p = (int)h[1]; P.n = h[2]; P.nloc = h[2] + h[3]; P.ndir = (int)h[4];
+    P.stride = ((P.nloc + 31) / 32) * 32;
+    nbgrid::Grid& g = P.g;
+    g.dim = P.dim; g.fe_order = P.p;
+    for (int j = 0; j < 3; j++) g.n[j] = j < P.dim ? (int32_t)h[5 + j] : 1;
+    g.nxp = (g.n[0] + 1) & ~1;
+    g.G = g.nxp * g.n[1] * g.n[2];
+    std::vector<int32_t> coords((size_t)P.nloc * P.dim);
+    if (fread(coords.data(), 4, coords.size(), f) != coords.size()) return false;
+    g.gidx_of_int.assign((size_t)P.nloc, -1);
+    for (int64_t u = 0; u < P.nloc; u++) {
+        int c[3] = {0, 0, 0};
+        for (int j = 0; j < P.dim; j++) c[j] = coords[(size_t)(u * P.dim + j)];
+        g.gidx_of_int[(size_t)u] = (int32_t)g.flat(c[0], c[1], c[2]);
+    }
+    P.dirs.resize((size_t)P.ndir); P.rowptr.resize((size_t)P.ndir); P.col.resize((size_t)P.ndir); P.val.resize((size_t)P.ndir);
+    P.wall_ptr.resize((size_t)P.ndir); P.wall_col.resize((size_t)P.ndir); P.wall_val.resize((size_t)P.ndir);
+    for (int a = 0; a < P.ndir; a++) {
+        int64_t nnz;
+        if (fread(&nnz, 8, 1, f) != 1) return false;
+        P.rowptr[(size_t)a].resize((size_t)P.n + 1); P.col[(size_t)a].resize((size_t)nnz); P.val[(size_t)a].resize((size_t)nnz);
+        if (fread(P.rowptr[(size_t)a].data(), 8, (size_t)P.n + 1, f) != (size_t)P.n + 1) return false;
+        if (fread(P.col[(size_t)a].data(), 4, (size_t)nnz, f) != (size_t)nnz) return false;
+        if (fread(P.val[(size_t)a].data(), 8, (size_t)nnz, f) != (size_t)nnz) return false;
+        P.dirs[(size_t)a].init(P.n);
+        if (!add_direction(P, a)) return false;
+    }
+    fclose(f);
+    std::mt19937_64 rng(7);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    P.x.resize((size_t)(P.ndir + 1) * P.stride);
+    for (auto& v : P.x) v = U(rng);
+    return true;
+}
+
+static int check(Problem& P, int cap);
 
 int main(int argc, char** argv)
 {
+    if (argc > 3 && std::string(argv[1]) == "file") {
+        Problem P;
+        if (!load_file(argv[2], P)) { printf("FAIL cannot read %s\n", argv[2]); return 1; }
+        return check(P, atoi(argv[3]));
+    }
     const int dim = argc > 1 ? atoi(argv[1]) : 3;
     int nc[3] = {argc > 2 ? atoi(argv[2]) : 3, argc > 3 ? atoi(argv[3]) : 3, argc > 4 ? atoi(argv[4]) : 3};
     const int p = argc > 5 ? atoi(argv[5]) : 4;
@@ -114,13 +196,30 @@ int main(int argc, char** argv)
                                    (int64_t)(b + 1) * stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block wall %s\n", msg); return 1; }
         }
     }
+    Problem P;
+    P.dim = dim; P.p = p; P.ndir = ndir; P.wall = wall; P.n = n; P.nloc = n; P.stride = stride; P.g = g;
+    P.x.swap(x); P.dirs.swap(dirs); P.rowptr.swap(rowptr); P.col.swap(col); P.val.swap(val);
+    P.wall_ptr.swap(wall_ptr); P.wall_col.swap(wall_col); P.wall_val.swap(wall_val);
+    return check(P, cap);
+}
+
+static int check(Problem& P, int cap)
+{
+    const int64_t n = P.n, stride = P.stride;
+    const int ndir = P.ndir, wall = P.wall;
+    nbgrid::Grid& g = P.g;
+    std::vector<double>& x = P.x;
+    std::vector<nbdict::DirBuild>& dirs = P.dirs;
+    auto &rowptr = P.rowptr, &wall_ptr = P.wall_ptr;
+    auto &col = P.col, &wall_col = P.wall_col;
+    auto &val = P.val, &wall_val = P.wall_val;
     nbgrid::Tables T;
     const int max_k = 128;
     if (!nbgrid::build(dirs, g, n, stride, 128, cap, max_k, 63, T)) { printf("INFEASIBLE\n"); return 0; }
     // grid copy of x
     const int64_t gstride = (g.G + 31) / 32 * 32;
     std::vector<double> xg((size_t)(ndir + 1) * gstride, 0.0);
-    for (int q = 0; q <= ndir; q++) for (int64_t i = 0; i < n; i++) xg[(size_t)(q * gstride + g.gidx_of_int[(size_t)i])] = x[(size_t)(q * stride + i)];
+    for (int q = 0; q <= ndir; q++) for (int64_t i = 0; i < P.nloc; i++) xg[(size_t)(q * gstride + g.gidx_of_int[(size_t)i])] = x[(size_t)(q * stride + i)];
     double max_err = 0.0, max_ref = 0.0;
     int64_t checked = 0, seen_rows = 0;
     std::vector<double> xs((size_t)cap);

@@ -184,6 +184,50 @@ def test_grid_tables_replay(tmp_path):
         assert np.array_equal(c2[:part.n_owned], coords[:part.n_owned][num.order]) and np.array_equal(c2[part.n_owned:], coords[part.n_owned:])
 
 
+def _dump_rank_problem(path, name, scaling, dim, cells, p, cfl, rank, world, cell_numbering, partition=None):
+    """One rank of a partitioned harness problem in the file format of tests/cpp/grid_check.cpp (file mode)."""
+    from natrium_b200 import harness
+    st = Stencil(name, scaling)
+    pb = harness.CartesianProblem(dim, cells, p)
+    dt = pb.timestep(st, cfl)
+    part = (partition or harness.SlabPartition)(pb, st, dt, rank, world)
+    num = harness.CellNumbering(part) if cell_numbering else None
+    dims, coords = (num if cell_numbering else part).grid_coords()
+    with open(path, "wb") as f:
+        f.write(np.array([dim, p, part.n_owned, part.n_ghost, st.getQ() - 1] + list(dims) + [1] * (3 - dim), dtype=np.int64).tobytes())
+        f.write(np.ascontiguousarray(coords, dtype=np.int32).tobytes())
+        for a in range(1, st.getQ()):
+            rp, col, val = harness.assemble_direction(pb, part, st, dt, a)
+            if num is not None:
+                rp, col, val = num.renumber_csr(rp, col, val)
+            f.write(np.array([len(val)], dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(rp, dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(col, dtype=np.int32).tobytes())
+            f.write(np.ascontiguousarray(val, dtype=np.float64).tobytes())
+    return part
+
+
+def test_grid_tables_replay_partitioned(tmp_path):
+    """The grid builder on the ranks of partitioned problems (ghost slots in the grid, rows whose lists straddle the periodic
+    seam or the ghost layer): the tables must be feasible on every rank (the multi-GPU bench runs the TMA box kernels), replay
+    to the CSR product, and leave only a thin layer of rows to the dictionary lists.  Regression: rank 0 of a 2-slab p = 4
+    mesh used to pick a seam-straddling list as the direction's template and gave up."""
+    import subprocess
+    exe = str(tmp_path / "grid_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "grid_check.cpp")], check=True)
+    cases = [("D3Q19", math.sqrt(3) / 0.05, 3, [4, 2, 4], 4, 0.4, 2, 1536), ("D3Q19", math.sqrt(3) / 0.05, 3, [3, 3, 6], 2, 0.4, 3, 1536),
+             ("D2Q25H", 1.0, 2, [5, 6], 2, 1.0, 2, 1536), ("D3Q45", 1.0, 3, [2, 2, 4], 2, 0.4, 2, 1280)]
+    for name, sc, dim, cells, p, cfl, world, cap in cases:
+        for r in range(world):
+            for cn in (True, False):
+                path = str(tmp_path / "case.bin")
+                _dump_rank_problem(path, name, sc, dim, cells, p, cfl, r, world, cn)
+                out = subprocess.run([exe, "file", path, str(cap)], check=True, capture_output=True, text=True).stdout
+                assert out.startswith("OK"), (name, cells, r, world, cn, out)
+                kv = dict(t.split("=") for t in out.split()[1:])
+                assert int(kv["box_rows"]) >= 0.85 * int(kv["checked"]), out
+
+
 @pytest.mark.parametrize("name,scaling,boundary,p,cfl,stretch", [
     ("D2Q9", 3.0, ["periodic", "wall"], 3, 0.8, True), ("D2Q25H", 1.0, ["wall", "wall"], 2, 1.0, False),
     ("D3Q45", 1.0, ["periodic", "wall", "periodic"], 2, 0.4, True), ("D3Q19", 2.0, ["periodic", "wall", "periodic"], 3, 0.4, True),
