@@ -587,6 +587,10 @@ def multirank_parity(args, rank, world, local, uid):
     c = case_spec("c2", args)
     cells = [4, 4, 2 * world]
     L = [2 * math.pi, 2 * math.pi, 2 * math.pi]
+    from natrium_b200 import Context
+    box = [Context.unique_id() if rank == 0 else None]          # a communicator of its own: an NCCL id is good for one
+    dist.broadcast_object_list(box, src=0)
+    uid = box[0]
     B = build_product(c, cells, L, local=local, rank=rank, world=world, uid=uid, grid=args.grid, fmt=args.format, tol=args.dedup_tol,
                       numbering=args.numbering, dof_order=args.dof_order)
     ctx = B["ctx"]

@@ -681,6 +681,34 @@ void orc_apply_stabilizer(int Q, int64_t n, int64_t stride, double *f, const dou
     }
 }
 
+/* ExponentialFilter<dim>::applyFilter, smoothing/ExponentialFilter.cpp:139-199 (called once per population by
+ * CFDSolver::filter, solver/CFDSolver.cpp:859-874).  Cells are visited one after the other in the given order
+ * (cell->get_dof_indices of the active-cell loop); each reads its DoFs from the vector that earlier cells have
+ * already written (a continuous FE shares face DoFs), projects to the Legendre modes (FullMatrix::vmult:
+ * dst(i) = sum_j A(i,j) src(j), j ascending), scales the modes with degree >= Nc by sigma and projects back.
+ * damped[i] != 0 marks the modes the reference multiplies (the others are left untouched, not multiplied by 1). */
+void orc_exponential_filter(int64_t n_cells, int n, const int32_t *cell_dofs, const double *to_legendre,
+                            const double *from_legendre, const double *sigma, const unsigned char *damped, double *v)
+{
+    double src[1024], leg[1024];
+    for (int64_t c = 0; c < n_cells; c++) {
+        const int32_t *idx = cell_dofs + c * n;
+        for (int i = 0; i < n; i++) src[i] = v[idx[i]];
+        for (int i = 0; i < n; i++) {
+            double s = 0.0;
+            for (int j = 0; j < n; j++) s += to_legendre[(size_t)i * n + j] * src[j];
+            leg[i] = s;
+        }
+        for (int i = 0; i < n; i++) if (damped[i]) leg[i] = sigma[i] * leg[i];
+        for (int i = 0; i < n; i++) {
+            double s = 0.0;
+            for (int j = 0; j < n; j++) s += from_legendre[(size_t)i * n + j] * leg[j];
+            src[i] = s;
+        }
+        for (int i = 0; i < n; i++) v[idx[i]] = src[i];
+    }
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -52,8 +52,8 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
         ctx.set_collision(nu, dt, equilibrium=_capi.QUARTIC_EQUILIBRIUM, with_g=True, gamma=1.4, prandtl=0.71, sutherland=True)
     else:
         ctx.set_collision(nu, dt)
-    if grid:
-        assert ctx.grid_info()["in_use"] == 1
+    # a rank that asserted here would leave its peers waiting in the exchange: the kernels in use are gathered and judged on rank 0
+    grid_in_use = int(ctx.grid_info()["in_use"]) if grid else -1
     x = host.owned_points()
     if dim == 2:
         rho, u = harness.taylor_green_2d(x)
@@ -81,7 +81,7 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
     if grid:
         ids = ids[num.order]
     gathered = [None] * world
-    dist.all_gather_object(gathered, (ids, got, f, g if with_g else None))
+    dist.all_gather_object(gathered, (ids, got, f, g if with_g else None, grid_in_use))
     ctx.close()
     if rank != 0:
         return True
@@ -91,7 +91,7 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
     N = pb.N
     F0, G0 = np.empty((st.getQ(), N)), np.empty((st.getQ(), N))
     RES = [np.empty((st.getQ(), N)) for _ in got]
-    for ids_r, got_r, f_r, g_r in gathered:
+    for ids_r, got_r, f_r, g_r, _ in gathered:
         F0[:, ids_r] = f_r
         if with_g:
             G0[:, ids_r] = g_r
@@ -127,8 +127,9 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
     if with_g:
         err = max(err, float(np.max(np.abs(RES[1] - G0) / np.abs(G0))))
     mass = F0.sum()
-    ok = err <= 1e-11 and abs(cons[0] - mass) <= 1e-12 * mass
-    print(f"multirank {name} world={world} {'grid' if grid else 'staged'}{' walled' if walls is not None else ''}: max rel err after {steps} steps = {err:.3e}, mass {cons[0]:.15g} vs {mass:.15g} -> {'OK' if ok else 'FAIL'}", flush=True)
+    kernels_ok = all(t[4] != 0 for t in gathered)        # grid cases: every rank really ran the TMA box kernels
+    ok = err <= 1e-11 and abs(cons[0] - mass) <= 1e-12 * mass and kernels_ok
+    print(f"multirank {name} world={world} {'grid' if grid else 'staged'}{' walled' if walls is not None else ''}: max rel err after {steps} steps = {err:.3e}, mass {cons[0]:.15g} vs {mass:.15g} -> {'OK' if ok else 'FAIL'}{'' if kernels_ok else ' (grid tables not in use on some rank)'}", flush=True)
     return ok
 
 
