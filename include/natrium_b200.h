@@ -238,6 +238,32 @@ int nb200_step(nb200_ctx *ctx, int n_steps);
 int nb200_set_post_collision_matrix(nb200_ctx *ctx, int Q, const double *A);
 int nb200_apply_post_collision(nb200_ctx *ctx);
 
+/* Filter hook between stream and collide (CFDSolver::filter, L/solver/CFDSolver.cpp:859-874; compressibleFilter,
+ * L/solver/CompressibleCFDSolver.h:315-333): ExponentialFilter<dim>::applyFilter (L/smoothing/ExponentialFilter.cpp:139-199)
+ * on every population of f (and g).  The host keeps what the reference computes once with deal.II and hands it over:
+ *   cell_dofs[n_cells][dofs_per_cell]  cell->get_dof_indices() of every locally owned cell IN THE ORDER of the reference's
+ *                                      active-cell loop, as local indices (owned DoFs or ghost slots);
+ *   to_legendre, from_legendre         getProjectToLegendre() / getProjectFromLegendre(), row-major [n][n], n = dofs_per_cell,
+ *                                      in the same element-local numbering as cell_dofs;
+ *   sigma[n]                           damping factor of every Legendre mode, exp(-alpha ((degree+1-Nc)/(max_degree+1-Nc))^s)
+ *                                      for degree >= Nc and exactly 1 otherwise (the reference leaves those modes alone).
+ * The reference's loop is sequential and cells of a continuous element share face DoFs: a cell reads what earlier cells
+ * wrote.  The library keeps exactly that order -- cells are sorted into levels (above every earlier cell they share a DoF
+ * with) and each level is one kernel launch -- so results equal the reference's whatever the cell order (lexicographic,
+ * Morton, ...).  interval = getFilterInterval(): inside nb200_step the iteration counter m_i is advanced per step and the
+ * filter runs when m_i % interval == 0 (those steps run stream, filter, collide as separate kernels); interval = 0 keeps
+ * it out of nb200_step.  nb200_apply_filter applies it once to the current populations of distribution `which`
+ * (the m_filter->applyFilter call site); nb200_set_iteration sets m_i (restart).  n_cells = 0 removes the filter.
+ * Several ranks: a cell's ghost DoFs are read from the ghost slots and written there only locally (the reference writes a
+ * non-ghosted vector); nb200_step refreshes all ghost slots of the streamed populations before the filter and the next
+ * step's exchange overwrites them, as m_f.updateGhosted() does.  dofs_per_cell <= 256. */
+int nb200_set_filter(nb200_ctx *ctx, int64_t n_cells, int dofs_per_cell, const int32_t *cell_dofs, const double *to_legendre,
+                     const double *from_legendre, const double *sigma, int interval);
+int nb200_apply_filter(nb200_ctx *ctx, int which);
+int nb200_set_iteration(nb200_ctx *ctx, int64_t iteration);
+/* out = { #cells, dofs per cell, #levels (kernel launches per distribution and application), interval, m_i } */
+int nb200_filter_info(const nb200_ctx *ctx, int64_t out[5]);
+
 /* One step driven with HOST buffers -- what a host-resident DistributionFunctions sees from
  * SemiLagrangian::stream(f_old, f, t) followed by selectCollision (SemiLagrangian.h:150-161, CollisionSelection.h:60-67):
  * f_in [Q][n] -> device, fused stream+collide, f_out [Q][n], rho [n], u [D][n] -> host (rho / u may be NULL).  Page-locked

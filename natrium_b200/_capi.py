@@ -78,6 +78,10 @@ SIGNATURES = {
     "nb200_set_post_collision_matrix": (C.c_int, [_vp, C.c_int, _dp]),
     "nb200_apply_post_collision": (C.c_int, [_vp]),
     "nb200_set_wall_hits": (C.c_int, [_vp, C.c_int64, _i32p, _i32p, _i32p, _dp]),
+    "nb200_set_filter": (C.c_int, [_vp, C.c_int64, C.c_int, _i32p, _dp, _dp, _dp, C.c_int]),
+    "nb200_apply_filter": (C.c_int, [_vp, C.c_int]),
+    "nb200_set_iteration": (C.c_int, [_vp, C.c_int64]),
+    "nb200_filter_info": (C.c_int, [_vp, _i64p]),
     "nb200_update_ghosted": (C.c_int, [_vp]),
     "nb200_stream": (C.c_int, [_vp, C.c_int]),
     "nb200_collide": (C.c_int, [_vp]),
@@ -294,6 +298,28 @@ class Context:
 
     def apply_post_collision(self):
         self._check(self.lib.nb200_apply_post_collision(self._h))
+
+    def set_filter(self, cell_dofs, to_legendre, from_legendre, sigma, interval=1):
+        """ExponentialFilter tables (nb200_set_filter): cell_dofs [n_cells, n] in the host's cell order; None removes it."""
+        if cell_dofs is None:
+            self._check(self.lib.nb200_set_filter(self._h, 0, 0, None, None, None, None, 0))
+            return
+        cd = np.ascontiguousarray(cell_dofs, dtype=np.int32)
+        to, fr, sg = _as_f64(to_legendre), _as_f64(from_legendre), _as_f64(sigma)
+        n = cd.shape[1]
+        assert to.shape == (n, n) and fr.shape == (n, n) and sg.shape == (n,)
+        self._check(self.lib.nb200_set_filter(self._h, cd.shape[0], n, cd.ctypes.data_as(_i32p), _dptr(to), _dptr(fr), _dptr(sg), int(interval)))
+
+    def apply_filter(self, which=0):
+        self._check(self.lib.nb200_apply_filter(self._h, which))
+
+    def set_iteration(self, i):
+        self._check(self.lib.nb200_set_iteration(self._h, int(i)))
+
+    def filter_info(self):
+        out = np.zeros(5, dtype=np.int64)
+        self._check(self.lib.nb200_filter_info(self._h, out.ctypes.data_as(_i64p)))
+        return dict(zip(("cells", "dofs_per_cell", "levels", "interval", "iteration"), (int(v) for v in out)))
 
     def set_mrt(self, M, T, omega):
         """Tables of MultipleRelaxationTime::SpecificCollisionData (make_M / make_T / make_diag)."""

@@ -292,6 +292,19 @@ int post(const NbLaunch& L)
 }
 #endif
 
+int filter(const NbLaunch& L)
+{
+    if (L.filt_n_cells <= 0) return 0;
+    const int threads = (L.filt_n + 31) / 32 * 32;
+    const size_t sm = (size_t)L.filt_n * Q * sizeof(double);
+    // the size depends on the context's FE order: set per call (cheap), not once per device
+    cudaError_t e = cudaFuncSetAttribute(k_filter_level<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return (int)e;
+    k_filter_level<Q><<<(unsigned)L.filt_n_cells, threads, sm, L.stream>>>(L.filt_n, L.filt_cells, L.filt_dofs, L.filt_toT, L.filt_fromT,
+                                                                        L.filt_sigma, L.yf, L.A.stride);
+    return (int)cudaGetLastError();
+}
+
 const NbStencilOps ops = {D, Q,
 #if NB_FUSE_F || (NB_WITH_G && NB_FUSE_G)
                           fused,
@@ -304,7 +317,7 @@ const NbStencilOps ops = {D, Q,
 #else
                           nullptr,
 #endif
-                          stream_grid};
+                          stream_grid, filter};
 
 }  // namespace
 

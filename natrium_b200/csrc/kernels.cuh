@@ -754,6 +754,62 @@ k_conserved_partial(int64_t n, int64_t stride, const double* __restrict__ f,
     if (threadIdx.x < 5) partial[blockIdx.x * 5 + threadIdx.x] = sm[threadIdx.x][0];
 }
 
+// ExponentialFilter<dim>::applyFilter (smoothing/ExponentialFilter.cpp:139-199) for the cells of ONE level, all Q populations
+// of a distribution at once (CFDSolver::filter loops the populations, CFDSolver.cpp:866-869).  The reference visits the
+// cells one after the other and a continuous FE shares face DoFs, so a cell reads what earlier cells wrote: the host sorts
+// the cells into levels (a cell's level is above that of every earlier cell it shares a DoF with); the cells of one level
+// share nothing and one launch handles them, one CTA per cell, thread i = row i of the two (p+1)^dim projections
+// (FullMatrix::vmult: sum over j ascending).  toT / fromT are the transposed matrices, so a warp's weight loads coalesce;
+// the cell's values sit in shared memory [n][Q] and are read as broadcasts.
+template <int Q>
+__global__ void __launch_bounds__(256)
+k_filter_level(int n, const int32_t* __restrict__ cells, const int32_t* __restrict__ cell_dofs, const double* __restrict__ toT,
+               const double* __restrict__ fromT, const double* __restrict__ sigma, double* __restrict__ pop, int64_t stride)
+{
+    extern __shared__ double smem_filter[];          // [n][Q]
+    const int i = threadIdx.x;
+    const int64_t cell = cells[blockIdx.x];
+    int32_t idx = 0;
+    if (i < n) {
+        idx = __ldg(cell_dofs + cell * n + i);
+#pragma unroll
+        for (int q = 0; q < Q; q++) smem_filter[i * Q + q] = pop[(int64_t)q * stride + idx];
+    }
+    __syncthreads();
+    double acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) acc[q] = 0.0;
+    if (i < n) {
+#pragma unroll 2
+        for (int j = 0; j < n; j++) {
+            const double w = __ldg(toT + (int64_t)j * n + i);
+#pragma unroll
+            for (int q = 0; q < Q; q++) acc[q] += w * smem_filter[j * Q + q];
+        }
+        const double sg = __ldg(sigma + i);
+#pragma unroll
+        for (int q = 0; q < Q; q++) acc[q] = sg * acc[q];
+    }
+    __syncthreads();
+    if (i < n) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) smem_filter[i * Q + q] = acc[q];
+    }
+    __syncthreads();
+    if (i < n) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) acc[q] = 0.0;
+#pragma unroll 2
+        for (int j = 0; j < n; j++) {
+            const double w = __ldg(fromT + (int64_t)j * n + i);
+#pragma unroll
+            for (int q = 0; q < Q; q++) acc[q] += w * smem_filter[j * Q + q];
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) pop[(int64_t)q * stride + idx] = acc[q];
+    }
+}
+
 static __global__ void k_conserved_final(int n_blocks, const double* __restrict__ partial, double* __restrict__ out)
 {
     if (threadIdx.x < 5) {

@@ -38,6 +38,9 @@ struct NbLaunch {
     const int32_t* gidx;    // collide with grid dual write: canonical row -> flat grid index (null = canonical only)
     const int16_t* grid_off; int grid_off_dirs;
     int n_rhs;              // stream_grid: 1 = the distribution in xf/yf, 2 = f and g in one pass
+    // exponential filter (k_filter_level): one level of cells on the populations in yf
+    int filt_n; int64_t filt_n_cells; const int32_t* filt_cells; const int32_t* filt_dofs;
+    const double* filt_toT; const double* filt_fromT; const double* filt_sigma;
 };
 
 struct NbStencilOps {
@@ -49,6 +52,7 @@ struct NbStencilOps {
     int (*bind)(const NbLaunch&);        // uploads the constant block if this context's version is not the bound one
     int (*post)(const NbLaunch&);        // post-collision matrix on yf; nullptr where the reference has none
     int (*stream_grid)(const NbLaunch&); // stream only over the grid copy (xf[, xg] -> yf[, yg], canonical output)
+    int (*filter)(const NbLaunch&);      // one level of the exponential filter on yf
 };
 
 const NbStencilOps* nb_ops_d2q9();

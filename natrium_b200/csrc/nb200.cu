@@ -214,6 +214,12 @@ struct nb200_ctx {
     int32_t *d_cta_interior = nullptr, *d_cta_boundary = nullptr;
     int64_t n_cta_interior = 0, n_cta_boundary = 0;
     bool overlap = true;
+    // exponential filter (nb200_set_filter): cells sorted into levels, transposed projections
+    int64_t filt_cells = 0, iteration = 0;
+    int filt_n = 0, filt_interval = 0;
+    std::vector<int64_t> filt_level_off;     // [#levels + 1] into d_filt_cells
+    int32_t *d_filt_cells = nullptr, *d_filt_dofs = nullptr;
+    double *d_filt_toT = nullptr, *d_filt_fromT = nullptr, *d_filt_sigma = nullptr;
 };
 
 static const NbStencilOps* find_ops(int D, int Q);
@@ -553,6 +559,9 @@ static void free_matrix(nb200_ctx* c)
     c->matrix_ready = false;
 }
 
+static void free_filter(nb200_ctx* c);
+static int dispatch_filter(nb200_ctx* c, int which);
+
 static void free_grid(nb200_ctx* c)
 {
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) { cudaFree(c->gpop[w][b]); c->gpop[w][b] = nullptr; }
@@ -572,6 +581,7 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     free_blocks(c);
     free_matrix(c);
     free_grid(c);
+    free_filter(c);
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) cudaFree(c->pop[w][b]);
     cudaFree(c->rho); cudaFree(c->u); cudaFree(c->T); cudaFree(c->sensor);
     cudaFree(c->d_flag); cudaFree(c->d_partial);
@@ -696,6 +706,7 @@ extern "C" int nb200_set_layout(nb200_ctx* c, int64_t n_owned, int64_t n_ghost, 
     free_blocks(c);
     free_matrix(c);
     free_grid(c);
+    free_filter(c);
     cudaFree(c->d_order); cudaFree(c->d_perm); cudaFree(c->d_stage);
     c->d_order = c->d_perm = nullptr; c->d_stage = nullptr;
     c->has_order = false;
@@ -711,7 +722,7 @@ extern "C" int nb200_set_dof_order(nb200_ctx* c, int64_t n, const int32_t* order
 {
     if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "set_dof_order: call set_layout first");
     if (n != c->n_owned || (n > 0 && !order)) return fail(c, NB200_ERR_ARG, "set_dof_order: n=%lld != n_owned=%lld", (long long)n, (long long)c->n_owned);
-    if (!c->blocks.empty() || c->matrix_ready || c->n_nbr || c->grid_hint) return fail(c, NB200_ERR_ARG, "set_dof_order: call right after set_layout (before set_dof_grid / matrix / halo uploads)");
+    if (!c->blocks.empty() || c->matrix_ready || c->n_nbr || c->grid_hint || c->filt_cells) return fail(c, NB200_ERR_ARG, "set_dof_order: call right after set_layout (before set_dof_grid / matrix / halo / filter uploads)");
     CUDA_TRY(c, cudaSetDevice(c->device));
     std::vector<int32_t> perm((size_t)n, -1);
     for (int64_t k = 0; k < n; k++) {
@@ -1988,7 +1999,9 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
     const bool split = c->overlap && c->nranks > 1 && c->n_nbr > 0 && c->fmt == NB_FMT_DICT && (grid || c->staged)
         && n_int > 0 && n_bnd > 0;
     for (int s = 0; s < n_steps; s++) {
-        if (c->n_hit_groups > 0) {
+        c->iteration++;                                                 // m_i++ (CFDSolver::run, CFDSolver.cpp:885)
+        const bool filt = c->filt_cells > 0 && c->filt_interval > 0 && c->iteration % c->filt_interval == 0;
+        if (c->n_hit_groups > 0 || filt) {
             // walls: reference order stream(f) -> wall hits (on the new f and the not yet streamed g) -> gStream -> collide
             // (CompressibleCFDSolver.h:181-314); the hit kernel sits between the two streams, so nothing is fused.
             // g is exchanged AFTER the hits: ThermalBounceBack rewrites g at wall DoFs, and the reference's gStream imports
@@ -2000,6 +2013,13 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             if (!rc && do_g) rc = halo_exchange(c, false, true);
             if (!rc && do_g && grid) rc = sync_grid(c, false, true, c->stream);
             if (!rc && do_g && c->n_slices > 0) rc = launch_stream(c, false, true);
+            if (!rc && filt) {
+                // CFDSolver::filter / compressibleFilter: between stream and collide.  Several ranks: every ghost slot gets
+                // the neighbour's streamed value first (cells at the rank boundary read them)
+                if (c->nranks > 1) rc = halo_exchange(c, true, do_g, /*pruned=*/false);
+                if (!rc) rc = dispatch_filter(c, 0);
+                if (!rc && do_g) rc = dispatch_filter(c, 1);
+            }
             if (!rc && c->n_owned > 0) rc = dispatch_collide(c);
             if (!rc) rc = dispatch_post(c);
             if (rc) return rc;
@@ -2045,6 +2065,123 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
         if (rc) return rc;
     }
     CUDA_TRY(c, cudaGetLastError());
+    return NB200_OK;
+}
+
+// ---- exponential filter ----------------------------------------------------------------------------
+static void free_filter(nb200_ctx* c)
+{
+    cudaFree(c->d_filt_cells); cudaFree(c->d_filt_dofs); cudaFree(c->d_filt_toT); cudaFree(c->d_filt_fromT); cudaFree(c->d_filt_sigma);
+    c->d_filt_cells = c->d_filt_dofs = nullptr;
+    c->d_filt_toT = c->d_filt_fromT = c->d_filt_sigma = nullptr;
+    c->filt_cells = 0; c->filt_n = 0; c->filt_interval = 0;
+    c->filt_level_off.clear();
+}
+
+extern "C" int nb200_set_filter(nb200_ctx* c, int64_t n_cells, int n, const int32_t* cell_dofs, const double* to_legendre,
+                                const double* from_legendre, const double* sigma, int interval)
+{
+    if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "set_filter: call set_layout first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    free_filter(c);
+    if (n_cells == 0) return NB200_OK;
+    if (n_cells < 0 || n < 1 || !cell_dofs || !to_legendre || !from_legendre || !sigma || interval < 0) return fail(c, NB200_ERR_ARG, "set_filter: bad argument");
+    if (n > 256) return fail(c, NB200_ERR_UNSUPPORTED, "set_filter: %d DoFs per cell (the filter kernel holds one cell per CTA, at most 256)", n);
+    if ((size_t)n * c->Q * sizeof(double) > 200 * 1024) return fail(c, NB200_ERR_UNSUPPORTED, "set_filter: %d DoFs per cell x %d populations exceed the shared memory of a CTA", n, c->Q);
+    const int64_t nloc = c->n_owned + c->n_ghost;
+    // internal indices; levels: above every earlier cell that shares a DoF (the reference's sequential order is kept)
+    std::vector<int32_t> dofs((size_t)n_cells * n);
+    std::vector<int32_t> last_level((size_t)std::max<int64_t>(1, nloc), 0), level((size_t)n_cells, 0);
+    int32_t n_levels = 0;
+    for (int64_t cell = 0; cell < n_cells; cell++) {
+        int32_t lv = 0;
+        for (int i = 0; i < n; i++) {
+            const int32_t u = cell_dofs[cell * n + i];
+            if (u < 0 || u >= nloc) return fail(c, NB200_ERR_ARG, "set_filter: DoF %d of cell %lld outside the owned + ghost range", (int)u, (long long)cell);
+            const int32_t d = (u < c->n_owned && c->has_order) ? c->perm[(size_t)u] : u;
+            dofs[(size_t)(cell * n + i)] = d;
+            lv = std::max(lv, last_level[(size_t)d]);
+        }
+        lv += 1;
+        for (int i = 0; i < n; i++) {
+            int32_t& ll = last_level[(size_t)dofs[(size_t)(cell * n + i)]];
+            if (ll == lv) return fail(c, NB200_ERR_ARG, "set_filter: cell %lld lists a DoF twice", (long long)cell);
+            ll = lv;
+        }
+        level[(size_t)cell] = lv;
+        n_levels = std::max(n_levels, lv);
+    }
+    c->filt_level_off.assign((size_t)n_levels + 1, 0);
+    for (int64_t cell = 0; cell < n_cells; cell++) c->filt_level_off[(size_t)level[(size_t)cell]]++;
+    for (int32_t l = 0; l < n_levels; l++) c->filt_level_off[(size_t)l + 1] += c->filt_level_off[(size_t)l];
+    std::vector<int32_t> sorted((size_t)n_cells);
+    {
+        std::vector<int64_t> cur(c->filt_level_off.begin(), c->filt_level_off.end() - 1);
+        for (int64_t cell = 0; cell < n_cells; cell++) sorted[(size_t)cur[(size_t)level[(size_t)cell] - 1]++] = (int32_t)cell;
+    }
+    std::vector<double> tT((size_t)n * n), fT((size_t)n * n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            tT[(size_t)j * n + i] = to_legendre[(size_t)i * n + j];
+            fT[(size_t)j * n + i] = from_legendre[(size_t)i * n + j];
+        }
+    CUDA_TRY(c, cudaMalloc(&c->d_filt_cells, (size_t)n_cells * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_filt_dofs, dofs.size() * 4));
+    CUDA_TRY(c, cudaMalloc(&c->d_filt_toT, tT.size() * 8));
+    CUDA_TRY(c, cudaMalloc(&c->d_filt_fromT, fT.size() * 8));
+    CUDA_TRY(c, cudaMalloc(&c->d_filt_sigma, (size_t)n * 8));
+    CUDA_TRY(c, cudaMemcpy(c->d_filt_cells, sorted.data(), (size_t)n_cells * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_filt_dofs, dofs.data(), dofs.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_filt_toT, tT.data(), tT.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_filt_fromT, fT.data(), fT.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(c, cudaMemcpy(c->d_filt_sigma, sigma, (size_t)n * 8, cudaMemcpyHostToDevice));
+    c->filt_cells = n_cells; c->filt_n = n; c->filt_interval = interval;
+    return NB200_OK;
+}
+
+// all levels of the filter on the current populations of distribution `which`
+static int dispatch_filter(nb200_ctx* c, int which)
+{
+    if (c->filt_cells == 0) return NB200_OK;
+    if (!c->ops || !c->ops->filter) return fail(c, NB200_ERR_UNSUPPORTED, "filter: no kernels built for D%dQ%d", c->D, c->Q);
+    NbLaunch L = make_launch(c);
+    L.yf = c->pop[which][c->cur[which]];
+    L.filt_n = c->filt_n; L.filt_dofs = c->d_filt_dofs;
+    L.filt_toT = c->d_filt_toT; L.filt_fromT = c->d_filt_fromT; L.filt_sigma = c->d_filt_sigma;
+    for (size_t l = 0; l + 1 < c->filt_level_off.size(); l++) {
+        L.filt_cells = c->d_filt_cells + c->filt_level_off[l];
+        L.filt_n_cells = c->filt_level_off[l + 1] - c->filt_level_off[l];
+        int rc = cuda_rc(c, c->ops->filter(L), "exponential filter");
+        if (rc) return rc;
+        c->launches++;
+    }
+    c->grid_valid[which] = false;
+    return NB200_OK;
+}
+
+extern "C" int nb200_apply_filter(nb200_ctx* c, int which)
+{
+    if (!c || !c->stride) return fail(c, NB200_ERR_ARG, "apply_filter: call set_layout first");
+    if (which < 0 || which > 1 || (which == 1 && !c->with_g)) return fail(c, NB200_ERR_ARG, "apply_filter: distribution %d not allocated", which);
+    if (c->filt_cells == 0) return fail(c, NB200_ERR_ARG, "apply_filter: no filter set");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    return dispatch_filter(c, which);
+}
+
+extern "C" int nb200_set_iteration(nb200_ctx* c, int64_t iteration)
+{
+    if (!c || iteration < 0) return fail(c, NB200_ERR_ARG, "set_iteration: bad argument");
+    c->iteration = iteration;
+    return NB200_OK;
+}
+
+extern "C" int nb200_filter_info(const nb200_ctx* c, int64_t out[5])
+{
+    if (!c || !out) return NB200_ERR_ARG;
+    out[0] = c->filt_cells; out[1] = c->filt_n;
+    out[2] = c->filt_level_off.empty() ? 0 : (int64_t)c->filt_level_off.size() - 1;
+    out[3] = c->filt_interval; out[4] = c->iteration;
     return NB200_OK;
 }
 

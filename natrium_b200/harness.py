@@ -226,6 +226,25 @@ class SlabPartition:
     def owned_global_ids(self):
         return (self.owned_planes[:, None] * self.pb.plane + np.arange(self.pb.plane)[None, :]).reshape(-1)
 
+    def cell_dofs(self):
+        """[n_cells, (p+1)^dim] local DoF indices (owned or ghost slots) of the rank's cells, cells in lexicographic order
+        (x fastest), element-local numbering lexicographic: what cell->get_dof_indices gives in the active-cell loop of a
+        Cartesian deal.II mesh with an FE_DGQ-like local numbering.  Input for nb200_set_filter."""
+        pb, p, dim = self.pb, self.pb.p, self.pb.dim
+        last = pb.axes[-1]
+        bounds = [(last.n * r) // self.nranks for r in range(self.nranks + 1)]
+        loc = np.arange(p + 1, dtype=np.int64)
+        cz = np.arange(bounds[self.rank], bounds[self.rank + 1], dtype=np.int64)
+        zb = self.base[cz[:, None] * p + loc[None, :]]                                # (ncz, p+1) plane bases
+        assert (zb >= 0).all(), "a plane of an own cell is neither owned nor a ghost"
+        gx = np.arange(pb.axes[0].n, dtype=np.int64)[:, None] * p + loc[None, :]      # (ncx, p+1)
+        if dim == 2:
+            ids = zb[:, None, :, None] + gx[None, :, None, :]                         # (cz, cx, lz, lx)
+        else:
+            gy = (np.arange(pb.axes[1].n, dtype=np.int64)[:, None] * p + loc[None, :]) * pb.nd[0]
+            ids = zb[:, None, None, :, None, None] + gy[None, :, None, None, :, None] + gx[None, None, :, None, None, :]
+        return np.ascontiguousarray(ids.reshape(-1, (p + 1) ** dim), dtype=np.int32)
+
     def grid_coords(self):
         """(dims, coords) for nb200_set_dof_grid: integer grid coordinates of every local DoF (owned, then ghosts) in a
         local tensor grid whose coordinates 0, p, 2p, ... are cell faces.  In a deal.II build the same numbers come from
@@ -482,6 +501,15 @@ class CellNumbering:
     def halo_plan(self):
         nbr, send_off, send_idx, recv_off = self.part.halo_plan()
         return nbr, send_off, self.perm[send_idx].astype(np.int32), recv_off
+
+    def cell_dofs(self):
+        """SlabPartition.cell_dofs in this numbering (ghost slots keep their indices)."""
+        cd = self.part.cell_dofs()
+        n = self.part.n_owned
+        out = cd.copy()
+        m = cd < n
+        out[m] = self.perm[cd[m]]
+        return out
 
     def renumber_csr(self, rowptr, col, val):
         n = self.n_owned

@@ -214,6 +214,63 @@ class PseudoEntropicStabilizer:
         self.m_solver.ctx.apply_post_collision()
 
 
+class ExponentialFilter:
+    """Mirror of natrium::ExponentialFilter<dim> (L/smoothing/ExponentialFilter.h:25-98): the constructor builds, once, the
+    projections between the nodal element basis and the tensor Legendre modes and the per-mode damping; applyFilter runs on
+    the device (nb200_set_filter / nb200_apply_filter).  The reference integrates with the operator's own Gauss-Lobatto rule
+    on the element's own nodes (L/advection/AdvectionOperator.cpp:34-39), for which quad_legendre^-1 quad_source
+    (ExponentialFilter.cpp:46-66) is the inverse of the matrix Psi[node][mode] of mode values at the nodes: this mirror forms
+    from_legendre = Psi and to_legendre = Psi^-1 directly.  Element-local numbering: lexicographic, x fastest."""
+
+    def __init__(self, alpha, s, Nc, by_sum, p, dim):
+        self.m_alpha, self.m_s, self.m_Nc, self.m_bySum, self.m_p, self.dim = float(alpha), float(s), int(Nc), bool(by_sum), int(p), int(dim)
+        n1 = p + 1
+        x = harness.gauss_lobatto_points(p)
+        # dealii::Polynomials::Legendre: orthonormal on [0,1]; three-term recurrence in t = 2x - 1
+        t = 2.0 * x - 1.0
+        leg = np.zeros((n1, n1))
+        leg[:, 0] = 1.0
+        if p >= 1:
+            leg[:, 1] = t
+        for k in range(2, n1):
+            leg[:, k] = ((2 * k - 1) * t * leg[:, k - 1] - (k - 1) * leg[:, k - 2]) / k
+        leg *= np.sqrt(2.0 * np.arange(n1) + 1.0)[None, :]
+        n = n1 ** dim
+        psi = np.ones((n, n))
+        for i in range(n):                    # node i: lexicographic, x fastest
+            node = [(i // n1 ** d) % n1 for d in range(dim)]
+            for m in range(n):                # mode m: x slowest (evaluateLegendreND, ExponentialFilter.cpp:70-94)
+                mode = [(m // n1 ** (dim - 1 - d)) % n1 for d in range(dim)]
+                v = 1.0
+                for d in range(dim):
+                    v *= leg[node[d], mode[d]]
+                psi[i, m] = v
+        self.m_projectFromLegendre = np.ascontiguousarray(psi)
+        self.m_projectToLegendre = np.ascontiguousarray(np.linalg.inv(psi))
+        # makeDegreeVectors (:96-137); in 3-D the reference's iy expression evaluates to i % (p+1) (operator precedence, :123)
+        self.m_degreeMax, self.m_degreeSum = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            if dim == 1:
+                idx = (i,)
+            elif dim == 2:
+                idx = (i // n1, i % n1)
+            else:
+                idx = (i // (n1 * n1), i % n1, i % n1)
+            self.m_degreeMax[i], self.m_degreeSum[i] = max(idx), sum(idx)
+        deg = self.m_degreeSum if self.m_bySum else self.m_degreeMax
+        max_degree = dim * p if self.m_bySum else p
+        self.sigma = np.ones(n)
+        hit = deg >= self.m_Nc
+        self.sigma[hit] = np.exp(-self.m_alpha * ((deg[hit] + 1.0 - self.m_Nc) / (max_degree + 1.0 - self.m_Nc)) ** self.m_s)
+
+    def getProjectToLegendre(self): return self.m_projectToLegendre
+    def getProjectFromLegendre(self): return self.m_projectFromLegendre
+
+    def attach(self, ctx, cell_dofs, interval=1):
+        """Hands the tables to the device library (cell_dofs: cell->get_dof_indices per locally owned cell, in loop order)."""
+        ctx.set_filter(cell_dofs, self.m_projectToLegendre, self.m_projectFromLegendre, self.sigma, interval)
+
+
 class CFDSolver:
     """Time loop owner.  ``run()`` keeps everything on the device (one fused kernel per step);
     ``stream()`` / ``collide()`` are the reference-ordered single operators."""
@@ -263,6 +320,17 @@ class CFDSolver:
         self.m_dataProcessors = getattr(self, "m_dataProcessors", []) + [proc]
         if isinstance(proc, PseudoEntropicStabilizer):
             self.ctx.set_post_collision_matrix(proc.matrix)      # device-resident run(): part of nb200_step
+
+    def setFilter(self, flt, interval=1):
+        """m_filter + getFilterInterval() (CFDSolver.cpp:448-476): the device applies it inside run() between stream and collide."""
+        self.m_filter, self.m_filterInterval = flt, int(interval)
+        part = self.m_advectionOperator.getPartition()
+        flt.attach(self.ctx, part.cell_dofs(), interval)
+
+    def filter(self):
+        """CFDSolver::filter (CFDSolver.cpp:859-874) as a single operator: every population of f."""
+        if getattr(self, "m_filter", None) is not None and self.m_i % self.m_filterInterval == 0:
+            self.ctx.apply_filter(0)
 
     def stream(self):
         self.m_advectionOperator.stream(self.m_f, self.m_f, self.m_time)

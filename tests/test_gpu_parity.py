@@ -1402,3 +1402,139 @@ def test_grid_step_host_and_mixed_calls(case, oracle_lib):
         ctx.close()
     for a, b in zip(res[0], res[1]):
         assert rel_err(b, a) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------
+# ExponentialFilter on the device: nb200_set_filter / nb200_apply_filter / filtered nb200_step
+# ---------------------------------------------------------------------------------------------------
+def _filter_tables(p, dim, alpha=36.0, s=2.0, Nc=1, by_sum=False):
+    from oracle import filter as F
+    to, fr = F.projection_matrices(p, dim)
+    sg, damped = F.damping(p, dim, alpha, s, Nc, by_sum)
+    return to, fr, sg, damped
+
+
+@pytest.mark.parametrize("cell_order", ["lexicographic", "reversed", "shuffled"])
+@pytest.mark.parametrize("case,fmt", [("tgv2d_small", None), ("c1_tgv2d_d2q9", ("dict", 1e-14, True)), ("tgv3d_d3q19_p2", None),
+                                      ("tgv3d_d3q19_small", ("dict", 1e-14, True, "grid")), ("tgv3d_d3q15", None),
+                                      ("tgv2d_d2q25", None), ("tgv3d_d3q45", None)])
+def test_exponential_filter_matches_oracle(case, fmt, cell_order, oracle_lib):
+    """nb200_apply_filter against the oracle's sequential cell loop (ExponentialFilter.cpp:139-199), population by
+    population as CFDSolver::filter does, for any order of the host's cell loop: the level schedule must reproduce the
+    order-dependent result (a cell reads the face DoFs earlier cells wrote) exactly, not just some filtered field."""
+    from oracle import filter as F
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, with_matrix=False, fmt=fmt)
+    with_g = bool(c.get("with_g"))
+    to, fr, sg, damped = _filter_tables(pb.p, pb.dim, Nc=2 if pb.p > 2 else 1)
+    cd = part.cell_dofs()
+    if cell_order == "reversed":
+        cd = cd[::-1].copy()
+    elif cell_order == "shuffled":
+        cd = cd[np.random.default_rng(5).permutation(len(cd))].copy()
+    ctx.set_filter(cd, to, fr, sg, interval=0)
+    info = ctx.filter_info()
+    assert info["cells"] == len(cd) and info["dofs_per_cell"] == (pb.p + 1) ** pb.dim and 1 < info["levels"] <= len(cd)
+    rng = np.random.default_rng(11)
+    f = o["f"] * (1.0 + 0.05 * rng.standard_normal(o["f"].shape))
+    ctx.upload_populations(0, f)
+    ctx.apply_filter(0)
+    got = ctx.download_populations(0)
+    ref = f.copy()
+    for q in range(ref.shape[0]):
+        row = np.ascontiguousarray(ref[q])
+        F.apply_filter(cd, to, fr, sg, damped, row)
+        ref[q] = row
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(got - ref) / scale) <= TOL_STEP
+    assert np.max(np.abs(ref - f) / scale) > 1e-4               # the filter did something
+    if with_g:
+        g = o["g"] * (1.0 + 0.05 * rng.standard_normal(o["g"].shape))
+        ctx.upload_populations(1, g)
+        ctx.apply_filter(1)
+        gg = ctx.download_populations(1)
+        refg = g.copy()
+        for q in range(refg.shape[0]):
+            row = np.ascontiguousarray(refg[q])
+            F.apply_filter(cd, to, fr, sg, damped, row)
+            refg[q] = row
+        assert np.max(np.abs(gg - refg) / np.abs(refg).max(axis=1, keepdims=True)) <= TOL_STEP
+        assert rel_err(ctx.download_populations(0), got) == 0.0      # f untouched by the g pass
+    ctx.close()
+
+
+@pytest.mark.parametrize("case,fmt,interval", [("c1_tgv2d_d2q9", None, 1), ("tgv3d_d3q19_p2", ("dict", 1e-14, False, "grid"), 2),
+                                              ("tgv3d_d3q19_small", ("dict", 1e-14, True), 3), ("tgv2d_d2q25", None, 2)])
+def test_filtered_step_matches_oracle(case, fmt, interval, oracle_lib):
+    """nb200_step with a filter: CFDSolver::run order stream -> filter (when m_i % interval == 0) -> collide
+    (CFDSolver.cpp:884-888; compressibleFilter for f + g), 6 steps against the oracle from the same start; the steps in
+    between run the fused kernel."""
+    from oracle import filter as F
+    o = common.oracle_problem(case)
+    ctx, c, st, pb, dt, part = make_ctx(case, fmt=fmt)
+    with_g = bool(c.get("with_g"))
+    set_collision(ctx, c, dt)
+    to, fr, sg, damped = _filter_tables(pb.p, pb.dim, alpha=5.0, s=4.0, Nc=pb.p)        # only the highest mode, mildly
+    cd = part.cell_dofs()
+    ctx.set_filter(cd, to, fr, sg, interval=interval)
+    f = o["f"].copy()
+    g = o["g"].copy() if with_g else None
+    ctx.upload_populations(0, f)
+    if with_g:
+        ctx.upload_populations(1, g)
+    steps = 6
+    ctx.step(steps)
+    ctx.synchronize()
+    assert ctx.filter_info()["iteration"] == steps
+
+    def filt(a):
+        for q in range(a.shape[0]):
+            row = np.ascontiguousarray(a[q])
+            F.apply_filter(cd, to, fr, sg, damped, row)
+            a[q] = row
+    unfiltered = f.copy()
+    for i in range(1, steps + 1):
+        f = oracle_lib.stream(o["blocks"], f)
+        if with_g:
+            g = oracle_lib.stream(o["blocks"], g)
+        if i % interval == 0:
+            filt(f)
+            if with_g:
+                filt(g)
+        if with_g:
+            assert oracle_lib.collide_bgk_fg(o["st"], f, g, c["nu"], dt, equilibrium=1, gamma=1.4, prandtl=0.71, sutherland=True)[-1] == 0
+        else:
+            assert oracle_lib.collide_bgk(o["st"], f, c["nu"], dt)[-1] == 0
+    got = ctx.download_populations(0)
+    assert rel_err(got, f) <= 10 * TOL_STEP, rel_err(got, f)
+    if with_g:
+        assert rel_err(ctx.download_populations(1), g) <= 10 * TOL_STEP
+    # and it is not the unfiltered run
+    ctx.set_filter(None, None, None, None)
+    ctx.upload_populations(0, unfiltered)
+    if with_g:
+        ctx.upload_populations(1, o["g"])
+    ctx.step(steps)
+    assert rel_err(ctx.download_populations(0), f) > 1e-9
+    ctx.close()
+
+
+def test_filter_errors():
+    from natrium_b200 import NatriumB200Error
+    ctx, c, st, pb, dt, part = make_ctx("tgv2d_small", with_matrix=False)
+    to, fr, sg, _ = _filter_tables(pb.p, pb.dim)
+    cd = part.cell_dofs()
+    with pytest.raises(NatriumB200Error):
+        ctx.apply_filter(0)                                    # nothing set
+    bad = cd.copy(); bad[0, 0] = part.n_owned + 5
+    with pytest.raises(NatriumB200Error):
+        ctx.set_filter(bad, to, fr, sg)
+    bad = cd.copy(); bad[1, 1] = bad[1, 0]
+    with pytest.raises(NatriumB200Error):
+        ctx.set_filter(bad, to, fr, sg)                        # a DoF twice in one cell
+    ctx.set_filter(cd, to, fr, sg)
+    with pytest.raises(NatriumB200Error):
+        ctx.apply_filter(1)                                    # no g in the layout
+    ctx.set_filter(None, None, None, None)
+    assert ctx.filter_info()["cells"] == 0
+    ctx.close()

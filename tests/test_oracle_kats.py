@@ -524,3 +524,90 @@ def test_moving_walls_drag_the_fluid(oracle_lib):
     assert np.max(np.abs(u[0] - 0.01)) < 1e-3
     assert np.max(np.abs(u[1])) < 1e-5
     assert abs(np.abs(rho).sum() / pb["dofs"].N - 1.0) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# ExponentialFilter: set-up restated in oracle/filter.py, cell loop in oracle/natrium_oracle.c
+# ---------------------------------------------------------------------------------------------------
+def test_exponential_filter_projection_kat():
+    """ExponentialFilter_TestProjection_test (test/smoothing/ExponentialFilter_test.cpp:80-116): p = 4, 1-d, nodal
+    coefficients 0.5 .. 0.9; the Legendre expansion built from getProjectToLegendre() takes the same value at x = 0.3 as the
+    nodal expansion (BOOST_CHECK_CLOSE 1e-10 %)."""
+    from oracle import filter as F
+    p = 4
+    to, fr = F.projection_matrices(p, 1)
+    dgq = np.array([0.5, 0.6, 0.7, 0.8, 0.9])
+    nodes, w = F.gauss_lobatto_01(p + 1)
+    assert abs(w.sum() - 1.0) < 1e-15
+    expected = float(dgq @ F.lagrange_1d(nodes, 0.3))
+    leg = to @ dgq
+    result = sum(leg[i] * F.legendre_01(i, 0.3) for i in range(p + 1))
+    assert abs(result - expected) <= 1e-12 * abs(expected)
+    assert np.abs(to @ fr - np.eye(p + 1)).max() < 1e-13
+    # ExponentialFilter_PolynomialDegree_test (:30-46): mode k is a polynomial of degree k, orthonormal on [0, 1]
+    xq, wq = np.polynomial.legendre.leggauss(12)
+    xq, wq = 0.5 * (xq + 1), 0.5 * wq
+    G = np.array([[np.sum(wq * F.legendre_01(i, xq) * F.legendre_01(j, xq)) for j in range(6)] for i in range(6)])
+    assert np.abs(G - np.eye(6)).max() < 1e-13
+
+
+@pytest.mark.parametrize("p,dim", [(4, 1), (3, 2), (2, 3), (4, 3)])
+def test_exponential_filter_host_mirror_equals_oracle_setup(p, dim):
+    """natrium_b200.host.ExponentialFilter (from_legendre = mode values at the nodes, to_legendre = its inverse) against the
+    oracle's literal quadrature sums; damping factors for degree-by-maximum and degree-by-sum, and the reference's 3-d
+    degree quirk (iy = iz)."""
+    from oracle import filter as F
+    from natrium_b200 import host
+    to, fr = F.projection_matrices(p, dim)
+    for by_sum, alpha, s, Nc in [(False, 36.0, 2.0, 1), (True, 10.0, 4.0, 2)]:
+        h = host.ExponentialFilter(alpha, s, Nc, by_sum, p, dim)
+        assert np.abs(h.getProjectToLegendre() - to).max() <= 1e-12 * np.abs(to).max()
+        assert np.abs(h.getProjectFromLegendre() - fr).max() <= 1e-12 * np.abs(fr).max()
+        sg, damped = F.damping(p, dim, alpha, s, Nc, by_sum)
+        assert np.array_equal(h.sigma, sg)
+        assert np.all(sg[damped == 0] == 1.0) and np.all(sg[damped == 1] < 1.0)
+    if dim == 3:
+        dq, _ = F.degree_vectors(p, 3, reference_quirk=True)
+        di, _ = F.degree_vectors(p, 3, reference_quirk=False)
+        assert not np.array_equal(dq, di)             # mode (0, 1, 0): the reference sees degree 0
+        assert dq[(p + 1)] == 0 and di[(p + 1)] == 1
+
+
+def test_exponential_filter_cell_loop(oracle_lib):
+    """applyFilter (ExponentialFilter.cpp:139-199) on a periodic 2-d mesh: the C loop equals a plain numpy restatement of the
+    sequential cell loop; constants and the element-wise mean mode are untouched; the result depends on the cell order
+    (shared face DoFs are read after earlier cells wrote them), which is why the device must keep the order; harness and
+    oracle agree on cell->get_dof_indices."""
+    from oracle import assembly, filter as F
+    from natrium_b200 import harness
+    from natrium_b200.stencils import Stencil
+    p, dim, cells = 3, 2, [4, 3]
+    mesh = assembly.CartesianMesh.uniform(dim, cells)
+    dofs = assembly.DofMap(mesh, p)
+    st = Stencil("D2Q9", 3.0)
+    pb = harness.CartesianProblem(dim, cells, p)
+    part = harness.SlabPartition(pb, st, pb.timestep(st, 0.4))
+    cd = part.cell_dofs()
+    assert np.array_equal(cd, np.array([dofs.cell_dofs(c) for c in mesh.cells()], dtype=np.int32))
+    to, fr = F.projection_matrices(p, dim)
+    sg, damped = F.damping(p, dim, 36.0, 2.0, 1)
+    rng = np.random.default_rng(3)
+    v0 = rng.standard_normal(pb.N)
+    v = F.apply_filter(cd, to, fr, sg, damped, v0.copy())
+    w = v0.copy()
+    for c in range(cd.shape[0]):
+        leg = to @ w[cd[c]]
+        leg = np.where(damped == 1, sg * leg, leg)
+        w[cd[c]] = fr @ leg
+    assert np.abs(v - w).max() <= 1e-13 * np.abs(w).max()
+    ones = F.apply_filter(cd, to, fr, sg, damped, np.ones(pb.N))
+    assert np.abs(ones - 1.0).max() < 1e-13
+    v_rev = F.apply_filter(cd[::-1].copy(), to, fr, sg, damped, v0.copy())
+    assert np.abs(v_rev - v).max() > 1e-6 * np.abs(v).max()
+    # only the highest mode damped (Nc = p): a smooth field is changed little, a rough one a lot (what the filter is for)
+    sg_top, damped_top = F.damping(p, dim, 36.0, 2.0, p)
+    x = part.owned_points()
+    smooth = np.cos(x[:, 0]) * np.sin(x[:, 1])
+    fs = F.apply_filter(cd, to, fr, sg_top, damped_top, smooth.copy())
+    vr = F.apply_filter(cd, to, fr, sg_top, damped_top, v0.copy())
+    assert np.abs(fs - smooth).max() < 0.2 and np.abs(vr - v0).max() > 5 * np.abs(fs - smooth).max()
