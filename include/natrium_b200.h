@@ -269,8 +269,10 @@ int nb200_filter_info(const nb200_ctx *ctx, int64_t out[5]);
  * f_in [Q][n] -> device, fused stream+collide, f_out [Q][n], rho [n], u [D][n] -> host (rho / u may be NULL).  Page-locked
  * buffers make the copies asynchronous; the call returns after enqueue, nb200_synchronize() fences it.  With
  * n_chunks > 1 upload, kernel and download are pipelined over pieces of the DoF range on separate streams (a piece's
- * kernel waits only for the pieces its rows read), so the two PCIe directions overlap; n_chunks <= 1, several ranks,
- * wall hits, f+g or a non-staged matrix format run the same legs in sequence.  Results are identical either way. */
+ * kernel waits only for the pieces its rows read), so the two PCIe directions overlap; with several ranks the pieces that
+ * hold values a neighbour needs are uploaded first, the ghost exchange runs behind them on its own stream and only the rows
+ * that read ghost slots wait for it.  n_chunks <= 1, wall hits, f+g or a non-staged matrix format run the same legs in
+ * sequence.  Results are identical either way. */
 int nb200_step_host(nb200_ctx *ctx, const double *f_in, double *f_out, double *rho, double *u, int64_t n, int n_chunks);
 
 /* The same for the compressible solver's two distributions (CompressibleCFDSolver::stream / gStream / collide,

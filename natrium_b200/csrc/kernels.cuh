@@ -253,7 +253,7 @@ k_stream_collide_fg_staged(StreamArgs A, const double* __restrict__ xf, const do
 // sits at (row offset + cGridOff[direction][k]).  Results are written to the canonical arrays and to the grid copy that
 // the next step's TMA reads.  Dynamic shared memory: [tile(s)][2 staging buffers (per distribution)].
 // ---------------------------------------------------------------------------------------------
-// two 16-bit offsets per word: entries 2j (low half) and 2j+1 (high half) of a class-0 row of the direction
+// two 16-bit BYTE offsets per word: entries 2j (low half) and 2j+1 (high half) of a class-0 row of the direction
 __constant__ unsigned cGridOff[NB_MAX_DIRS][NB_GRID_MAXK / 2];
 
 #ifndef NB_GRID_OCC_F
@@ -306,7 +306,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
                         double* __restrict__ rho_out, double* __restrict__ u_out, int* __restrict__ flag)
 {
     extern __shared__ __align__(128) double smem_grid[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar[3];
     __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
     double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);    // [Q][128]
@@ -317,15 +317,11 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     const int32_t row = __ldg(A.tile_row + slot);
     const bool active = row >= 0;
     srow[tid] = row;
-    {   // the descriptors of all directions: each parks in the tile slot its result will overwrite
-        const int2* __restrict__ dp = A.sdesc + slot;
-#pragma unroll 1
-        for (int a = 0; a < Q - 1; a++, dp += A.gdesc_stride) nb_cp_async8(&tile[a + 1][tid], reinterpret_cast<const double*>(dp));
-    }
     tile[0][tid] = active ? x[row] : 0.0;
     if (tid == 0) {
         nb_mbar_init(&mbar[0], 1);
         nb_mbar_init(&mbar[1], 1);
+        nb_mbar_init(&mbar[2], 1);
         cnt[0] = cnt[1] = 0;
         nb_mbar_fence_init();
     }
@@ -334,9 +330,16 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     if (tid < 32) {      // both buffers are free: the first two passes start right away (warp 0 issues the copies)
         if (p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0], tid);
         if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + NB_GRID_CAP, xs, &mbar[1], tid);
+    } else if (tid < 64) {
+        // the descriptors of all directions, one bulk copy of 128 x 8 bytes per direction: each parks in the tile row its
+        // results will overwrite (no LSU instructions and no L1 allocation: the L1 is left to the weight patterns)
+        const int lane = tid - 32;
+        if (lane == 0) nb_mbar_expect_tx(&mbar[2], (unsigned)((Q - 1) * NB_CTA_ROWS * sizeof(int2)));
+        __syncwarp();
+        for (int a = lane; a < Q - 1; a += 32)
+            nb_bulk_load(&tile[a + 1][0], A.sdesc + (int64_t)a * A.gdesc_stride + tl * NB_CTA_ROWS, NB_CTA_ROWS * sizeof(int2), &mbar[2]);
     }
-    nb_cp_async_wait_all();
-    __syncthreads();          // descriptors of the partner rows are in place
+    nb_mbar_wait(&mbar[2], 0u);          // descriptors (also those of the partner rows) are in place
     const int half = tid >> 6, t0 = tid & 63;
     const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
     for (int p = p0; p < p1; p++) {
@@ -382,7 +385,7 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
                          double* __restrict__ s_out, int* __restrict__ flag)
 {
     extern __shared__ __align__(128) double smem_grid[];
-    __shared__ uint64_t mbar[2];
+    __shared__ uint64_t mbar[3];
     __shared__ int cnt[2];
     __shared__ int32_t srow[NB_CTA_ROWS];
     __shared__ double ctab[Q * NB_CT_PITCH];
@@ -397,16 +400,12 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     const int32_t row = __ldg(A.tile_row + slot);
     const bool active = row >= 0;
     srow[tid] = row;
-    {
-        const int2* __restrict__ dp = A.sdesc + slot;
-#pragma unroll 1
-        for (int a = 0; a < Q - 1; a++, dp += A.gdesc_stride) nb_cp_async8(&tf[a + 1][tid], reinterpret_cast<const double*>(dp));
-    }
     tf[0][tid] = active ? xf[row] : 0.0;
     tg[0][tid] = active ? xg[row] : 0.0;
     if (tid == 0) {
         nb_mbar_init(&mbar[0], 1);
         nb_mbar_init(&mbar[1], 1);
+        nb_mbar_init(&mbar[2], 1);
         cnt[0] = cnt[1] = 0;
         nb_mbar_fence_init();
     }
@@ -415,9 +414,14 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
     if (tid < 32) {
         if (p0 < p1) nb_grid_issue<2>(A, A.gpass[p0], xsf, xsg, &mbar[0], tid);
         if (p0 + 1 < p1) nb_grid_issue<2>(A, A.gpass[p0 + 1], xsf + NB_GRID_CAP_FGF, xsg + NB_GRID_CAP_FGF, &mbar[1], tid);
+    } else if (tid < 64) {      // descriptors by bulk copies, as in k_stream_collide_f_grid
+        const int lane = tid - 32;
+        if (lane == 0) nb_mbar_expect_tx(&mbar[2], (unsigned)((Q - 1) * NB_CTA_ROWS * sizeof(int2)));
+        __syncwarp();
+        for (int a = lane; a < Q - 1; a += 32)
+            nb_bulk_load(&tf[a + 1][0], A.sdesc + (int64_t)a * A.gdesc_stride + tl * NB_CTA_ROWS, NB_CTA_ROWS * sizeof(int2), &mbar[2]);
     }
-    nb_cp_async_wait_all();
-    __syncthreads();
+    nb_mbar_wait(&mbar[2], 0u);
     const int half = tid >> 6, t0 = tid & 63;
     const int32_t r0 = srow[t0], r1 = srow[t0 + 64];
     for (int p = p0; p < p1; p++) {

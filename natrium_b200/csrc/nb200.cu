@@ -154,7 +154,7 @@ struct nb200_ctx {
     NbGridPass* d_gpass = nullptr;
     NbGridBox* d_gbox = nullptr;
     void* d_tmaps = nullptr;                 // [which][buffer][(Q-1)] CUtensorMap (128 bytes each)
-    std::vector<int16_t> grid_off;           // [(Q-1)][NB_GRID_MAXK] host copy of the offset table (constant memory of the unit)
+    std::vector<int16_t> grid_off;           // [(Q-1)][NB_GRID_MAXK] host copy of the offset table in BYTES (constant memory of the unit)
     int32_t *d_gtile_interior = nullptr, *d_gtile_boundary = nullptr;
     int64_t n_gtile_interior = 0, n_gtile_boundary = 0;
     int64_t grid_rows = 0, grid_generic_rows = 0, grid_boxes = 0, grid_passes = 0;
@@ -191,11 +191,16 @@ struct nb200_ctx {
     } plans[8];
     // host-buffer step (nb200_step_host): chunk pipeline over three streams
     std::vector<int32_t> cta_max_user;       // per CTA: largest user DoF index its rows read (owned columns) or own
+    std::vector<uint8_t> cta_reads_ghost;    // per CTA of the staged tables: its staged values include a ghost slot
+    std::vector<int32_t> send_idx_user;      // nb200_set_halo's send indices as given (user numbering)
     struct HostStep {
         bool ready = false;
         int C = 0;
         std::vector<int64_t> u_off, cta_off;         // [C+1] user-index chunks / CTA chunks
         std::vector<int> need_up, order, dl_after, dl_order;
+        std::vector<int> up_order;                   // upload order of the user chunks (chunks that hold send indices first)
+        std::vector<uint8_t> chunk_reads_ghost;      // per CTA chunk: waits for the ghost exchange
+        int halo_after = -1;                         // upload position after which the exchange can start (-1: no exchange)
         int32_t* d_iota = nullptr;
         double *d_in = nullptr, *d_out = nullptr;    // [Q][n] and [Q+1+D][n], user order
         cudaStream_t s_up = nullptr, s_dn = nullptr;
@@ -550,6 +555,7 @@ static void free_matrix(nb200_ctx* c)
         H = nb200_ctx::HostStep();
     }
     c->cta_max_user.clear();
+    c->cta_reads_ghost.clear();
     cudaFree(c->d_tile_row); cudaFree(c->d_tile_gidx); cudaFree(c->d_tile_pass); cudaFree(c->d_gdesc); cudaFree(c->d_gpass);
     cudaFree(c->d_gbox); cudaFree(c->d_tmaps); cudaFree(c->d_gtile_interior); cudaFree(c->d_gtile_boundary);
     c->d_tile_row = c->d_tile_gidx = c->d_tile_pass = nullptr; c->d_gdesc = nullptr; c->d_gpass = nullptr; c->d_gbox = nullptr;
@@ -995,7 +1001,12 @@ static int upload_grid_tables(nb200_ctx* c, nbgrid::Tables& T)
             CUDA_TRY(c, cudaMemcpy(c->d_gtile_boundary, boundary.data(), boundary.size() * 4, cudaMemcpyHostToDevice));
         }
     }
-    c->grid_off = T.off_table;
+    // the kernels add the offsets to byte addresses: the constant table holds them times 8 (16 bits: boxes stay below 8192 values)
+    c->grid_off.resize(T.off_table.size());
+    for (size_t i = 0; i < T.off_table.size(); i++) {
+        if (T.off_table[i] < 0 || T.off_table[i] > 8191) return fail(c, NB200_ERR_UNSUPPORTED, "grid tables: offset %d outside the 16-bit byte-offset range", (int)T.off_table[i]);
+        c->grid_off[i] = (int16_t)(uint16_t)(T.off_table[i] * 8);
+    }
     c->n_tiles = T.n_tiles;
     c->gdesc_stride = T.desc_stride;
     c->grid_rows = T.grid_rows; c->grid_generic_rows = T.generic_rows; c->grid_boxes = T.total_boxes; c->grid_passes = (int64_t)T.passes.size();
@@ -1120,6 +1131,7 @@ static int finalize_dict(nb200_ctx* c)
             std::vector<int32_t> interior, boundary;
             const int64_t n_cta = (int64_t)SB.cta_ptr.size() - 1;
             c->cta_max_user.assign((size_t)n_cta, 0);
+            c->cta_reads_ghost.clear();
             for (int64_t b = 0; b < n_cta; b++) {
                 bool ghost = false;
                 int32_t mx = 0;
@@ -1134,6 +1146,7 @@ static int finalize_dict(nb200_ctx* c)
                     }
                 }
                 c->cta_max_user[(size_t)b] = mx;
+                c->cta_reads_ghost.push_back(ghost ? 1 : 0);
                 (ghost ? boundary : interior).push_back((int32_t)b);
             }
             cudaFree(c->d_cta_interior); cudaFree(c->d_cta_boundary);
@@ -1252,6 +1265,8 @@ extern "C" int nb200_set_halo(nb200_ctx* c, int n_nbr, const int32_t* nbr_rank, 
         if (nbr_rank[k] < 0 || nbr_rank[k] >= c->nranks || nbr_rank[k] == c->rank) return fail(c, NB200_ERR_ARG, "set_halo: bad neighbour rank");
     for (int64_t k = 0; k < c->n_send; k++)
         if (send_idx[k] < 0 || send_idx[k] >= c->n_owned) return fail(c, NB200_ERR_ARG, "set_halo: send index out of owned range");
+    c->send_idx_user.assign(send_idx, send_idx + c->n_send);
+    c->hs.ready = false;
     if (c->n_send) {
         std::vector<int32_t> si(send_idx, send_idx + c->n_send);
         if (c->has_order) for (auto& v : si) v = c->perm[(size_t)v];
@@ -2225,12 +2240,29 @@ static int host_step_plan(nb200_ctx* c, int C)
         while (k < C - 1 && u >= H.u_off[(size_t)k + 1]) k++;
         return k;
     };
-    // CTA chunk k can run once user chunks 0..need_up[k] are on the device (uploads are issued in order)
+    // upload order: several ranks send owned values to their neighbours before the rows that read ghosts can run, so the
+    // user chunks that hold send indices go first and the exchange starts behind them (a slab sends its first and last planes)
+    const bool multi = c->nranks > 1 && c->n_nbr > 0;
+    std::vector<uint8_t> has_send((size_t)C, 0);
+    if (multi) for (int32_t u : c->send_idx_user) has_send[(size_t)chunk_of_user(u)] = 1;
+    H.up_order.clear();
+    for (int j = 0; j < C; j++) if (has_send[(size_t)j]) H.up_order.push_back(j);
+    H.halo_after = multi ? (int)H.up_order.size() - 1 : -1;
+    for (int j = 0; j < C; j++) if (!has_send[(size_t)j]) H.up_order.push_back(j);
+    std::vector<int> pos_up((size_t)C), pos_prefix((size_t)C);
+    for (int i = 0; i < C; i++) pos_up[(size_t)H.up_order[(size_t)i]] = i;
+    for (int j = 0; j < C; j++) pos_prefix[(size_t)j] = std::max(pos_up[(size_t)j], j ? pos_prefix[(size_t)j - 1] : 0);
+    // CTA chunk k can run once user chunks 0..hi_k are on the device: it waits for the upload event at the latest position
+    // any of them has in the upload order (uploads complete in order on their stream)
     H.need_up.assign((size_t)C, 0);
+    H.chunk_reads_ghost.assign((size_t)C, 0);
     for (int k = 0; k < C; k++) {
         int32_t mx = 0;
-        for (int64_t b = H.cta_off[(size_t)k]; b < H.cta_off[(size_t)k + 1]; b++) mx = std::max(mx, c->cta_max_user[(size_t)b]);
-        H.need_up[(size_t)k] = chunk_of_user(mx);
+        for (int64_t b = H.cta_off[(size_t)k]; b < H.cta_off[(size_t)k + 1]; b++) {
+            mx = std::max(mx, c->cta_max_user[(size_t)b]);
+            if (multi && c->cta_reads_ghost[(size_t)b]) H.chunk_reads_ghost[(size_t)k] = 1;
+        }
+        H.need_up[(size_t)k] = pos_prefix[(size_t)chunk_of_user(mx)];
     }
     H.order.resize((size_t)C);
     for (int k = 0; k < C; k++) H.order[(size_t)k] = k;
@@ -2267,7 +2299,8 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     if (!f_in || !f_out || n != c->n_owned) return fail(c, NB200_ERR_ARG, "step_host: bad argument");
     if (c->cp.in_init) return fail(c, NB200_ERR_ARG, "step_host: in_init collisions are only available through nb200_collide");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    const bool pipelined = n_chunks > 1 && c->nranks == 1 && c->fmt == NB_FMT_DICT && c->staged && use_fused(c) && !c->cp.with_g
+    const bool multi = c->nranks > 1 && c->n_nbr > 0;
+    const bool pipelined = n_chunks > 1 && (!multi || c->comm_stream) && c->fmt == NB_FMT_DICT && c->staged && use_fused(c) && !c->cp.with_g
         && c->n_hit_groups == 0 && !c->post_set && n >= (int64_t)n_chunks * 4 * NB_CTA_ROWS;
     if (!pipelined) {      // same result, legs in sequence
         rc = copy_all(c, 0, const_cast<double*>(f_in), n, true, false);
@@ -2286,7 +2319,10 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     CUDA_TRY(c, cudaEventRecord(H.ev_start, c->stream));          // earlier work on the context stream
     CUDA_TRY(c, cudaStreamWaitEvent(H.s_up, H.ev_start, 0));
     CUDA_TRY(c, cudaStreamWaitEvent(H.s_dn, H.ev_start, 0));
-    for (int k = 0; k < C; k++) {
+    c->grid_valid[0] = false;                                     // the grid copy (if any) does not see the uploaded values
+    if (multi) CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, H.ev_start, 0));     // pack / unpack kernels read no constants
+    for (int pos = 0; pos < C; pos++) {
+        const int k = H.up_order[(size_t)pos];
         const int64_t u0 = H.u_off[(size_t)k], u1 = H.u_off[(size_t)k + 1];
         if (u1 > u0) {
             if (perm) {
@@ -2297,11 +2333,20 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
                 CUDA_TRY(c, cudaMemcpy2DAsync(x + u0, (size_t)c->stride * 8, f_in + u0, (size_t)n * 8, (size_t)(u1 - u0) * 8, (size_t)Q, cudaMemcpyHostToDevice, H.s_up));
             }
         }
-        CUDA_TRY(c, cudaEventRecord(H.ev_up[(size_t)k], H.s_up));
+        CUDA_TRY(c, cudaEventRecord(H.ev_up[(size_t)pos], H.s_up));
+        if (pos == H.halo_after) {
+            // every value a neighbour needs is on the device: pack / exchange / unpack on the exchange stream while the
+            // remaining uploads and the rows that read no ghost go on
+            CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, H.ev_up[(size_t)pos], 0));
+            rc = halo_exchange(c, true, false, true, c->comm_stream);
+            if (rc) return rc;
+            CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+        }
     }
     for (int i = 0; i < C; i++) {
         const int k = H.order[(size_t)i];
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)H.need_up[(size_t)k]], 0));
+        if (H.chunk_reads_ghost[(size_t)k]) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
         const int64_t b0 = H.cta_off[(size_t)k], b1 = H.cta_off[(size_t)k + 1];
         if (b1 > b0) {
             NbLaunch L = make_launch(c, H.d_iota + b0, b1 - b0, /*allow_grid=*/false);     // chunks are 128-row blocks of the staged tables
@@ -2340,6 +2385,7 @@ extern "C" int nb200_step_host(nb200_ctx* c, const double* f_in, double* f_out, 
     CUDA_TRY(c, cudaEventRecord(H.ev_dn, H.s_dn));
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_dn, 0));      // the context stream is the fence for callers
     CUDA_TRY(c, cudaStreamWaitEvent(c->stream, H.ev_up[(size_t)C - 1], 0));
+    if (multi && H.halo_after >= 0) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
     c->cur[0] ^= 1;
     c->grid_valid[0] = false;
     CUDA_TRY(c, cudaGetLastError());

@@ -14,11 +14,13 @@ from natrium_b200 import Context, harness, _capi  # noqa: E402
 from natrium_b200.stencils import Stencil          # noqa: E402
 
 
-def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, with_g, steps=6, grid=False, walls=None):
+def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, with_g, steps=6, grid=False, walls=None, host_chunks=0):
     """grid: the host numbers its DoFs cell by cell and gives the structure hint (TMA box kernels, ghost values also land in
     the grid copies); otherwise lexicographic numbering + the internal order hint (staged kernels).
     walls: per-axis flags -> ThermalBounceBack(0.85) walls + EXACT_DIFFERENCE force (D3Q45 f+g): the reference's order
-    stream(f) -> hits on f and g -> exchange g -> stream(g) -> collide across ranks."""
+    stream(f) -> hits on f and g -> exchange g -> stream(g) -> collide across ranks.
+    host_chunks > 0: the steps go through nb200_step_host with pinned host buffers and that many pipeline pieces (uploads of the
+    pieces that hold send values first, exchange behind them, rows that read ghosts behind the exchange)."""
     st = Stencil(name, scaling)
     verts = None
     if walls is not None:
@@ -73,7 +75,19 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
     else:
         f = harness.equilibrium_distributions(st, rho, u)
     ctx.upload_populations(0, f)
-    ctx.step(steps)
+    if host_chunks:
+        n_loc, Qn, Dn = host.n_owned if grid else part.n_owned, st.getQ(), st.getD()
+        bufs = [torch.empty((Qn, n_loc), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        mom = torch.empty((1 + Dn, n_loc), dtype=torch.float64, pin_memory=True)
+        bufs[0].numpy()[...] = f
+        l0 = ctx.kernel_launches()
+        for s_ in range(steps):
+            ctx.step_host(bufs[s_ & 1].data_ptr(), bufs[(s_ + 1) & 1].data_ptr(), mom.data_ptr(), mom.data_ptr() + 8 * n_loc, host_chunks)
+        ctx.synchronize()
+        assert ctx.kernel_launches() - l0 >= steps * host_chunks, "the pipelined path did not run"
+        assert np.array_equal(ctx.download_populations(0), bufs[steps & 1].numpy())
+    else:
+        ctx.step(steps)
     ctx.synchronize()
     cons = ctx.conserved()
     got = [ctx.download_populations(0)] + ([ctx.download_populations(1)] if with_g else [])
@@ -149,6 +163,9 @@ def main():
         ("grid-d3q19-p4", ("D3Q19", 3, [4, 2, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(grid=True)),
         ("grid-d2q25", ("D2Q25H", 2, [5, 3 * world], 2, 1.0, 0.01, 1.0, True), dict(grid=True)),
         ("grid-d3q45", ("D3Q45", 3, [2, 2, 2 * world], 2, 1.0, 0.01, 0.4, True), dict(steps=3, grid=True)),
+        # host-buffer steps across ranks: the chunk pipeline with the exchange inside (>= 2048 rows per rank to engage it)
+        ("hoststep-d3q19-p4", ("D3Q19", 3, [4, 4, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(host_chunks=4, steps=4)),
+        ("hoststep-cellnum", ("D3Q19", 3, [4, 4, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(host_chunks=3, steps=3, grid=True)),
         # walls across ranks (thermal hits rewrite g before it is exchanged and streamed), staged and grid kernels
         ("staged-walled", ("D3Q45", 3, [2, 3, 2 * world], 2, 1.0, 0.01, 0.4, True), dict(steps=3, walls=[False, True, False])),
         ("grid-walled", ("D3Q45", 3, [2, 3, 2 * world], 2, 1.0, 0.01, 0.4, True), dict(steps=3, grid=True, walls=[False, True, False])),
