@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--dedup-tol", type=float, default=1e-14, help="value tolerance of the dictionary format (library default)")
     ap.add_argument("--configs", default="c1,c3,c4,c5", help="other BASELINE configurations to time and gate after the headline (N = 1 only); '' = none")
     ap.add_argument("--no-gates", action="store_true", help="skip the GPU-vs-oracle parity gates")
+    ap.add_argument("--no-block-partition", action="store_true", help="N > 1: skip the block-partition side line")
     return ap.parse_args()
 
 
@@ -225,7 +226,8 @@ def initial_fields(c, st, x):
     raise ValueError(c["init"])
 
 
-def build_product(c, cells, length, local=0, rank=0, world=1, uid=None, grid="on", fmt="dict", tol=1e-14, numbering="cell", dof_order="none"):
+def build_product(c, cells, length, local=0, rank=0, world=1, uid=None, grid="on", fmt="dict", tol=1e-14, numbering="cell", dof_order="none",
+                  blocks=None):
     """One context for case c on a mesh of `cells` (the slab of this rank when world > 1): stencil, layout, hints, matrix,
     halo, wall hits, collision, initial populations.  The timed contexts and the gate contexts all come from here."""
     from natrium_b200 import Context, harness, _capi
@@ -235,7 +237,11 @@ def build_product(c, cells, length, local=0, rank=0, world=1, uid=None, grid="on
     dt = pb.timestep(st, c["cfl"])
     ctx = Context(local, rank, world, uid)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
-    part = harness.SlabPartition(pb, st, dt, rank, world)
+    if blocks is not None:      # block partition (Z-curve-like): the host numbers lexicographically inside its box, order hint, staged kernels
+        part = harness.BlockPartition(pb, st, dt, rank, blocks)
+        numbering, grid, dof_order = "lex", "off", "cell"
+    else:
+        part = harness.SlabPartition(pb, st, dt, rank, world)
     with_g = bool(c.get("with_g"))
     ctx.set_layout(part.n_owned, part.n_ghost, with_g)
     fmt_code = {"dict": _capi.FORMAT_DICT, "dict-unstaged": _capi.FORMAT_DICT_UNSTAGED, "ell": _capi.FORMAT_ELL}[fmt]
@@ -578,21 +584,24 @@ def run_side_config(key, args, local):
     return out
 
 
-def multirank_parity(args, rank, world, local, uid):
-    """N > 1: the slab-partitioned step (ghost exchange over NCCL, interior / boundary split) on a small mesh against the
-    single-domain oracle, gathered on rank 0."""
+BLOCKS_OF_WORLD = {2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}
+
+
+def multirank_parity(args, rank, world, local, uid, blocks=None):
+    """N > 1: the slab-partitioned (or, blocks given, block-partitioned) step (ghost exchange over NCCL, interior / boundary
+    split) on a small mesh against the single-domain oracle, gathered on rank 0."""
     import torch
     import torch.distributed as dist
     from natrium_b200 import harness
     c = case_spec("c2", args)
-    cells = [4, 4, 2 * world]
+    cells = [4, 4, 2 * world] if blocks is None else [2 * b for b in blocks]
     L = [2 * math.pi, 2 * math.pi, 2 * math.pi]
     from natrium_b200 import Context
     box = [Context.unique_id() if rank == 0 else None]          # a communicator of its own: an NCCL id is good for one
     dist.broadcast_object_list(box, src=0)
     uid = box[0]
     B = build_product(c, cells, L, local=local, rank=rank, world=world, uid=uid, grid=args.grid, fmt=args.format, tol=args.dedup_tol,
-                      numbering=args.numbering, dof_order=args.dof_order)
+                      numbering=args.numbering, dof_order=args.dof_order, blocks=blocks)
     ctx = B["ctx"]
     steps = 5
     ctx.step(steps)
@@ -611,8 +620,48 @@ def multirank_parity(args, rank, world, local, uid):
     for g, a in parts:
         full[:, g] = a
     err = float(np.max(np.abs(full - one) / np.maximum(np.abs(one), 1e-300)))
-    return {"mesh": "x".join(str(v) for v in cells) + " cells over " + str(world) + " slabs", "steps": steps, "max_rel_err": err,
-            "tolerance": 1e-11, "ok": bool(err <= 1e-11)}
+    return {"mesh": "x".join(str(v) for v in cells) + " cells over " + (str(world) + " slabs" if blocks is None else "x".join(str(b) for b in blocks) + " blocks"),
+            "steps": steps, "max_rel_err": err, "tolerance": 1e-11, "ok": bool(err <= 1e-11)}
+
+
+def block_partition_line(args, rank, world, local):
+    """N in {2, 4, 8}: the headline problem family on a block partition (2x1x1 / 2x2x1 / 2x2x2 blocks of 16^3 cells: up to 6
+    neighbours, edge ghosts, a cut across the x-fastest numbering) -- what the reference's p4est Z-curve partition looks like
+    (L/advection/SemiLagrangian.cpp:185-193) -- timed device-resident next to the slab headline, with its own parity gate."""
+    import torch
+    import torch.distributed as dist
+    from natrium_b200 import Context
+    blocks = BLOCKS_OF_WORLD[world]
+    c = case_spec("c2", args)
+    per = 16
+    cells = [per * b for b in blocks]
+    L = [2 * math.pi * b for b in blocks]
+    box = [Context.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    B = build_product(c, cells, L, local=local, rank=rank, world=world, uid=box[0], fmt=args.format, tol=args.dedup_tol, blocks=blocks)
+    ctx, st, pb, part = B["ctx"], B["st"], B["pb"], B["part"]
+    n_nbr = len(part.halo_plan()[0])
+
+    def barrier():
+        ctx.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    ctx.collide()
+    steps = max(20, min(args.steps, 500))
+    ms, _ = time_steps(ctx, steps, max(3, args.warmup), barrier)
+    t = torch.tensor([ms, float(n_nbr)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, max_nbr = float(t[0].item()), int(t[1].item())
+    cons = ctx.conserved()
+    info = ctx.matrix_format_info()
+    ctx.close()
+    parity = multirank_parity(args, rank, world, local, None, blocks=blocks)
+    if rank != 0:
+        return None
+    return {"workload": f"TGV3D D3Q19 BGK p={c['p']}, {'x'.join(str(b) for b in blocks)} blocks of {per}^3 cells ({pb.N} DoFs)", "blocks": blocks,
+            "max_neighbours": max_nbr, "ms_per_step": ms / steps, "steps": steps, "value": pb.N * st.getQ() * steps / (ms * 1e-3) / 1e6, "unit": UNIT,
+            "kernels": "staged dictionary kernels (no grid hint), interior / boundary split", "staged": info.get("staged"),
+            "conserved_finite": bool(np.isfinite(cons).all()), "parity": parity}
 
 
 def build_single_domain_oracle(c, cells, L, steps):
@@ -767,6 +816,12 @@ def run_ours(args):
             parity_mr = multirank_parity(args, rank, world, local, uid)
         except Exception as ex:
             parity_mr = {"ok": False, "error": str(ex)}
+    block_line = None
+    if world in BLOCKS_OF_WORLD and not args.no_block_partition:
+        try:
+            block_line = block_partition_line(args, rank, world, local)
+        except Exception as ex:       # every rank takes the same path up to its own failure; the line survives
+            block_line = {"error": str(ex)}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -793,7 +848,7 @@ def run_ours(args):
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "chunks": args.e2e_chunks,
                         "api": "nb200_step_host (pinned host buffers in and out every step)", "cpu_affinity_of_rank0": affinity},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
-                "parity_multirank": parity_mr, "configs": configs,
+                "parity_multirank": parity_mr, "partition_block": block_line, "configs": configs,
                 "n_dofs_global": n_global, "matrix_assembly_upload_s": B["t_asm"],
                 "conserved": [float(x) for x in cons]}
         print(json.dumps(line), flush=True)

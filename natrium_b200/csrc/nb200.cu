@@ -500,7 +500,7 @@ extern "C" int nb200_create(nb200_ctx** out, int device, int rank, int nranks, c
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaMalloc(&c->d_flag, sizeof(int)) != cudaSuccess || cudaMemset(c->d_flag, 0, sizeof(int)) != cudaSuccess) {
-        delete c;
+        nb200_destroy(c);       // releases whatever was created so far
         return NB200_ERR_CUDA;
     }
     if (nranks > 1) {
@@ -509,15 +509,15 @@ extern "C" int nb200_create(nb200_ctx** out, int device, int rank, int nranks, c
         // the exchange (and the boundary CTAs behind it) must not queue behind the interior kernel's ~16k CTAs
         if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_prev, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess) { delete c; return NB200_ERR_CUDA; }
+            cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess) { nb200_destroy(c); return NB200_ERR_CUDA; }
         {
             static const char* env = getenv("NB200_OVERLAP");      // experiments only: NB200_OVERLAP=0 serialises exchange and kernels
             c->overlap = !(env && env[0] == '0');
         }
-        if (!nccl_unique_id || !g_nccl.load(c->err)) { delete c; return NB200_ERR_NCCL; }
+        if (!nccl_unique_id || !g_nccl.load(c->err)) { nb200_destroy(c); return NB200_ERR_NCCL; }
         ncclUniqueId id;
         memcpy(&id, nccl_unique_id, sizeof(id));
-        if (g_nccl.CommInitRank(&c->comm, nranks, id, rank) != 0) { delete c; return NB200_ERR_NCCL; }
+        if (g_nccl.CommInitRank(&c->comm, nranks, id, rank) != 0) { c->comm = nullptr; nb200_destroy(c); return NB200_ERR_NCCL; }
     }
     *out = c;
     return NB200_OK;
@@ -583,7 +583,7 @@ extern "C" void nb200_destroy(nb200_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     free_blocks(c);
     free_matrix(c);
     free_grid(c);
@@ -600,8 +600,9 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     if (c->ev_prev) cudaEventDestroy(c->ev_prev);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
-    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -669,6 +670,15 @@ extern "C" int nb200_set_stencil(nb200_ctx* c, int D, int Q, const double* e_sca
             h.H4[i][11] = H4(i, 1, 1, 1, 2); h.H4[i][12] = H4(i, 0, 0, 1, 2); h.H4[i][13] = H4(i, 0, 1, 1, 2);
             h.H4[i][14] = H4(i, 0, 1, 2, 2);
         }
+    }
+    if (c->stride && (c->D != D || c->Q != Q)) {
+        // buffers, matrix and tables were sized for the old stencil: the layout has to be declared again
+        CUDA_TRY(c, cudaSetDevice(c->device));
+        if (c->stream) CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        free_blocks(c); free_matrix(c); free_grid(c); free_filter(c);
+        c->stride = 0;
+        c->n_owned = c->n_ghost = 0;
+        c->matrix_ready = false;
     }
     c->D = D; c->Q = Q;
     c->stencil_set = true;
@@ -1254,12 +1264,24 @@ extern "C" int nb200_set_halo(nb200_ctx* c, int n_nbr, const int32_t* nbr_rank, 
     cudaFree(c->d_send_idx); cudaFree(c->d_sendbuf); cudaFree(c->d_recvbuf);
     c->d_send_idx = nullptr; c->d_sendbuf = c->d_recvbuf = nullptr;
     for (auto& pl : c->plans) { cudaFree(pl.d_send_segs); cudaFree(pl.d_recv_segs); pl = nb200_ctx::HaloPlan(); }
+    if (n_nbr > 0 && (!nbr_rank || !send_off || !recv_off)) return fail(c, NB200_ERR_ARG, "set_halo: null plan for %d neighbours", n_nbr);
     c->n_nbr = n_nbr;
+    c->hs.ready = false;
+    if (n_nbr == 0) {           // clears the plan; the arrays of a rank without neighbours may be null
+        c->nbr_rank.clear();
+        c->send_off.assign(1, 0);
+        c->recv_off.assign(1, 0);
+        c->send_idx_user.clear();
+        c->n_send = c->n_recv = 0;
+        if (c->n_ghost != 0) return fail(c, NB200_ERR_ARG, "set_halo: no neighbours but the layout has %lld ghosts", (long long)c->n_ghost);
+        return NB200_OK;
+    }
     c->nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
     c->send_off.assign(send_off, send_off + n_nbr + 1);
     c->recv_off.assign(recv_off, recv_off + n_nbr + 1);
-    c->n_send = n_nbr ? send_off[n_nbr] : 0;
-    c->n_recv = n_nbr ? recv_off[n_nbr] : 0;
+    c->n_send = send_off[n_nbr];
+    c->n_recv = recv_off[n_nbr];
+    if (c->n_send > 0 && !send_idx) return fail(c, NB200_ERR_ARG, "set_halo: null send indices");
     if (c->n_recv != c->n_ghost) return fail(c, NB200_ERR_ARG, "set_halo: recv plan covers %lld ghosts, layout has %lld", (long long)c->n_recv, (long long)c->n_ghost);
     for (int k = 0; k < n_nbr; k++)
         if (nbr_rank[k] < 0 || nbr_rank[k] >= c->nranks || nbr_rank[k] == c->rank) return fail(c, NB200_ERR_ARG, "set_halo: bad neighbour rank");

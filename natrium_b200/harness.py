@@ -297,11 +297,152 @@ class SlabPartition:
         return np.array(dims, dtype=np.int32), np.ascontiguousarray(coords, dtype=np.int32)
 
 
+class BlockPartition:
+    """px x py (x pz) blocks of cells -- what a p4est Z-curve partition of a regular mesh gives on 4 or 8 ranks
+    (SemiLagrangian.cpp:185-193 iterates the locally owned cells of such a partition): up to 3^dim - 1 neighbours, edge and
+    corner ghosts.  A DoF belongs to the rank that owns the first cell (lexicographic) that sees it, axis by axis, so the
+    owned set is a box of the DoF grid; local order of the owned DoFs is lexicographic inside the box (x fastest), ghosts
+    follow grouped by owner rank (ascending), inside a rank by global id."""
+
+    def __init__(self, problem, stencil, dt, rank, blocks):
+        self.pb, self.rank, self.blocks = problem, rank, list(blocks)
+        dim = problem.dim
+        assert len(self.blocks) == dim
+        self.nranks = int(np.prod(self.blocks))
+        self._stencil, self._dt = stencil, dt
+        # per-axis owner of every 1-d DoF index
+        self.axis_owner = []
+        for d in range(dim):
+            ax = problem.axes[d]
+            if self.blocks[d] > ax.n:
+                raise ValueError("more blocks than cells along an axis")
+            bounds = [(ax.n * r) // self.blocks[d] for r in range(self.blocks[d] + 1)]
+            cell_owner = np.zeros(ax.n, dtype=np.int64)
+            for r in range(self.blocks[d]):
+                cell_owner[bounds[r]:bounds[r + 1]] = r
+            self.axis_owner.append(cell_owner[ax.home])
+        self._tracks = [{float(-dt * e[d]): problem.axes[d].track(float(-dt * e[d])) for e in stencil.getDirections()[1:]} for d in range(dim)]
+        self.own_axes = self._own_axes(rank)
+        self.owned_gids = self._box_ids(self.own_axes)
+        self.n_owned = len(self.owned_gids)
+        self.ghost_gids = self._ghosts_of(rank)
+        self.n_ghost = len(self.ghost_gids)
+        self.g2l = np.full(problem.N, -1, dtype=np.int64)
+        self.g2l[self.owned_gids] = np.arange(self.n_owned)
+        self.g2l[self.ghost_gids] = self.n_owned + np.arange(self.n_ghost)
+
+    # rank <-> block coordinates, x fastest
+    def _coords_of(self, r):
+        out = []
+        for d in range(self.pb.dim):
+            out.append(r % self.blocks[d])
+            r //= self.blocks[d]
+        return out
+
+    def _own_axes(self, r):
+        rc = self._coords_of(r)
+        return [np.nonzero(self.axis_owner[d] == rc[d])[0] for d in range(self.pb.dim)]
+
+    def _box_ids(self, idx):
+        """global ids of the tensor product of per-axis index arrays, lexicographic (x fastest)"""
+        nd = self.pb.nd
+        if self.pb.dim == 2:
+            return (idx[1][:, None] * nd[0] + idx[0][None, :]).reshape(-1)
+        return ((idx[2][:, None, None] * nd[1] + idx[1][None, :, None]) * nd[0] + idx[0][None, None, :]).reshape(-1)
+
+    def owner_of(self, gids):
+        nd, dim = self.pb.nd, self.pb.dim
+        g = np.asarray(gids, dtype=np.int64)
+        ix = [g % nd[0], (g // nd[0]) % nd[1]] + ([g // (nd[0] * nd[1])] if dim == 3 else [])
+        r, mul = np.zeros_like(g), 1
+        for d in range(dim):
+            r = r + self.axis_owner[d][ix[d]] * mul
+            mul *= self.blocks[d]
+        return r
+
+    def _ghosts_of(self, r):
+        own = self._own_axes(r)
+        read = []
+        for e in self._stencil.getDirections()[1:]:
+            per_axis = [np.unique(self._tracks[d][float(-self._dt * e[d])][0][own[d]]) for d in range(self.pb.dim)]
+            read.append(self._box_ids(per_axis))
+        read = np.unique(np.concatenate(read))
+        gh = read[self.owner_of(read) != r]
+        return gh[np.lexsort((gh, self.owner_of(gh)))]
+
+    def halo_plan(self):
+        """(nbr_rank, send_off, send_idx, recv_off) for nb200_set_halo."""
+        mine = self.owner_of(self.ghost_gids)
+        theirs = {r: self._ghosts_of(r) for r in range(self.nranks) if r != self.rank}
+        needs_me = {r: g[self.owner_of(g) == self.rank] for r, g in theirs.items()}
+        nbrs = sorted(set(mine.tolist()) | {r for r, g in needs_me.items() if len(g)})
+        send_off, recv_off, send_idx = [0], [0], []
+        for r in nbrs:
+            send_idx.append(self.g2l[needs_me[r]])
+            send_off.append(send_off[-1] + len(needs_me[r]))
+            recv_off.append(recv_off[-1] + int(np.sum(mine == r)))
+        send_idx = np.concatenate(send_idx).astype(np.int32) if send_idx else np.zeros(0, dtype=np.int32)
+        return (np.array(nbrs, dtype=np.int32), np.array(send_off, dtype=np.int64), send_idx, np.array(recv_off, dtype=np.int64))
+
+    def owned_global_ids(self):
+        return self.owned_gids
+
+    def owned_points(self):
+        ax = self.pb.axes
+        grids = np.meshgrid(*[ax[d].x[self.own_axes[d]] for d in range(self.pb.dim)][::-1], indexing="ij")[::-1]
+        return np.stack([g.reshape(-1) for g in grids], axis=1)
+
+    def cell_blocked_order(self):
+        """Owned local DoF indices cell by cell (own cells lexicographic, first visit wins): nb200_set_dof_order input."""
+        pb, p, dim = self.pb, self.pb.p, self.pb.dim
+        rc = self._coords_of(self.rank)
+        loc = np.arange(p + 1, dtype=np.int64)
+        cells = []
+        for d in range(dim):
+            n = pb.axes[d].n
+            cells.append(np.arange((n * rc[d]) // self.blocks[d], (n * (rc[d] + 1)) // self.blocks[d], dtype=np.int64))
+        g = [cells[d][:, None] * p + loc[None, :] for d in range(dim)]         # (cells_d, p+1) 1-d DoF indices
+        nd = pb.nd
+        if dim == 2:
+            ids = g[1][:, None, :, None] * nd[0] + g[0][None, :, None, :]
+        else:
+            ids = (g[2][:, None, None, :, None, None] * nd[1] + g[1][None, :, None, None, :, None]) * nd[0] + g[0][None, None, :, None, None, :]
+        loc_ids = self.g2l[ids.reshape(-1)]
+        loc_ids = loc_ids[(loc_ids >= 0) & (loc_ids < self.n_owned)]
+        uniq, first = np.unique(loc_ids, return_index=True)
+        order = uniq[np.argsort(first, kind="stable")]
+        assert len(order) == self.n_owned
+        return order.astype(np.int32)
+
+    def dense_direction(self, alpha):
+        """(col, val), shape (owned rows, k): columns in local numbering, entries in (z, y, x) order"""
+        pb, dim = self.pb, self.pb.dim
+        e = self._stencil.getDirection(alpha)
+        tr = [self._tracks[d][float(-self._dt * e[d])] for d in range(dim)]
+        c = [tr[d][0][self.own_axes[d]] for d in range(dim)]
+        w = [tr[d][1][self.own_axes[d]] for d in range(dim)]
+        nd = pb.nd
+        if dim == 2:
+            col = c[1][:, None, :, None] * nd[0] + c[0][None, :, None, :]
+            val = w[0][None, :, None, :] * w[1][:, None, :, None]
+        else:
+            col = (c[2][:, None, None, :, None, None] * nd[1] + c[1][None, :, None, None, :, None]) * nd[0] + c[0][None, None, :, None, None, :]
+            val = (w[0][None, None, :, None, None, :] * w[1][None, :, None, None, :, None]) * w[2][:, None, None, :, None, None]
+        k = int(np.prod(col.shape[dim:]))
+        rows = int(np.prod(col.shape[:dim]))
+        col = self.g2l[np.broadcast_to(col, val.shape).reshape(rows, k)]
+        if (col < 0).any():
+            raise RuntimeError("a row reads a DoF that is neither owned nor a ghost")
+        return np.ascontiguousarray(col), np.ascontiguousarray(val.reshape(rows, k))
+
+
 # ------------------------------------------------------------------------------------------
 # streaming matrix
 # ------------------------------------------------------------------------------------------
 def _dense_direction(problem, part, stencil, dt, alpha):
     """(col, val) of shape (owned rows, k): the periodic tensor-product row of every owned DoF, entries in (z, y, x) order."""
+    if isinstance(part, BlockPartition):
+        return part.dense_direction(alpha)
     e = stencil.getDirection(alpha)
     dim = problem.dim
     tr = [problem.axes[d].track(float(-dt * e[d])) for d in range(dim)]

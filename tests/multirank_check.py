@@ -14,7 +14,7 @@ from natrium_b200 import Context, harness, _capi  # noqa: E402
 from natrium_b200.stencils import Stencil          # noqa: E402
 
 
-def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, with_g, steps=6, grid=False, walls=None, host_chunks=0):
+def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, with_g, steps=6, grid=False, walls=None, host_chunks=0, blocks=None):
     """grid: the host numbers its DoFs cell by cell and gives the structure hint (TMA box kernels, ghost values also land in
     the grid copies); otherwise lexicographic numbering + the internal order hint (staged kernels).
     walls: per-axis flags -> ThermalBounceBack(0.85) walls + EXACT_DIFFERENCE force (D3Q45 f+g): the reference's order
@@ -28,7 +28,9 @@ def run_case(rank, world, local, uid, name, dim, cells, p, scaling, nu, cfl, wit
         verts = [np.linspace(0, 2.0, cells[0] + 1), 1.0 * (y - 0.8 * np.sin(2 * np.pi * y) / (2 * np.pi)), np.linspace(0, 2.0, cells[2] + 1)]
     pb = harness.CartesianProblem(dim, cells, p, verts=verts)
     dt = pb.timestep(st, cfl)
-    part = harness.SlabPartition(pb, st, dt, rank, world)
+    # blocks: a block partition (2 x 1 x 1 on 2 ranks cuts ACROSS the x-fastest numbering, 2 x 2 x 1 / 2 x 2 x 2 on 4 / 8 ranks
+    # give 3 / 6 neighbours with edge ghosts) instead of slabs along the last axis
+    part = harness.BlockPartition(pb, st, dt, rank, blocks) if blocks is not None else harness.SlabPartition(pb, st, dt, rank, world)
     ctx = Context(local, rank, world, uid)
     ctx.set_stencil(st.getDirections(), st.getWeights(), st.getScaling(), st.getSpeedOfSoundSquare())
     ctx.set_layout(part.n_owned, part.n_ghost, with_g)
@@ -163,6 +165,10 @@ def main():
         ("grid-d3q19-p4", ("D3Q19", 3, [4, 2, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(grid=True)),
         ("grid-d2q25", ("D2Q25H", 2, [5, 3 * world], 2, 1.0, 0.01, 1.0, True), dict(grid=True)),
         ("grid-d3q45", ("D3Q45", 3, [2, 2, 2 * world], 2, 1.0, 0.01, 0.4, True), dict(steps=3, grid=True)),
+        # block partition: staged kernels, exchange with every neighbour the partition has
+        ("block-d3q19", ("D3Q19", 3, [4, 4, 4], 2, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False),
+         dict(blocks={2: [2, 1, 1], 4: [2, 2, 1], 8: [2, 2, 2]}.get(world))),
+        ("block-d2q25", ("D2Q25H", 2, [6, 6], 2, 1.0, 0.01, 1.0, True), dict(blocks={2: [2, 1], 4: [2, 2], 8: [4, 2]}.get(world))),
         # host-buffer steps across ranks: the chunk pipeline with the exchange inside (>= 2048 rows per rank to engage it)
         ("hoststep-d3q19-p4", ("D3Q19", 3, [4, 4, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(host_chunks=4, steps=4)),
         ("hoststep-cellnum", ("D3Q19", 3, [4, 4, 2 * world], 4, np.sqrt(3) / 0.05, 2 * np.pi, 0.4, False), dict(host_chunks=3, steps=3, grid=True)),
@@ -174,6 +180,8 @@ def main():
     ok = True
     for label, a, kw in cases:
         if only and label not in only:
+            continue
+        if label.startswith("block-") and kw.get("blocks") is None:
             continue
         if rank == 0:
             print(f"case {label} ...", flush=True)
