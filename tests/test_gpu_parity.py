@@ -1358,6 +1358,7 @@ def test_conserved_moments_1000_steps_3d(case, with_grid, oracle_lib):
         return np.array([rho.sum(), m[0].sum(), m[1].sum(), m[2].sum(), en])
 
     done = 0
+    en0 = abs(sums(f, g)[4])
     for target in (1, 10, 100, 1000):
         ctx.step(target - done)
         for _ in range(target - done):
@@ -1365,7 +1366,9 @@ def test_conserved_moments_1000_steps_3d(case, with_grid, oracle_lib):
         done = target
         got, ref = ctx.conserved(), sums(f, g)
         assert abs(got[0] - ref[0]) <= TOL_CONS * abs(ref[0]), (target, got, ref)
-        assert abs(got[4] - ref[4]) <= 1e-11 * abs(ref[4]), (target, got, ref)
+        # the f-only case is a viscous Taylor-Green vortex at Re = 1: its kinetic energy decays by ten orders of magnitude
+        # over the run, so the energy is compared on the scale it started from
+        assert abs(got[4] - ref[4]) <= 1e-11 * max(abs(ref[4]), en0), (target, got, ref)
         scale = np.abs(e).max() * ref[0]
         assert np.max(np.abs(got[1:4] - ref[1:4])) <= TOL_CONS * scale, (target, got, ref)
         assert rel_err(ctx.download_populations(0), f) <= 1e-9, target
