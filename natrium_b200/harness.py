@@ -670,12 +670,25 @@ class CellNumbering:
         return rowptr2, col2, val2
 
 
-def upload_streaming_matrix(ctx, problem, part, stencil, dt, numbering=None):
+def row_noise(val, alpha, eps):
+    """Worst-case input for the device format: every stored value gets its own relative perturbation (deterministic,
+    |.| <= eps), so that no two rows of the matrix share a weight pattern -- what an unstructured mesh gives.  Applied to the
+    lexicographic-numbering CSR of direction alpha, before any renumbering, by the product and the checker alike."""
+    k = np.arange(len(val), dtype=np.uint64) + np.uint64(alpha) * np.uint64(0x9E3779B97F4A7C15)
+    k ^= k >> np.uint64(31); k *= np.uint64(0xBF58476D1CE4E5B9); k ^= k >> np.uint64(29)
+    u = (k >> np.uint64(11)).astype(np.float64) / float(1 << 53)              # [0, 1)
+    return val * (1.0 + eps * (2.0 * u - 1.0))
+
+
+def upload_streaming_matrix(ctx, problem, part, stencil, dt, numbering=None, noise=0.0):
     """Assemble and hand over all diagonal blocks one at a time (peak host memory = one block).
-    numbering: a CellNumbering of ``part`` -- rows and owned columns are renumbered before the upload."""
+    numbering: a CellNumbering of ``part`` -- rows and owned columns are renumbered before the upload.
+    noise > 0: row_noise on every block (worst-case matrix for the device format)."""
     nnz = 0
     for alpha in range(1, stencil.getQ()):
         rowptr, col, val = assemble_direction(problem, part, stencil, dt, alpha)
+        if noise > 0.0:
+            val = row_noise(val, alpha, noise)
         if numbering is not None:
             rowptr, col, val = numbering.renumber_csr(rowptr, col, val)
         ctx.upload_block_csr(alpha - 1, alpha - 1, rowptr, col, val)
