@@ -765,22 +765,39 @@ def run_ours(args):
     bufs = [hf_a, hf_b]
     rho_ptr, u_ptr = hmom.data_ptr(), hmom.data_ptr() + 8 * n
 
-    def e2e_step(i):
-        ctx.step_host(bufs[i & 1].data_ptr(), bufs[(i + 1) & 1].data_ptr(), rho_ptr, u_ptr, args.e2e_chunks)
+    e2e_chunks = args.e2e_chunks
 
-    e2e_step(0)
-    e2e_step(1)
-    barrier()
-    ctx.timer_start()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    ms_e2e = ctx.timer_stop()
-    barrier()
+    def e2e_step(i):
+        ctx.step_host(bufs[i & 1].data_ptr(), bufs[(i + 1) & 1].data_ptr(), rho_ptr, u_ptr, e2e_chunks)
+
+    def e2e_time(n_steps):
+        e2e_step(0)
+        e2e_step(1)
+        barrier()
+        ctx.timer_start()
+        for i in range(n_steps):
+            e2e_step(i)
+        ms_ = ctx.timer_stop()
+        barrier()
+        if world > 1:
+            t_ = torch.tensor([ms_], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_
+
+    e2e_probe = None
+    if world > 1 and args.e2e_chunks > 1:
+        # n_chunks is the caller's knob (include/natrium_b200.h): with several GPUs under one host the duplex chunk pipeline and
+        # the sequential legs load the PCIe root / host memory differently, so a short probe of both picks the setting that is
+        # then timed (every rank sees the same all-reduced times and takes the same branch)
+        e2e_probe = {}
+        for ch in (args.e2e_chunks, 1):
+            e2e_chunks = ch
+            e2e_probe[str(ch)] = e2e_time(2) / 2
+        e2e_chunks = min(e2e_probe, key=e2e_probe.get)
+        e2e_chunks = int(e2e_chunks)
+    ms_e2e = e2e_time(e2e_steps)
     assert np.isfinite(hmom.numpy()).all() and np.isfinite(bufs[e2e_steps & 1].numpy()).all()
-    if world > 1:
-        t = torch.tensor([ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
     e2e_val = n_global * Q * e2e_steps / (ms_e2e * 1e-3) / 1e6
     h2d = Q * n * 8
     d2h = Q * n * 8 + (1 + D) * n * 8
@@ -851,7 +868,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "chunks": args.e2e_chunks,
+                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "chunks": e2e_chunks, "chunks_probe_ms_per_step": e2e_probe,
                         "api": "nb200_step_host (pinned host buffers in and out every step)", "cpu_affinity_of_rank0": affinity},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_base, "parity": parity,
                 "parity_multirank": parity_mr, "partition_block": block_line, "configs": configs,

@@ -45,6 +45,9 @@ struct Grid {
     int64_t nxp = 0;               // padded x pitch (even, so that rows are 16-byte aligned)
     int64_t G = 0;                 // nxp * n[1] * n[2]
     int fe_order = 0;
+    int xshift = 0;                // the host's x coordinates were shifted by this much when the grid was declared (cell faces sit
+                                   // at xshift + multiples of p): 1 makes the x origin of every whole-cell half-tile even, which a
+                                   // TMA store of the half-tile into the grid copy needs (16-byte aligned inner coordinate)
     std::vector<int32_t> gidx_of_int;   // [n_owned + n_ghost] internal canonical index -> flat grid index
     int64_t flat(int x, int y, int z) const { return ((int64_t)z * n[1] + y) * nxp + x; }
     void unflat(int64_t g, int c[3]) const
@@ -103,6 +106,9 @@ struct Tables {
     std::vector<int32_t> box_vol;                 // [n_dirs] doubles per box, rounded up to 16 (128-byte smem alignment)
     std::vector<int16_t> off_table;               // [n_dirs][max_k] offset of entry k relative to entry 0 inside a box
     std::vector<uint8_t> tile_reads_ghost;        // [n_tiles]
+    std::vector<int16_t> tile_store;              // [n_tiles][4]: grid origin (x, y, z) of the tile's first half, bit h of [3] = half h
+                                                  // may be written to the grid copy as ONE box (TMA store) instead of per thread
+    int half_dims[3] = {1, 1, 1};                 // box of a half-tile
     int64_t generic_rows = 0, grid_rows = 0, total_boxes = 0, max_pass_doubles = 0;
 };
 
@@ -143,13 +149,20 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
     const int half_rows = rows_per_tile / 2;
     // tiles are aligned to cells: cell c of an axis owns coordinates 1 + c p .. (c + 1) p (coordinate 0 belongs to the
     // first cell), so tiles start at coordinate 1 - tile length (a thin first tile that only holds coordinate 0)
-    const int org0 = g.fe_order > 0 ? 1 : 0;
+    const int org[3] = {(g.fe_order > 0 ? 1 : 0) + g.xshift, g.fe_order > 0 ? 1 : 0, g.fe_order > 0 ? 1 : 0};
     const int tl[3] = {2 * h[0], h[1], h[2]};
     int nt[3];
     for (int a = 0; a < 3; a++) {
         if (a >= g.dim) { nt[a] = 1; continue; }
-        nt[a] = (g.n[a] - org0 + tl[a] - 1) / tl[a] + (org0 ? 1 : 0);
+        nt[a] = (g.n[a] - org[a] + tl[a] - 1) / tl[a] + (org[a] ? 1 : 0);
     }
+    for (int a = 0; a < 3; a++) T.half_dims[a] = a < g.dim ? h[a] : 1;
+    // grid points that hold a local DoF at all (owned or ghost): a box store may run over the others (padding), never over a
+    // ghost or over a row of another tile
+    std::vector<uint8_t> has_dof((size_t)g.G, 0);
+    for (int32_t f : g.gidx_of_int) if (f >= 0) has_dof[(size_t)f] = 1;
+    const bool store_shape_ok = (h[0] * 8) % 16 == 0 && half_rows >= h[0] * h[1] * h[2];
+    T.tile_store.clear();
     // grid point -> canonical row (owned only)
     std::vector<int32_t> row_of_g((size_t)g.G, -1);
     for (int64_t i = 0; i < n_owned; i++) row_of_g[(size_t)g.gidx_of_int[(size_t)i]] = (int32_t)i;
@@ -160,8 +173,8 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
     for (int tz = 0; tz < nt[2]; tz++)
         for (int ty = 0; ty < nt[1]; ty++)
             for (int tx = 0; tx < nt[0]; tx++) {
-                int o[3] = {org0 + (tx - (org0 ? 1 : 0)) * tl[0], g.dim > 1 ? org0 + (ty - (org0 ? 1 : 0)) * tl[1] : 0,
-                            g.dim > 2 ? org0 + (tz - (org0 ? 1 : 0)) * tl[2] : 0};
+                int o[3] = {org[0] + (tx - (org[0] ? 1 : 0)) * tl[0], g.dim > 1 ? org[1] + (ty - (org[1] ? 1 : 0)) * tl[1] : 0,
+                            g.dim > 2 ? org[2] + (tz - (org[2] ? 1 : 0)) * tl[2] : 0};
                 int32_t rows[256], gi[256];
                 bool any = false;
                 for (int t = 0; t < rows_per_tile; t++) {
@@ -180,6 +193,26 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
                     }
                 }
                 if (!any) continue;
+                {   // which halves can go to the grid copy as one box
+                    int flags = 0;
+                    for (int hf = 0; hf < 2 && store_shape_ok; hf++) {
+                        const int bx0 = o[0] + hf * h[0];
+                        if (bx0 & 1) continue;                               // TMA: even inner coordinate
+                        bool ok = true, some = false;
+                        for (int tt = 0; tt < h[0] * h[1] * h[2] && ok; tt++) {
+                            const int c[3] = {bx0 + tt % h[0], o[1] + (tt / h[0]) % h[1], o[2] + tt / (h[0] * h[1])};
+                            if (c[0] < 0 || c[0] >= g.n[0] || c[1] < 0 || c[1] >= g.n[1] || c[2] < 0 || c[2] >= g.n[2]) continue;   // clipped by the copy
+                            if (c[0] >= g.nxp) { ok = false; break; }
+                            const int64_t f = g.flat(c[0], c[1], c[2]);
+                            if (rows[hf * half_rows + tt] >= 0) some = true;
+                            else if (has_dof[(size_t)f]) ok = false;        // a ghost (or nothing of ours): leave it alone
+                        }
+                        // points of the box between n[0] and the padded pitch are written too (harmless: never read as values)
+                        if (ok && some) flags |= 1 << hf;
+                    }
+                    const int16_t rec[4] = {(int16_t)o[0], (int16_t)o[1], (int16_t)o[2], (int16_t)flags};
+                    T.tile_store.insert(T.tile_store.end(), rec, rec + 4);
+                }
                 T.tile_row.insert(T.tile_row.end(), rows, rows + rows_per_tile);
                 T.tile_gidx.insert(T.tile_gidx.end(), gi, gi + rows_per_tile);
                 TileGeo tg; tg.o[0] = o[0]; tg.o[1] = o[1]; tg.o[2] = o[2];
