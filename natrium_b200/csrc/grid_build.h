@@ -198,6 +198,9 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
                     for (int hf = 0; hf < 2 && store_shape_ok; hf++) {
                         const int bx0 = o[0] + hf * h[0];
                         if (bx0 & 1) continue;                               // TMA: even inner coordinate
+                        // boxes that stick out of the grid copy are left to the threads (the copy would clip them, but only whole
+                        // boxes are worth the special case: they are all but a surface layer of the tiles)
+                        if (bx0 < 0 || bx0 + h[0] > g.nxp || o[1] < 0 || o[1] + h[1] > g.n[1] || o[2] < 0 || o[2] + h[2] > g.n[2]) continue;
                         bool ok = true, some = false;
                         for (int tt = 0; tt < h[0] * h[1] * h[2] && ok; tt++) {
                             const int c[3] = {bx0 + tt % h[0], o[1] + (tt / h[0]) % h[1], o[2] + tt / (h[0] * h[1])};

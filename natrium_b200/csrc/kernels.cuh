@@ -308,6 +308,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     extern __shared__ __align__(128) double smem_grid[];
     __shared__ uint64_t mbar[3];
     __shared__ int cnt[2];
+    __shared__ int s_tflags;
     __shared__ int32_t srow[NB_CTA_ROWS];
     double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);    // [Q][128]
     double* xs = smem_grid + Q * NB_CTA_ROWS;                                               // [2][NB_GRID_CAP]
@@ -323,6 +324,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
         nb_mbar_init(&mbar[1], 1);
         nb_mbar_init(&mbar[2], 1);
         cnt[0] = cnt[1] = 0;
+        s_tflags = A.tile_store ? (int)__ldg(reinterpret_cast<const short*>(A.tile_store) + tl * 4 + 3) : 0;
         nb_mbar_fence_init();
     }
     __syncthreads();
@@ -359,21 +361,39 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
         nb_grid_release<1>(A, p, p1, buf, tid & 31, cnt, xs, xs, NB_GRID_CAP, mbar);
     }
     __syncthreads();          // results of a row come from the other half of the CTA
-    if (!active) return;
-    double f[Q];
+    // a half-tile of whole cells is a box of the grid copy: where the builder allows it the half goes out as ONE TMA store per
+    // population from the tile in shared memory instead of 32-byte pieces from every thread (6 store wavefronts per warp and
+    // population on the L1 data pipe); the canonical array is written by the threads either way (contiguous rows)
+    if (active) {
+        double f[Q];
 #pragma unroll
-    for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
-    double rho, v[3] = {0.0, 0.0, 0.0};
-    if (nb_collide_f<D, Q, EQ>(f, rho, v, false, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
-    const int64_t gi = __ldg(A.tile_gidx + slot);
+        for (int q = 0; q < Q; q++) f[q] = tile[q][tid];
+        double rho, v[3] = {0.0, 0.0, 0.0};
+        if (nb_collide_f<D, Q, EQ>(f, rho, v, false, EQ == NB_KIND_MRT_ENTROPIC ? rho_out[row] : 1.0)) *flag = 1;
+        // second copy: into the tile (box store below) or straight into the grid copy
+        double* __restrict__ y2 = ((s_tflags >> half) & 1) ? &tile[0][tid] : ygrid + __ldg(A.tile_gidx + slot);
+        const int64_t pitch2 = ((s_tflags >> half) & 1) ? (int64_t)NB_CTA_ROWS : A.gstride;
 #pragma unroll
-    for (int q = 0; q < Q; q++) {
-        y[(int64_t)q * A.stride + row] = f[q];
-        ygrid[(int64_t)q * A.gstride + gi] = f[q];
+        for (int q = 0; q < Q; q++) {
+            y[(int64_t)q * A.stride + row] = f[q];
+            y2[(int64_t)q * pitch2] = f[q];
+        }
+        rho_out[row] = rho;
+#pragma unroll
+        for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = v[j];
     }
-    rho_out[row] = rho;
-#pragma unroll
-    for (int j = 0; j < D; j++) u_out[(int64_t)j * A.n_owned + row] = v[j];
+    if (s_tflags) {           // uniform over the CTA
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tile writes above, before the async-proxy reads
+        __syncthreads();
+        if (t0 == 0 && ((s_tflags >> half) & 1)) {
+            const short4 ts = __ldg(A.tile_store + tl);
+            const int bx = (int)ts.x + half * A.half_x;
+#pragma unroll 1
+            for (int q = 0; q < Q; q++)
+                nb_tma_store_3d(reinterpret_cast<const char*>(A.tmap_out_f) + 128 * q, &tile[q][half * (NB_CTA_ROWS / 2)], bx, (int)ts.y, (int)ts.z);
+            nb_tma_store_commit_and_wait();
+        }
+    }
 }
 
 // f + g: both distributions staged by the same boxes; [tile f][tile g][2 buffers f][2 buffers g]

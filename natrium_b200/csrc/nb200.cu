@@ -153,7 +153,11 @@ struct nb200_ctx {
     int2* d_gdesc = nullptr;
     NbGridPass* d_gpass = nullptr;
     NbGridBox* d_gbox = nullptr;
-    void* d_tmaps = nullptr;                 // [which][buffer][(Q-1)] CUtensorMap (128 bytes each)
+    void* d_tmaps = nullptr;                 // [which][buffer][(Q-1)] CUtensorMap (128 bytes each) of the box loads, then
+                                             // [which][buffer][Q] maps (box = one half-tile) for the box stores
+    int16_t* d_tile_store = nullptr;         // [n_tiles][4] (grid_build.h: Tables::tile_store)
+    int grid_half_x = 1;
+    int64_t grid_store_halves = 0;
     std::vector<int16_t> grid_off;           // [(Q-1)][NB_GRID_MAXK] host copy of the offset table in BYTES (constant memory of the unit)
     int32_t *d_gtile_interior = nullptr, *d_gtile_boundary = nullptr;
     int64_t n_gtile_interior = 0, n_gtile_boundary = 0;
@@ -560,6 +564,9 @@ static void free_matrix(nb200_ctx* c)
     cudaFree(c->d_gbox); cudaFree(c->d_tmaps); cudaFree(c->d_gtile_interior); cudaFree(c->d_gtile_boundary);
     c->d_tile_row = c->d_tile_gidx = c->d_tile_pass = nullptr; c->d_gdesc = nullptr; c->d_gpass = nullptr; c->d_gbox = nullptr;
     c->d_tmaps = nullptr; c->d_gtile_interior = c->d_gtile_boundary = nullptr;
+    cudaFree(c->d_tile_store);
+    c->d_tile_store = nullptr;
+    c->grid_store_halves = 0;
     c->grid_ready = false;
     c->n_tiles = c->gdesc_stride = c->n_gtile_interior = c->n_gtile_boundary = 0;
     c->matrix_ready = false;
@@ -770,7 +777,10 @@ extern "C" int nb200_set_dof_grid(nb200_ctx* c, int dim, const int32_t* dims, co
     nbgrid::Grid& g = c->grid;
     g.dim = dim;
     g.fe_order = fe_order;
-    for (int j = 0; j < 3; j++) g.n[j] = j < dim ? dims[j] : 1;
+    // with cells declared, the grid copy keeps one empty column in front of x = 0: the x origin of every whole-cell half-tile
+    // becomes even, so that a half-tile can be stored into the copy as one TMA box (grid_build.h)
+    g.xshift = fe_order > 0 ? 1 : 0;
+    for (int j = 0; j < 3; j++) g.n[j] = j < dim ? dims[j] + (j == 0 ? g.xshift : 0) : 1;
     for (int j = 0; j < dim; j++) if (g.n[j] < 1 || g.n[j] > 32000) return fail(c, NB200_ERR_ARG, "set_dof_grid: grid dimension %d out of range", (int)g.n[j]);
     g.nxp = (g.n[0] + 1) & ~1;
     g.G = g.nxp * g.n[1] * g.n[2];
@@ -783,10 +793,11 @@ extern "C" int nb200_set_dof_grid(nb200_ctx* c, int dim, const int32_t* dims, co
         int cc[3] = {0, 0, 0};
         for (int j = 0; j < dim; j++) {
             cc[j] = coords[u * dim + j];
-            if (cc[j] < 0 || cc[j] >= g.n[j]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: coordinate of DoF %lld outside the grid", (long long)u); }
+            if (cc[j] < 0 || cc[j] >= dims[j]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: coordinate of DoF %lld outside the grid", (long long)u); }
         }
+        cc[0] += g.xshift;
         const int64_t f = g.flat(cc[0], cc[1], cc[2]);
-        if (seen[(size_t)f]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: two DoFs at grid point (%d,%d,%d)", cc[0], cc[1], cc[2]); }
+        if (seen[(size_t)f]) { free_grid(c); return fail(c, NB200_ERR_ARG, "set_dof_grid: two DoFs at grid point (%d,%d,%d)", cc[0] - g.xshift, cc[1], cc[2]); }
         seen[(size_t)f] = 1;
         const int64_t i = (u < c->n_owned && c->has_order) ? c->perm[(size_t)u] : u;      // internal canonical index
         g.gidx_of_int[(size_t)i] = (int32_t)f;
@@ -961,8 +972,25 @@ static int upload_grid_tables(nb200_ctx* c, nbgrid::Tables& T)
         encode = (NbEncodeTiled)fn;
     }
     const int n_dist = c->with_g ? 2 : 1;
-    std::vector<CUtensorMap> maps((size_t)2 * 2 * nb);
+    std::vector<CUtensorMap> maps((size_t)2 * 2 * nb + (size_t)2 * 2 * c->Q);
     memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    for (int w = 0; w < n_dist; w++)
+        for (int b = 0; b < 2; b++)
+            for (int q = 0; q < c->Q; q++) {         // box stores: one half-tile of population q
+                const cuuint64_t gdim[3] = {(cuuint64_t)g.nxp, (cuuint64_t)g.n[1], (cuuint64_t)g.n[2]};
+                const cuuint64_t gstr[2] = {(cuuint64_t)g.nxp * 8, (cuuint64_t)g.nxp * g.n[1] * 8};
+                const cuuint32_t box[3] = {(cuuint32_t)T.half_dims[0], (cuuint32_t)T.half_dims[1], (cuuint32_t)T.half_dims[2]};
+                const cuuint32_t est[3] = {1, 1, 1};
+                void* base = c->gpop[w][b] + (int64_t)q * c->gstride;
+                CUresult r = encode(&maps[(size_t)(4 * nb + (w * 2 + b) * c->Q + q)], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, est,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {            // odd half-tile shapes: keep the per-thread stores
+                    for (size_t i = 3; i < T.tile_store.size(); i += 4) T.tile_store[i] = 0;
+                    w = n_dist; b = 2;
+                    break;
+                }
+            }
     for (int w = 0; w < n_dist; w++)
         for (int b = 0; b < 2; b++)
             for (int a = 0; a < nb; a++) {
@@ -983,6 +1011,11 @@ static int upload_grid_tables(nb200_ctx* c, nbgrid::Tables& T)
     CUDA_TRY(c, cudaMalloc(&c->d_tile_gidx, nslot * 4));
     CUDA_TRY(c, cudaMemcpy(c->d_tile_row, T.tile_row.data(), nslot * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(c, cudaMemcpy(c->d_tile_gidx, T.tile_gidx.data(), nslot * 4, cudaMemcpyHostToDevice));
+    c->grid_store_halves = 0;
+    for (size_t i = 3; i < T.tile_store.size(); i += 4) c->grid_store_halves += (T.tile_store[i] & 1) + ((T.tile_store[i] >> 1) & 1);
+    CUDA_TRY(c, cudaMalloc(&c->d_tile_store, std::max<size_t>(8, T.tile_store.size() * 2)));
+    if (!T.tile_store.empty()) CUDA_TRY(c, cudaMemcpy(c->d_tile_store, T.tile_store.data(), T.tile_store.size() * 2, cudaMemcpyHostToDevice));
+    c->grid_half_x = T.half_dims[0];
     CUDA_TRY(c, cudaMalloc(&c->d_tile_pass, T.tile_pass.size() * 4));
     CUDA_TRY(c, cudaMemcpy(c->d_tile_pass, T.tile_pass.data(), T.tile_pass.size() * 4, cudaMemcpyHostToDevice));
     {
@@ -1735,6 +1768,7 @@ static StreamArgs stream_args(nb200_ctx* c)
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
     A.tile_row = c->d_tile_row; A.tile_gidx = c->d_tile_gidx; A.gpass = c->d_gpass; A.gbox = c->d_gbox;
     A.tmap_f = A.tmap_g = nullptr;
+    A.tile_store = nullptr; A.tmap_out_f = nullptr; A.half_x = 1;
     A.gstride = c->gstride; A.gdesc_stride = c->gdesc_stride;
     return A;
 }
@@ -1760,6 +1794,10 @@ static void grid_args(const nb200_ctx* c, StreamArgs& A)
     A.stage_cta = c->d_tile_pass;
     A.tmap_f = (const char*)c->d_tmaps + ((size_t)(0 * 2 + c->cur[0]) * nb) * 128;
     A.tmap_g = c->with_g ? (const char*)c->d_tmaps + ((size_t)(1 * 2 + c->cur[1]) * nb) * 128 : nullptr;
+    // box stores go into the grid copy of the NEXT buffer of f (the one the fused kernel writes)
+    A.tile_store = c->grid_store_halves > 0 ? reinterpret_cast<const short4*>(c->d_tile_store) : nullptr;
+    A.tmap_out_f = (const char*)c->d_tmaps + ((size_t)4 * nb + (size_t)(0 * 2 + (c->cur[0] ^ 1)) * c->Q) * 128;
+    A.half_x = c->grid_half_x;
 }
 
 // brings the grid copies of the current buffers in line with the canonical arrays (no-op while they are)

@@ -131,6 +131,10 @@ struct StreamArgs {
     const void* tmap_g;                      //         ... of g
     int64_t gstride;                         // population pitch of the grid copies
     int64_t gdesc_stride;                    // pitch of the grid descriptors (sdesc) = n_tiles * NB_CTA_ROWS
+    const short4* __restrict__ tile_store;   // [n_tiles] grid origin of the tile's first half + flags: bit h = half h is written to
+                                             // the grid copy as one box (TMA store); null = per-thread stores only
+    const void* tmap_out_f;                  // [Q] CUtensorMap (box = one half-tile) of every population in the NEXT grid copy of f
+    int half_x;                              // x extent of a half-tile
 };
 
 // one ELL row dot product for 1 or 2 right-hand sides (f and g share the matrix pass)
@@ -498,6 +502,18 @@ __device__ __forceinline__ void nb_tma_load_3d(double* smem_dst, const void* tma
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(z),
                    "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// box of shared memory (dense, x fastest) -> the 3-d tensor `tmap` at origin (x, y, z); points outside the tensor are clipped
+__device__ __forceinline__ void nb_tma_store_3d(const void* tmap, const double* smem_src, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void nb_tma_store_commit_and_wait()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // contiguous bytes global -> shared through the TMA unit (no LSU instructions, no L1 allocation), counted on `bar`;

@@ -57,7 +57,8 @@ static bool load_file(const char* path, Problem& P)
     P.stride = ((P.nloc + 31) / 32) * 32;
     nbgrid::Grid& g = P.g;
     g.dim = P.dim; g.fe_order = P.p;
-    for (int j = 0; j < 3; j++) g.n[j] = j < P.dim ? (int32_t)h[5 + j] : 1;
+    g.xshift = 1;                                   // as nb200_set_dof_grid does when the cells are declared (fe_order > 0)
+    for (int j = 0; j < 3; j++) g.n[j] = j < P.dim ? (int32_t)h[5 + j] + (j == 0 ? g.xshift : 0) : 1;
     g.nxp = (g.n[0] + 1) & ~1;
     g.G = g.nxp * g.n[1] * g.n[2];
     std::vector<int32_t> coords((size_t)P.nloc * P.dim);
@@ -66,7 +67,7 @@ static bool load_file(const char* path, Problem& P)
     for (int64_t u = 0; u < P.nloc; u++) {
         int c[3] = {0, 0, 0};
         for (int j = 0; j < P.dim; j++) c[j] = coords[(size_t)(u * P.dim + j)];
-        g.gidx_of_int[(size_t)u] = (int32_t)g.flat(c[0], c[1], c[2]);
+        g.gidx_of_int[(size_t)u] = (int32_t)g.flat(c[0] + g.xshift, c[1], c[2]);
     }
     P.dirs.resize((size_t)P.ndir); P.rowptr.resize((size_t)P.ndir); P.col.resize((size_t)P.ndir); P.val.resize((size_t)P.ndir);
     P.wall_ptr.resize((size_t)P.ndir); P.wall_col.resize((size_t)P.ndir); P.wall_val.resize((size_t)P.ndir);
@@ -290,8 +291,37 @@ static int check(Problem& P, int cap)
         if (next_dir != ndir) { printf("FAIL passes do not cover all directions\n"); return 1; }
     }
     if (seen_rows != n) { printf("FAIL %lld of %lld rows in tiles\n", (long long)seen_rows, (long long)n); return 1; }
+    // box stores: a flagged half-tile written as one box (out-of-range points clipped) must put every row of the half at its own
+    // grid point and touch no grid point that holds another DoF
+    int64_t store_halves = 0, store_rows = 0;
+    {
+        std::vector<int32_t> dof_at((size_t)g.G, -1);
+        for (size_t i = 0; i < g.gidx_of_int.size(); i++) dof_at[(size_t)g.gidx_of_int[i]] = (int32_t)i;
+        const int* hd = T.half_dims;
+        if (T.tile_store.size() != (size_t)T.n_tiles * 4) { printf("FAIL tile_store size\n"); return 1; }
+        for (int64_t b = 0; b < T.n_tiles; b++)
+            for (int hf = 0; hf < 2; hf++) {
+                const int16_t* ts = T.tile_store.data() + (size_t)b * 4;
+                if (!((ts[3] >> hf) & 1)) continue;
+                store_halves++;
+                const int bx = ts[0] + hf * hd[0];
+                if ((bx & 1) || (hd[0] * 8) % 16) { printf("FAIL box store alignment\n"); return 1; }
+                for (int tt = 0; tt < hd[0] * hd[1] * hd[2]; tt++) {
+                    const int c[3] = {bx + tt % hd[0], ts[1] + (tt / hd[0]) % hd[1], ts[2] + tt / (hd[0] * hd[1])};
+                    const int32_t r = T.tile_row[(size_t)(b * 128 + hf * 64 + tt)];
+                    const bool inside = c[0] >= 0 && c[0] < g.nxp && c[1] >= 0 && c[1] < g.n[1] && c[2] >= 0 && c[2] < g.n[2];
+                    if (!inside) { if (r >= 0) { printf("FAIL row outside the grid in a box store\n"); return 1; } continue; }
+                    const int64_t f = g.flat(c[0], c[1], c[2]);
+                    if (r >= 0) { if (g.gidx_of_int[(size_t)r] != f) { printf("FAIL box store puts a row elsewhere\n"); return 1; } store_rows++; }
+                    else if (dof_at[(size_t)f] >= 0) { printf("FAIL box store overwrites another DoF\n"); return 1; }
+                }
+                for (int tt = hd[0] * hd[1] * hd[2]; tt < 64; tt++)
+                    if (T.tile_row[(size_t)(b * 128 + hf * 64 + tt)] >= 0) { printf("FAIL row beyond the half-tile box\n"); return 1; }
+            }
+    }
     if (!(max_err <= 1e-13 * max_ref)) { printf("FAIL max_err %g (scale %g)\n", max_err, max_ref); return 1; }
-    printf("OK rows=%lld checked=%lld tiles=%lld boxes=%lld passes=%zu box_rows=%lld generic=%lld max_pass=%lld err=%.2e\n", (long long)n, (long long)checked,
-           (long long)T.n_tiles, (long long)T.total_boxes, T.passes.size(), (long long)T.grid_rows, (long long)T.generic_rows, (long long)T.max_pass_doubles, max_err);
+    printf("OK rows=%lld checked=%lld tiles=%lld boxes=%lld passes=%zu box_rows=%lld generic=%lld max_pass=%lld err=%.2e store_halves=%lld store_rows=%lld\n", (long long)n, (long long)checked,
+           (long long)T.n_tiles, (long long)T.total_boxes, T.passes.size(), (long long)T.grid_rows, (long long)T.generic_rows, (long long)T.max_pass_doubles, max_err,
+           (long long)store_halves, (long long)store_rows);
     return 0;
 }
