@@ -7,6 +7,6 @@ be built (``__graft_entry__.build()``) and a GPU must be present to create a con
 """
 from . import _capi, harness, host, mrt, stencils  # noqa: F401
 from ._capi import CollisionException, Context, NatriumB200Error  # noqa: F401
-from .host import (CFDSolver, CompressibleCFDSolver, DistributionFunctions, PseudoEntropicStabilizer,  # noqa: F401
+from .host import (CFDSolver, CompressibleCFDSolver, DistributionFunctions, ExponentialFilter, PseudoEntropicStabilizer,  # noqa: F401
                    SemiLagrangian, SolverConfiguration, selectCollision)
 from .stencils import Stencil  # noqa: F401

@@ -111,13 +111,16 @@ int fused(const NbLaunch& L)
         else return -1;                                                                          \
     } while (0)
         if (L.fmt == NB_FMT_GRID) {
+            // the attribute allows the largest buffers; the launch asks for what this context's tables were built for
             const size_t smem_gr = (size_t)(Q * NB_CTA_ROWS + 2 * NB_GRID_CAP) * sizeof(double);
+            const size_t smem_use = (size_t)(Q * NB_CTA_ROWS + 2 * L.A.grid_cap) * sizeof(double);
+            if (L.A.grid_cap < 16 || L.A.grid_cap > NB_GRID_CAP) return (int)cudaErrorInvalidValue;
 #define NB_LAUNCH_FGR(EQ)                                                                                                   \
     do {                                                                                                                   \
         static unsigned attr_mask = 0;                                                                                     \
         int e = set_smem(k_stream_collide_f_grid<D, Q, EQ>, smem_gr, &attr_mask);                                          \
         if (e) return e;                                                                                                   \
-        k_stream_collide_f_grid<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_gr, L.stream>>>(L.A, L.xf, L.yf, L.ygf, L.rho, L.u, L.flag); \
+        k_stream_collide_f_grid<D, Q, EQ><<<grid, NB_CTA_ROWS, smem_use, L.stream>>>(L.A, L.xf, L.yf, L.ygf, L.rho, L.u, L.flag); \
     } while (0)
             if (L.eq == NB_EQ_BGK) NB_LAUNCH_FGR(NB_EQ_BGK);
             else if (L.eq == NB_EQ_QUARTIC) NB_LAUNCH_FGR(NB_EQ_QUARTIC);

@@ -311,7 +311,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     __shared__ int s_tflags;
     __shared__ int32_t srow[NB_CTA_ROWS];
     double (*tile)[NB_CTA_ROWS] = reinterpret_cast<double (*)[NB_CTA_ROWS]>(smem_grid);    // [Q][128]
-    double* xs = smem_grid + Q * NB_CTA_ROWS;                                               // [2][NB_GRID_CAP]
+    double* xs = smem_grid + Q * NB_CTA_ROWS;                                               // [2][A.grid_cap]
     const int tid = threadIdx.x;
     const int64_t tl = A.cta_map ? (int64_t)__ldg(A.cta_map + blockIdx.x) : (int64_t)blockIdx.x;
     const int64_t slot = tl * NB_CTA_ROWS + tid;
@@ -331,7 +331,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
     const int p0 = __ldg(A.stage_cta + tl), p1 = __ldg(A.stage_cta + tl + 1);
     if (tid < 32) {      // both buffers are free: the first two passes start right away (warp 0 issues the copies)
         if (p0 < p1) nb_grid_issue<1>(A, A.gpass[p0], xs, xs, &mbar[0], tid);
-        if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + NB_GRID_CAP, xs, &mbar[1], tid);
+        if (p0 + 1 < p1) nb_grid_issue<1>(A, A.gpass[p0 + 1], xs + A.grid_cap, xs, &mbar[1], tid);
     } else if (tid < 64) {
         // the descriptors of all directions, one bulk copy of 128 x 8 bytes per direction: each parks in the tile row its
         // results will overwrite (no LSU instructions and no L1 allocation: the L1 is left to the weight patterns)
@@ -348,7 +348,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
         const int buf = (p - p0) & 1;
         const NbGridPass ps = A.gpass[p];
         nb_mbar_wait(&mbar[buf], (unsigned)(((p - p0) >> 1) & 1));
-        const double* __restrict__ xb = xs + buf * NB_GRID_CAP;
+        const double* __restrict__ xb = xs + buf * A.grid_cap;
 #pragma unroll 1
         for (int a = ps.a0 + ((ps.a0 ^ half) & 1); a < ps.a1; a += 2) {
             const int2 d0 = reinterpret_cast<const int2*>(&tile[a + 1][t0])[0];
@@ -358,7 +358,7 @@ k_stream_collide_f_grid(StreamArgs A, const double* __restrict__ x, double* __re
             tile[a + 1][t0] = r[0];
             tile[a + 1][t0 + 64] = r[1];
         }
-        nb_grid_release<1>(A, p, p1, buf, tid & 31, cnt, xs, xs, NB_GRID_CAP, mbar);
+        nb_grid_release<1>(A, p, p1, buf, tid & 31, cnt, xs, xs, A.grid_cap, mbar);
     }
     __syncthreads();          // results of a row come from the other half of the CTA
     // a half-tile of whole cells is a box of the grid copy: where the builder allows it the half goes out as ONE TMA store per

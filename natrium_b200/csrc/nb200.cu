@@ -1094,6 +1094,15 @@ static int finalize_dict(nb200_ctx* c)
         static const char* envg = getenv("NB200_GRID");       // experiments only: NB200_GRID=0 keeps the staged dictionary kernels
         if (!(envg && envg[0] == '0')) {
             c->grid_cap = NB_GRID_CAP_OF(c->Q, c->with_g ? 2 : 1);
+            if (!c->with_g) {
+                // several ranks: the exchange (pack, NCCL send/recv, unpack) and the boundary tiles run NEXT to the interior
+                // tiles of the fused kernel; with 1536-value passes five CTAs take every byte of an SM's shared memory and the
+                // exchange kernels find no room until the interior kernel drains (measured: 0.75 instead of 0.60 ms/step on 4
+                // GPUs).  1024-value passes leave 45 KB per SM free, as the staged kernels do.
+                if (c->nranks > 1 && c->overlap) c->grid_cap = std::min(c->grid_cap, NB_GRID_CAP_MULTI);
+                static const char* envc = getenv("NB200_GRID_CAP");     // experiments only
+                if (envc && atoi(envc) >= 256) c->grid_cap = std::min(atoi(envc), (int)NB_GRID_CAP);
+            }
             grid_ok = nbgrid::build(c->dirs, c->grid, n, c->stride, NB_CTA_ROWS, c->grid_cap, NB_GRID_MAXK, NB_MAX_CLS - 1, GT);
         }
     }
@@ -1768,7 +1777,7 @@ static StreamArgs stream_args(nb200_ctx* c)
     A.n_slices = c->n_slices; A.n_owned = c->n_owned; A.stride = c->stride;
     A.tile_row = c->d_tile_row; A.tile_gidx = c->d_tile_gidx; A.gpass = c->d_gpass; A.gbox = c->d_gbox;
     A.tmap_f = A.tmap_g = nullptr;
-    A.tile_store = nullptr; A.tmap_out_f = nullptr; A.half_x = 1;
+    A.tile_store = nullptr; A.tmap_out_f = nullptr; A.half_x = 1; A.grid_cap = NB_GRID_CAP;
     A.gstride = c->gstride; A.gdesc_stride = c->gdesc_stride;
     return A;
 }
@@ -1798,6 +1807,7 @@ static void grid_args(const nb200_ctx* c, StreamArgs& A)
     A.tile_store = c->grid_store_halves > 0 ? reinterpret_cast<const short4*>(c->d_tile_store) : nullptr;
     A.tmap_out_f = (const char*)c->d_tmaps + ((size_t)4 * nb + (size_t)(0 * 2 + (c->cur[0] ^ 1)) * c->Q) * 128;
     A.half_x = c->grid_half_x;
+    A.grid_cap = c->grid_cap;
 }
 
 // brings the grid copies of the current buffers in line with the canonical arrays (no-op while they are)

@@ -48,6 +48,9 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2, NB_FMT_GRID = 3 };
 #define NB_GRID_CAP_FGF 512        // f + g, stencils that run the fused kernel (Q <= 25, D2Q25H: small 2-d boxes)
 #endif
 // capacity of one staging buffer per distribution for a stencil with Q directions and n_rhs distributions
+#ifndef NB_GRID_CAP_MULTI
+#define NB_GRID_CAP_MULTI 1024     // f only, several ranks with the overlapped exchange: leaves shared memory for the exchange kernels
+#endif
 #define NB_GRID_CAP_OF(Q, n_rhs) ((n_rhs) == 2 ? ((Q) <= 25 ? NB_GRID_CAP_FGF : NB_GRID_CAP_FG) : NB_GRID_CAP)
 #define NB_GRID_MAXK 128
 // row lengths with a compile-time instance of the pair product: 3-d units add the lengths of three moving axes
@@ -135,6 +138,8 @@ struct StreamArgs {
                                              // the grid copy as one box (TMA store); null = per-thread stores only
     const void* tmap_out_f;                  // [Q] CUtensorMap (box = one half-tile) of every population in the NEXT grid copy of f
     int half_x;                              // x extent of a half-tile
+    int grid_cap;                            // values per staging buffer of the fused f kernel (<= NB_GRID_CAP; the tables were
+                                             // built for it): smaller when other kernels must fit next to it on an SM
 };
 
 // one ELL row dot product for 1 or 2 right-hand sides (f and g share the matrix pass)

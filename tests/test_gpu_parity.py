@@ -1541,3 +1541,41 @@ def test_filter_errors():
     ctx.set_filter(None, None, None, None)
     assert ctx.filter_info()["cells"] == 0
     ctx.close()
+
+
+def test_host_mirror_solver_with_filter(oracle_lib):
+    """The reference-shaped host API with a filter (CFDSolver::filter between stream and collide, CFDSolver.cpp:884-888):
+    natrium_b200.ExponentialFilter builds the tables the reference builds with deal.II, CFDSolver.setFilter hands them over,
+    run() filters inside nb200_step; compared with the oracle's stream -> filter -> collide loop that uses the ORACLE's own
+    tables (oracle/filter.py), so the host mirror's tables are checked end to end as well."""
+    from oracle import filter as F
+    from natrium_b200 import CFDSolver, ExponentialFilter, SolverConfiguration, harness
+    case = "tgv2d_small"
+    o = common.oracle_problem(case)
+    c = o["c"]
+    cfg = SolverConfiguration()
+    cfg.setStencil("D2Q9")
+    cfg.setStencilScaling(c["scaling"])
+    cfg.setSedgOrderOfFiniteElement(c["p"])
+    cfg.setCFL(c["cfl"])
+    pb = harness.CartesianProblem(c["dim"], c["cells"], c["p"])
+    solver = CFDSolver(cfg, pb, c["nu"])
+    solver.setInitialFields(o["rho"], o["u"])
+    alpha, s, Nc = 8.0, 4.0, c["p"]
+    solver.setFilter(ExponentialFilter(alpha, s, Nc, False, c["p"], c["dim"]), interval=2)
+    solver.run(4)
+    to, fr = F.projection_matrices(c["p"], c["dim"])
+    sg, damped = F.damping(c["p"], c["dim"], alpha, s, Nc)
+    cd = solver.getAdvectionOperator().getPartition().cell_dofs()
+    f = o["f"].copy()
+    oracle_lib.collide_bgk(o["st"], f, c["nu"], o["dt"])          # run(): collide once before the loop
+    for i in range(1, 5):
+        f = oracle_lib.stream(o["blocks"], f)
+        if i % 2 == 0:
+            for q in range(f.shape[0]):
+                row = np.ascontiguousarray(f[q])
+                F.apply_filter(cd, to, fr, sg, damped, row)
+                f[q] = row
+        assert oracle_lib.collide_bgk(o["st"], f, c["nu"], o["dt"])[-1] == 0
+    assert rel_err(solver.getF().to_host(), f) <= 1e-11
+    solver.ctx.close()
