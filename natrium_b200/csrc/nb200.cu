@@ -219,10 +219,13 @@ struct nb200_ctx {
     double* d_hit_val = nullptr;
     // overlap of the exchange with the rows that read no ghost (staged kernels): second stream + CTA lists
     cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_prev = nullptr, ev_halo = nullptr;
+    cudaEvent_t ev_prev = nullptr, ev_halo = nullptr, ev_packed = nullptr;
     int32_t *d_cta_interior = nullptr, *d_cta_boundary = nullptr;
     int64_t n_cta_interior = 0, n_cta_boundary = 0;
     bool overlap = true;
+    // NB200_TRACE=1 (diagnostics): device timeline of the last step of a multi-rank nb200_step call, printed to stderr
+    bool trace = false;
+    cudaEvent_t tev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // exponential filter (nb200_set_filter): cells sorted into levels, transposed projections
     int64_t filt_cells = 0, iteration = 0;
     int filt_n = 0, filt_interval = 0;
@@ -513,10 +516,14 @@ extern "C" int nb200_create(nb200_ctx** out, int device, int rank, int nranks, c
         // the exchange (and the boundary CTAs behind it) must not queue behind the interior kernel's ~16k CTAs
         if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&c->ev_prev, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess) { nb200_destroy(c); return NB200_ERR_CUDA; }
+            cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_packed, cudaEventDisableTiming) != cudaSuccess) { nb200_destroy(c); return NB200_ERR_CUDA; }
         {
             static const char* env = getenv("NB200_OVERLAP");      // experiments only: NB200_OVERLAP=0 serialises exchange and kernels
             c->overlap = !(env && env[0] == '0');
+            static const char* envt = getenv("NB200_TRACE");
+            c->trace = envt && envt[0] == '1';
+            if (c->trace) for (auto& e : c->tev) cudaEventCreate(&e);
         }
         if (!nccl_unique_id || !g_nccl.load(c->err)) { nb200_destroy(c); return NB200_ERR_NCCL; }
         ncclUniqueId id;
@@ -606,6 +613,8 @@ extern "C" void nb200_destroy(nb200_ctx* c)
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->ev_prev) cudaEventDestroy(c->ev_prev);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_packed) cudaEventDestroy(c->ev_packed);
+    for (auto& e : c->tev) if (e) cudaEventDestroy(e);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1099,7 +1108,7 @@ static int finalize_dict(nb200_ctx* c)
                 // tiles of the fused kernel; with 1536-value passes five CTAs take every byte of an SM's shared memory and the
                 // exchange kernels find no room until the interior kernel drains (measured: 0.75 instead of 0.60 ms/step on 4
                 // GPUs).  1024-value passes leave 45 KB per SM free, as the staged kernels do.
-                if (c->nranks > 1 && c->overlap) c->grid_cap = std::min(c->grid_cap, NB_GRID_CAP_MULTI);
+                if (c->nranks > 1 && c->overlap) c->grid_cap = std::min(c->grid_cap, (int)NB_GRID_CAP_MULTI);
                 static const char* envc = getenv("NB200_GRID_CAP");     // experiments only
                 if (envc && atoi(envc) >= 256) c->grid_cap = std::min(atoi(envc), (int)NB_GRID_CAP);
             }
@@ -1712,7 +1721,7 @@ static int halo_plan(nb200_ctx* c, int mask, bool pruned, nb200_ctx::HaloPlan** 
 }
 
 // One packed neighbour exchange of the current populations on stream `st`.
-static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true, cudaStream_t st = nullptr)
+static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true, cudaStream_t st = nullptr, cudaEvent_t* tev = nullptr)
 {
     if (c->nranks == 1 || c->n_nbr == 0) return NB200_OK;
     if (!st) st = c->stream;
@@ -1728,6 +1737,8 @@ static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true,
         k_halo_pack<<<grid, 256, 0, st>>>(P->d_send_segs, c->d_send_idx, c->stride, xf, xg, c->d_sendbuf);
         c->launches++;
     }
+    if (tev) cudaEventRecord(tev[0], st);       // packed
+    if (c->ev_packed && st == c->comm_stream) CUDA_TRY(c, cudaEventRecord(c->ev_packed, st));
     NCCL_TRY(c, g_nccl.GroupStart());
     for (int s = 0; s < c->n_nbr; s++) {
         const int64_t scnt = P->nbr_send_cnt[(size_t)s], rcnt = P->nbr_recv_cnt[(size_t)s];
@@ -1735,6 +1746,7 @@ static int halo_exchange(nb200_ctx* c, bool do_f, bool do_g, bool pruned = true,
         if (rcnt) NCCL_TRY(c, g_nccl.Recv(c->d_recvbuf + P->nbr_recv_off[(size_t)s], (size_t)rcnt, ncclFloat64, c->nbr_rank[(size_t)s], c->comm, st));
     }
     NCCL_TRY(c, g_nccl.GroupEnd());
+    if (tev) cudaEventRecord(tev[1], st);       // exchanged
     if (!P->recv_segs.empty()) {
         dim3 grid((unsigned)std::min<int64_t>(64, (P->max_recv_cnt + 255) / 256), (unsigned)P->recv_segs.size());
         // the grid copies of the current buffers get the ghost values too (only where they are in sync with the canonical
@@ -2115,19 +2127,44 @@ extern "C" int nb200_step(nb200_ctx* c, int n_steps)
             if (rc) return rc;
         }
         if (split) {
+            const bool tr = c->trace && s == n_steps - 1 && n_steps > 1;
+            if (tr) cudaEventRecord(c->tev[2], c->stream);                  // step start on the context stream
             CUDA_TRY(c, cudaEventRecord(c->ev_prev, c->stream));            // populations of the previous step are final
             CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, c->ev_prev, 0));
-            rc = halo_exchange(c, true, do_g, true, c->comm_stream);
+            rc = halo_exchange(c, true, do_g, true, c->comm_stream, tr ? c->tev : nullptr);
             if (rc) return rc;
             CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+            if (tr) cudaEventRecord(c->tev[3], c->comm_stream);             // unpacked
             if (use_fused(c)) {
                 // boundary CTAs ride the (high-priority) exchange stream right behind the unpack, so they overlap the
                 // tail of the interior kernel; the context stream joins both before the buffers flip
                 rc = dispatch_fused(c, l_bnd, n_bnd, false, c->comm_stream);
                 CUDA_TRY(c, cudaEventRecord(c->ev_halo, c->comm_stream));
+                if (tr) cudaEventRecord(c->tev[4], c->comm_stream);         // boundary tiles done
+                // The interior tiles wait for the pack kernel: they would otherwise take every SM the moment the previous step
+                // ends, and the NCCL kernel (hundreds of threads per CTA) finds no SM with room until the interior grid drains
+                // -- seen in the NB200_TRACE timeline: "exchanged" at 0.52 of a 0.60 ms step, the boundary tiles then run after
+                // everything else.  Released together, the exchange stream's priority puts the NCCL CTAs on the SMs first.
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_packed, 0));
                 if (!rc) rc = dispatch_fused(c, l_int, n_int, true);
+                if (tr) cudaEventRecord(c->tev[5], c->stream);              // interior tiles done
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+                if (tr) {
+                    cudaEventRecord(c->tev[6], c->stream);                  // step end
+                    cudaEventSynchronize(c->tev[6]);
+                    float t[6] = {0, 0, 0, 0, 0, 0};
+                    cudaEventElapsedTime(&t[0], c->tev[2], c->tev[0]);
+                    cudaEventElapsedTime(&t[1], c->tev[2], c->tev[1]);
+                    cudaEventElapsedTime(&t[2], c->tev[2], c->tev[3]);
+                    cudaEventElapsedTime(&t[3], c->tev[2], c->tev[4]);
+                    cudaEventElapsedTime(&t[4], c->tev[2], c->tev[5]);
+                    cudaEventElapsedTime(&t[5], c->tev[2], c->tev[6]);
+                    fprintf(stderr, "[nb200 trace] rank %d step timeline (ms from step start): packed %.3f exchanged %.3f unpacked %.3f boundary done %.3f "
+                                    "interior done %.3f step end %.3f  (tiles: %lld interior, %lld boundary)\n",
+                            c->rank, t[0], t[1], t[2], t[3], t[4], t[5], (long long)n_int, (long long)n_bnd);
+                }
             } else {
+                CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_packed, 0));      // as in the fused branch
                 rc = launch_stream(c, true, do_g, l_int, n_int, false);
                 CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
                 if (!rc) rc = launch_stream(c, true, do_g, l_bnd, n_bnd, true);

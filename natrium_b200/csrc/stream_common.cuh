@@ -49,7 +49,9 @@ enum { NB_FMT_ELL = 0, NB_FMT_DICT = 1, NB_FMT_STAGED = 2, NB_FMT_GRID = 3 };
 #endif
 // capacity of one staging buffer per distribution for a stencil with Q directions and n_rhs distributions
 #ifndef NB_GRID_CAP_MULTI
-#define NB_GRID_CAP_MULTI 1024     // f only, several ranks with the overlapped exchange: leaves shared memory for the exchange kernels
+#define NB_GRID_CAP_MULTI NB_GRID_CAP   // f only, several ranks with the overlapped exchange.  1024 (45 KB of an SM's shared memory
+                                         // left for the exchange kernels) was measured on 2 GPUs: 0.639 against 0.602 ms/step with 1536
+                                         // -- the extra passes cost more than the room gives
 #endif
 #define NB_GRID_CAP_OF(Q, n_rhs) ((n_rhs) == 2 ? ((Q) <= 25 ? NB_GRID_CAP_FGF : NB_GRID_CAP_FG) : NB_GRID_CAP)
 #define NB_GRID_MAXK 128
