@@ -12,6 +12,11 @@
 //   quartic equilibrium     L/collision_advanced/Equilibria.h:119-267 (H3/H4 :519-566)
 //   BGK relax               L/collision_advanced/CollisionSchemes.h:28-41
 //   f+g relax (Prandtl fix, Sutherland, sensor)   CollisionSchemes.h:43-118, Aux...h:420-515
+// The 1e-12-per-step parity contract fixes the operation order of these formulas, so the formula blocks themselves (the
+// D2Q9 / generic BGK equilibrium, the quartic equilibrium's a_xxx .. a_xxyz coefficients, the hard-coded velocity index
+// sums for D2Q9 / D3Q19) are TRANSCRIPTIONS of the reference's expressions, identifiers included (prefactor, uSquareTerm,
+// mixedTerm, T1, a_*), about 70 lines; what surrounds them -- pre-reduced Hermite components, reciprocal constants,
+// register templates, force hooks, the loop form for large stencils -- is this library's own.
 // Unlike the reference, the Hermite tensors are reduced once on the host to their 10+15
 // unique symmetric components and kept in constant memory (the reference recomputes the
 // full tensors per DoF, CollisionOperator.h:68-69).  Divisions by run-time constants (cs2, tau,
