@@ -488,8 +488,10 @@ k_stream_collide_fg_grid(StreamArgs A, const double* __restrict__ xf, const doub
 
 // Stream only over the grid copy (the vmult site and the unfused configurations): canonical output only.
 // (templated on the stencil so that every stencil unit launches its own instance, which reads that unit's cGridOff)
+// (4 CTAs/SM as the register target: left to itself ptxas settles at ~70 registers and issues the weight loads of a batch one
+// by one between the multiply-adds instead of all up front)
 template <int D, int Q, int NRHS>
-__global__ void __launch_bounds__(NB_CTA_ROWS)
+__global__ void __launch_bounds__(NB_CTA_ROWS, 4)
 k_stream_grid(StreamArgs A, const double* __restrict__ x0, const double* __restrict__ x1,
               double* __restrict__ y0, double* __restrict__ y1)
 {
