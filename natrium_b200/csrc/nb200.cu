@@ -31,6 +31,7 @@
 #include "launch.h"
 #include "dict_build.h"
 #include "grid_build.h"
+#include "filter_build.h"
 
 // ---------------------------------------------------------------------------------------------
 // NCCL, bound at run time (dlopen) so that a single-GPU user needs no NCCL at all and a
@@ -2212,36 +2213,21 @@ extern "C" int nb200_set_filter(nb200_ctx* c, int64_t n_cells, int n, const int3
     if (n > 256) return fail(c, NB200_ERR_UNSUPPORTED, "set_filter: %d DoFs per cell (the filter kernel holds one cell per CTA, at most 256)", n);
     if ((size_t)n * c->Q * sizeof(double) > 200 * 1024) return fail(c, NB200_ERR_UNSUPPORTED, "set_filter: %d DoFs per cell x %d populations exceed the shared memory of a CTA", n, c->Q);
     const int64_t nloc = c->n_owned + c->n_ghost;
-    // internal indices; levels: above every earlier cell that shares a DoF (the reference's sequential order is kept)
+    // internal indices, then the level schedule that keeps the reference's sequential cell order (filter_build.h)
     std::vector<int32_t> dofs((size_t)n_cells * n);
-    std::vector<int32_t> last_level((size_t)std::max<int64_t>(1, nloc), 0), level((size_t)n_cells, 0);
-    int32_t n_levels = 0;
-    for (int64_t cell = 0; cell < n_cells; cell++) {
-        int32_t lv = 0;
+    for (int64_t cell = 0; cell < n_cells; cell++)
         for (int i = 0; i < n; i++) {
             const int32_t u = cell_dofs[cell * n + i];
             if (u < 0 || u >= nloc) return fail(c, NB200_ERR_ARG, "set_filter: DoF %d of cell %lld outside the owned + ghost range", (int)u, (long long)cell);
-            const int32_t d = (u < c->n_owned && c->has_order) ? c->perm[(size_t)u] : u;
-            dofs[(size_t)(cell * n + i)] = d;
-            lv = std::max(lv, last_level[(size_t)d]);
+            dofs[(size_t)(cell * n + i)] = (u < c->n_owned && c->has_order) ? c->perm[(size_t)u] : u;
         }
-        lv += 1;
-        for (int i = 0; i < n; i++) {
-            int32_t& ll = last_level[(size_t)dofs[(size_t)(cell * n + i)]];
-            if (ll == lv) return fail(c, NB200_ERR_ARG, "set_filter: cell %lld lists a DoF twice", (long long)cell);
-            ll = lv;
-        }
-        level[(size_t)cell] = lv;
-        n_levels = std::max(n_levels, lv);
-    }
-    c->filt_level_off.assign((size_t)n_levels + 1, 0);
-    for (int64_t cell = 0; cell < n_cells; cell++) c->filt_level_off[(size_t)level[(size_t)cell]]++;
-    for (int32_t l = 0; l < n_levels; l++) c->filt_level_off[(size_t)l + 1] += c->filt_level_off[(size_t)l];
-    std::vector<int32_t> sorted((size_t)n_cells);
+    nbfilter::Levels LV;
     {
-        std::vector<int64_t> cur(c->filt_level_off.begin(), c->filt_level_off.end() - 1);
-        for (int64_t cell = 0; cell < n_cells; cell++) sorted[(size_t)cur[(size_t)level[(size_t)cell] - 1]++] = (int32_t)cell;
+        const int64_t bad = nbfilter::build_levels(n_cells, n, dofs.data(), nloc, LV);
+        if (bad) return fail(c, NB200_ERR_ARG, "set_filter: cell %lld lists a DoF twice", (long long)(bad - 1));
     }
+    c->filt_level_off = LV.level_off;
+    const std::vector<int32_t>& sorted = LV.cells;
     std::vector<double> tT((size_t)n * n), fT((size_t)n * n);
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++) {

@@ -303,3 +303,15 @@ def test_dictionary_builder_semantics(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "dict_check.cpp")], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.startswith("OK"), out
+
+
+def test_filter_level_schedule(tmp_path):
+    """Host-side level schedule of the exponential filter (natrium_b200/csrc/filter_build.h): cells of a level share no DoF,
+    cells that share a DoF keep their order across levels, and a non-commuting cell update applied level by level (any order
+    inside a level) equals the sequential loop bit for bit -- for lexicographic, reversed, Morton and shuffled cell orders."""
+    import subprocess
+    exe = str(tmp_path / "filter_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "filter_check.cpp")], check=True)
+    for args in ["2 4 3 1 2 0 1", "2 6 5 1 3 1 2", "3 4 4 4 2 2 3", "3 3 4 2 4 3 4", "3 8 8 8 1 0 5", "2 9 7 1 4 2 6", "3 16 16 16 1 2 7"]:
+        out = subprocess.run([exe, *args.split()], check=True, capture_output=True, text=True).stdout
+        assert out.startswith("OK"), (args, out)
