@@ -287,9 +287,12 @@ int nb200_step_host_fg(nb200_ctx *ctx, const double *f_in, const double *g_in, d
 int nb200_download_moments(nb200_ctx *ctx, double *rho, double *u, double *T, double *sensor, int64_t n);
 
 /* Global (all-rank) sums over owned DoFs of the current populations:
- * out = { sum rho, sum rho*u_x, sum rho*u_y, sum rho*u_z, sum energy } with
- * energy = 0.5*rho*|u|^2 (+ rho*Cv*T when with_g), u scaled.  Diagnostic mirror of
- * PhysicalProperties::mass / kineticEnergy (L/solver/PhysicalProperties.cpp:29-131) as plain sums. */
+ * out = { sum rho, sum rho*u_x, sum rho*u_y, sum rho*u_z, sum energy }, momentum with the scaled velocities (sum_i e_i f_i).
+ * energy, f only:  0.5 * |sum_i e_i f_i|^2 / rho  (kinetic energy, scaled velocities);
+ * energy, f + g:   0.5 * (sum_i |e_i/scaling|^2 f_i / cs2 + sum_i g_i)  (the total energy the two distributions carry, in the
+ *                  lattice units of calculateTemperature, AuxiliaryCollisionFunctions.h:290-307: = rho (0.5 |u|^2/cs2 + Cv T)).
+ * The two branches are different quantities by design (the compressible one is what the f+g collision conserves); both are
+ * plain sums over DoFs, a diagnostic mirror of PhysicalProperties::mass / kineticEnergy (L/solver/PhysicalProperties.cpp:29-131). */
 int nb200_conserved(nb200_ctx *ctx, double out[5]);
 
 /* Blocks until queued work is done; returns NB200_ERR_DENSITY if the sticky density flag is set. */
