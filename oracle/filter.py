@@ -16,6 +16,9 @@ Bug-for-bug: the 3-D degree vector of the reference computes iy as `(i % (p+1) *
 precedence is i % (p+1) = iz (:123).  Results identical to the reference's need the same degrees, so it is restated as is
 (`reference_quirk=True`); `False` gives the intended (ix, iy, iz).
 
+Pinned to the reference's own code: tests/test_oracle_vs_ref.py runs L/smoothing/ExponentialFilter.cpp, compiled from
+/root/reference against oracle/ref_stubs_filter (oracle/_ref/libnatrium_ref_filter.so), beside these functions.
+
 The Legendre basis is dealii::Polynomials::Legendre: orthonormal on [0, 1], L_k(x) = sqrt(2k+1) P_k(2x - 1); the mode index
 decomposes with x slowest (evaluateLegendreND, :70-94).  The filter itself does not depend on the normalisation.
 """

@@ -149,3 +149,40 @@ def select_collision_range(name, scaling, f, a, b, viscosity, dt, rho_scratch, u
         C.c_int(0), C.c_int(0), C.c_double(viscosity), C.c_double(dt), C.c_int(0), C.c_int(0), C.c_double(1.4), C.c_int(0),
         C.c_double(1.0), C.c_int(0), C.c_int64(n), C.c_int64(stride), C.cast(base, _dp), None, _d(rho_scratch), _d(u_scratch),
         None, None, err, C.c_int(256))
+
+
+# ---- the reference's own ExponentialFilter (oracle/_ref/libnatrium_ref_filter.so, oracle/ref_filter_driver.cpp) ----
+_SO_FILTER = os.path.join(_HERE, "_ref", "libnatrium_ref_filter.so")
+_LIB_FILTER = None
+
+
+def filter_available():
+    build()
+    return os.path.exists(_SO_FILTER)
+
+
+def _filter_lib():
+    global _LIB_FILTER
+    if _LIB_FILTER is None:
+        if not filter_available():
+            raise RuntimeError("oracle/_ref/libnatrium_ref_filter.so is missing and /root/reference is not present to build it")
+        _LIB_FILTER = C.CDLL(_SO_FILTER)
+    return _LIB_FILTER
+
+
+def exponential_filter(dim, p, alpha, s, Nc, by_sum=False, cell_dofs=None, v=None):
+    """natrium::ExponentialFilter<dim>(alpha, s, Nc, by_sum, QGaussLobatto(p+1), Lagrange element on the same nodes): returns
+    (getProjectToLegendre(), getProjectFromLegendre()); with cell_dofs [n_cells, (p+1)^dim] and v, applyFilter runs in place
+    on v over the cells in the given order (element-local numbering lexicographic, x fastest)."""
+    n = (p + 1) ** dim
+    to, fr = np.zeros((n, n)), np.zeros((n, n))
+    n_cells, cd_p, v_p = 0, None, None
+    if cell_dofs is not None:
+        cd = np.ascontiguousarray(cell_dofs, dtype=np.int32)
+        assert cd.shape[1] == n and v is not None and v.dtype == np.float64 and v.flags.c_contiguous
+        n_cells, cd_p, v_p = cd.shape[0], cd.ctypes.data_as(C.POINTER(C.c_int32)), _d(v)
+    rc = _filter_lib().ref_exponential_filter(C.c_int(dim), C.c_int(p), C.c_double(alpha), C.c_double(s), C.c_int(Nc), C.c_int(1 if by_sum else 0),
+                                              _d(to), _d(fr), C.c_int64(n_cells), cd_p, v_p)
+    if rc:
+        raise ValueError((dim, p))
+    return to, fr

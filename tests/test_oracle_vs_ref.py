@@ -268,3 +268,89 @@ def test_thermal_bounce_back_point():
         changed += ref.thermal_wall_point(1.0, 0.85, fi, gi)
         assert close(af[:, i], fi) and close(ag[:, i], gi)
     assert 0 < changed < n
+
+
+# ---------------------------------------------------------------------------------------------------
+# f4: the reference's own ExponentialFilter (L/smoothing/ExponentialFilter.cpp compiled against oracle/ref_stubs_filter)
+# ---------------------------------------------------------------------------------------------------
+filter_ref = pytest.mark.skipif(not ref.filter_available(), reason="oracle/_ref filter library not built and /root/reference absent")
+
+
+@filter_ref
+@pytest.mark.parametrize("p,dim", [(4, 1), (2, 2), (4, 2), (2, 3), (3, 3), (4, 3)])
+def test_filter_projection_matrices_vs_reference(p, dim):
+    """makeProjectionMatrices (ExponentialFilter.cpp:30-68) as compiled from the reference against oracle/filter.py's
+    restatement and the product's host mirror (natrium_b200.host.ExponentialFilter).  The three invert different matrices with
+    different algorithms (Gauss-Jordan on the quadrature sums / LAPACK on the same / LAPACK on the nodal Vandermonde), so the
+    bar is 1e-11 relative to the largest entry; to @ from = 1 to 1e-12."""
+    from oracle import filter as F
+    from natrium_b200 import host
+    to_r, fr_r = ref.exponential_filter(dim, p, 36.0, 2.0, 1)
+    to_o, fr_o = F.projection_matrices(p, dim)
+    h = host.ExponentialFilter(36.0, 2.0, 1, False, p, dim)
+    n = (p + 1) ** dim
+    assert np.abs(to_r @ fr_r - np.eye(n)).max() <= 1e-12
+    for a, b in ((to_o, to_r), (fr_o, fr_r), (h.getProjectToLegendre(), to_r), (h.getProjectFromLegendre(), fr_r)):
+        assert np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
+
+
+@filter_ref
+@pytest.mark.parametrize("p,dim,alpha,s,Nc,by_sum", [(4, 1, 36.0, 2.0, 1, False), (3, 2, 36.0, 2.0, 1, False), (4, 2, 10.0, 4.0, 2, True),
+                                                    (2, 3, 36.0, 2.0, 1, False), (3, 3, 8.0, 4.0, 2, False), (4, 3, 36.0, 2.0, 1, False),
+                                                    (3, 3, 10.0, 2.0, 2, True)])
+def test_filter_damping_per_mode_vs_reference(p, dim, alpha, s, Nc, by_sum):
+    """makeDegreeVectors + the damping formula inside applyFilter (ExponentialFilter.cpp:96-137,171-183): one cell whose nodal
+    values are Legendre mode i comes back scaled by sigma_i, which reads the factor the REFERENCE applies to every mode off
+    its own compiled code -- including the 3-d degree vector's operator-precedence quirk (:123, iy evaluates to iz) that
+    oracle/filter.py and the host mirror restate on purpose."""
+    from oracle import filter as F
+    from natrium_b200 import host
+    n = (p + 1) ** dim
+    to_r, fr_r = ref.exponential_filter(dim, p, alpha, s, Nc, by_sum)
+    sigma_ref = np.zeros(n)
+    cd = np.arange(n, dtype=np.int32)[None, :]
+    for i in range(n):
+        v = np.ascontiguousarray(fr_r[:, i])
+        ref.exponential_filter(dim, p, alpha, s, Nc, by_sum, cell_dofs=cd, v=v)
+        k = int(np.argmax(np.abs(fr_r[:, i])))
+        sigma_ref[i] = v[k] / fr_r[k, i]
+        assert np.abs(v - sigma_ref[i] * fr_r[:, i]).max() <= 1e-11 * np.abs(fr_r[:, i]).max()
+    sg, damped = F.damping(p, dim, alpha, s, Nc, by_sum)
+    assert np.abs(sg - sigma_ref).max() <= 1e-11
+    assert np.abs(host.ExponentialFilter(alpha, s, Nc, by_sum, p, dim).sigma - sigma_ref).max() <= 1e-11
+    if dim == 3:
+        sg_intended, _ = F.damping(p, dim, alpha, s, Nc, by_sum, reference_quirk=False)
+        assert np.abs(sg_intended - sigma_ref).max() > 1e-3          # the reference really has the quirk
+
+
+@filter_ref
+@pytest.mark.parametrize("dim,cells,p,order", [(2, [4, 3], 3, "lex"), (2, [5, 4], 2, "reversed"), (3, [3, 2, 2], 2, "shuffled"), (3, [2, 2, 3], 4, "lex"),
+                                               (3, [3, 3, 2], 3, "shuffled")])
+def test_filter_cell_loop_vs_reference(dim, cells, p, order):
+    """applyFilter (ExponentialFilter.cpp:139-199) on a mesh of cells that share their face DoFs: the oracle's C loop
+    (orc_exponential_filter, fed with the REFERENCE's matrices and the oracle's damping) against the reference's own loop, for
+    lexicographic, reversed and shuffled cell orders (the result depends on the order).  <= 1e-14 relative."""
+    from oracle import filter as F
+    from natrium_b200 import harness
+    from natrium_b200.stencils import Stencil
+    st = Stencil("D2Q9" if dim == 2 else "D3Q19", 3.0)
+    pb = harness.CartesianProblem(dim, cells, p)
+    part = harness.SlabPartition(pb, st, pb.timestep(st, 0.4))
+    cd = part.cell_dofs()
+    if order == "reversed":
+        cd = cd[::-1].copy()
+    elif order == "shuffled":
+        cd = cd[np.random.default_rng(3).permutation(len(cd))].copy()
+    alpha, s, Nc = 6.0, 2.0, 1
+    to_r, fr_r = ref.exponential_filter(dim, p, alpha, s, Nc)
+    sg, damped = F.damping(p, dim, alpha, s, Nc)
+    v0 = np.random.default_rng(11).standard_normal(pb.N)
+    v_ref = v0.copy()
+    ref.exponential_filter(dim, p, alpha, s, Nc, cell_dofs=cd, v=v_ref)
+    v_orc = F.apply_filter(cd, to_r, fr_r, sg, damped, v0.copy())
+    assert np.abs(v_orc - v_ref).max() <= 1e-14 * np.abs(v_ref).max()
+    assert np.abs(v_ref - v0).max() > 0.1
+    # and with the oracle's own matrices: same field up to the conditioning of the projections
+    to_o, fr_o = F.projection_matrices(p, dim)
+    v_own = F.apply_filter(cd, to_o, fr_o, sg, damped, v0.copy())
+    assert np.abs(v_own - v_ref).max() <= 1e-11 * np.abs(v_ref).max()
