@@ -96,6 +96,24 @@ struct DirBuild {
         row_cls.assign((size_t)n_rows, -1);
         nnz = 0;
     }
+    // Class 0 is the one the kernels treat best (its parameters travel in the kernel arguments, the grid kernels take its rows
+    // from TMA boxes): make it the class that holds the most rows.  Classes are numbered as row lengths first appear, and the
+    // first row of a direction can be an oddity -- the corner DoF of a walled mesh whose path is stuck (one entry) made all
+    // nine-entry rows of 8 of D2Q25H's 24 directions second class.  Call once all blocks are in.
+    void majority_class_first()
+    {
+        if (cls.size() < 2) return;
+        std::vector<int64_t> cnt(cls.size(), 0);
+        for (int8_t c : row_cls) if (c >= 0) cnt[(size_t)c]++;
+        size_t best = 0;
+        for (size_t c = 1; c < cls.size(); c++) if (cnt[c] > cnt[best]) best = c;
+        if (best == 0) return;
+        std::swap(cls[0], cls[best]);
+        for (auto& c : row_cls) {
+            if (c == 0) c = (int8_t)best;
+            else if (c == (int8_t)best) c = 0;
+        }
+    }
     // Class holding rows of length K.  The first `exact_limit` distinct lengths get a class of their own;
     // later ones share power-of-two classes (rows are padded with zero weights), so the class count is bounded.
     int class_of(int K, int exact_limit, int* padded_K)

@@ -1078,6 +1078,7 @@ static int finalize_dict(nb200_ctx* c)
         c->dirs.resize((size_t)nb);
         for (auto& d : c->dirs) d.init(n);
     }
+    for (auto& d : c->dirs) d.majority_class_first();
     c->desc_stride = std::max<int64_t>(32, c->n_slices * 32);
     std::vector<NbDirClass> hcls((size_t)nb * NB_MAX_CLS);
     memset(hcls.data(), 0, hcls.size() * sizeof(NbDirClass));

@@ -18,6 +18,13 @@
 #include <cmath>
 #include "../../natrium_b200/csrc/grid_build.h"
 
+struct ExtraBlock {            // an off-diagonal block of a direction's block row (bounce-back walls): reads population bj + 1
+    int bj = 0;
+    std::vector<int64_t> rowptr;
+    std::vector<int32_t> col;
+    std::vector<double> val;
+};
+
 struct Problem {
     int dim = 3, p = 4, ndir = 0, wall = 0;
     int64_t n = 0, nloc = 0, stride = 0;          // rows (owned), owned + ghost, population pitch
@@ -27,6 +34,7 @@ struct Problem {
     std::vector<std::vector<int64_t>> rowptr, wall_ptr;
     std::vector<std::vector<int32_t>> col, wall_col;
     std::vector<std::vector<double>> val, wall_val;
+    std::vector<std::vector<ExtraBlock>> extra;       // file mode, multi-block format
 };
 
 static bool add_direction(Problem& P, int a)
@@ -53,7 +61,8 @@ static bool load_file(const char* path, Problem& P)
     if (!f) return false;
     int64_t h[8];
     if (fread(h, 8, 8, f) != 8) return false;
-    P.dim = (int)h[0]; P.p = (int)h[1]; P.n = h[2]; P.nloc = h[2] + h[3]; P.ndir = (int)h[4];
+    const bool multi = h[4] < 0;        // negative direction count: every direction lists its blocks {nblk; per block: bj, nnz, rowptr, col, val}
+    P.dim = (int)h[0]; P.p = (int)h[1]; P.n = h[2]; P.nloc = h[2] + h[3]; P.ndir = (int)(multi ? -h[4] : h[4]);
     P.stride = ((P.nloc + 31) / 32) * 32;
     nbgrid::Grid& g = P.g;
     g.dim = P.dim; g.fe_order = P.p;
@@ -71,8 +80,38 @@ static bool load_file(const char* path, Problem& P)
     }
     P.dirs.resize((size_t)P.ndir); P.rowptr.resize((size_t)P.ndir); P.col.resize((size_t)P.ndir); P.val.resize((size_t)P.ndir);
     P.wall_ptr.resize((size_t)P.ndir); P.wall_col.resize((size_t)P.ndir); P.wall_val.resize((size_t)P.ndir);
+    P.extra.resize((size_t)P.ndir);
     for (int a = 0; a < P.ndir; a++) {
-        int64_t nnz;
+        int64_t nblk = 1, bj = a, nnz;
+        if (multi && fread(&nblk, 8, 1, f) != 1) return false;
+        if (multi) {
+            // the diagonal block first (it fills rowptr / col / val), the others go to `extra`
+            std::vector<ExtraBlock> blks((size_t)nblk);
+            for (auto& B : blks) {
+                if (fread(&bj, 8, 1, f) != 1 || fread(&nnz, 8, 1, f) != 1) return false;
+                B.bj = (int)bj;
+                B.rowptr.resize((size_t)P.n + 1); B.col.resize((size_t)nnz); B.val.resize((size_t)nnz);
+                if (fread(B.rowptr.data(), 8, (size_t)P.n + 1, f) != (size_t)P.n + 1) return false;
+                if (nnz && (fread(B.col.data(), 4, (size_t)nnz, f) != (size_t)nnz || fread(B.val.data(), 8, (size_t)nnz, f) != (size_t)nnz)) return false;
+            }
+            P.dirs[(size_t)a].init(P.n);
+            bool have_diag = false;
+            for (auto& B : blks) {
+                if (B.bj == a) { P.rowptr[(size_t)a] = B.rowptr; P.col[(size_t)a] = B.col; P.val[(size_t)a] = B.val; have_diag = true; }
+            }
+            if (!have_diag) { P.rowptr[(size_t)a].assign((size_t)P.n + 1, 0); }
+            if (!add_direction(P, a)) return false;
+            for (auto& B : blks) {
+                if (B.bj == a) continue;
+                std::vector<int32_t> sc; std::vector<double> sv;
+                const int32_t* cp = B.col.data(); const double* vp = B.val.data();
+                if (nbgrid::sort_rows_by_grid(P.g.gidx_of_int, P.n, B.rowptr.data(), cp, vp, sc, sv)) { cp = sc.data(); vp = sv.data(); }
+                const char* msg = "";
+                if (!nbdict::add_block(P.dirs[(size_t)a], P.n, B.rowptr.data(), cp, vp, (int64_t)(B.bj + 1) * P.stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block %s\n", msg); return false; }
+                P.extra[(size_t)a].push_back(B);
+            }
+            continue;
+        }
         if (fread(&nnz, 8, 1, f) != 1) return false;
         P.rowptr[(size_t)a].resize((size_t)P.n + 1); P.col[(size_t)a].resize((size_t)nnz); P.val[(size_t)a].resize((size_t)nnz);
         if (fread(P.rowptr[(size_t)a].data(), 8, (size_t)P.n + 1, f) != (size_t)P.n + 1) return false;
@@ -214,6 +253,7 @@ static int check(Problem& P, int cap)
     auto &rowptr = P.rowptr, &wall_ptr = P.wall_ptr;
     auto &col = P.col, &wall_col = P.wall_col;
     auto &val = P.val, &wall_val = P.wall_val;
+    for (auto& d : dirs) d.majority_class_first();      // as finalize_dict does
     nbgrid::Tables T;
     const int max_k = 128;
     if (!nbgrid::build(dirs, g, n, stride, 128, cap, max_k, 63, T)) { printf("INFEASIBLE\n"); return 0; }
@@ -266,6 +306,11 @@ static int check(Problem& P, int cap)
                         const double tt = val[(size_t)a][(size_t)k] * x[(size_t)((int64_t)(a + 1) * stride + col[(size_t)a][(size_t)k])];
                         ref += tt; aref += std::fabs(tt);
                     }
+                    if (!P.extra.empty()) for (const ExtraBlock& B : P.extra[(size_t)a])
+                        for (int64_t k = B.rowptr[(size_t)r]; k < B.rowptr[(size_t)r + 1]; k++) {
+                            const double tt = B.val[(size_t)k] * x[(size_t)((int64_t)(B.bj + 1) * stride + B.col[(size_t)k])];
+                            ref += tt; aref += std::fabs(tt);
+                        }
                     if (wall) for (int64_t k = wall_ptr[(size_t)a][(size_t)r]; k < wall_ptr[(size_t)a][(size_t)r + 1]; k++) {
                         const double tt = wall_val[(size_t)a][(size_t)k] * x[(size_t)((int64_t)((a + 1) % ndir + 1) * stride + wall_col[(size_t)a][(size_t)k])];
                         ref += tt; aref += std::fabs(tt);
@@ -289,6 +334,18 @@ static int check(Problem& P, int cap)
                 }
         }
         if (next_dir != ndir) { printf("FAIL passes do not cover all directions\n"); return 1; }
+    }
+    if (getenv("GRID_CHECK_VERBOSE")) {       // per direction: rows from boxes / from their lists, class-0 row length, box shape
+        for (int a = 0; a < ndir; a++) {
+            int64_t gen = 0, box = 0;
+            for (int64_t sl = 0; sl < T.n_tiles * 128; sl++) {
+                if (T.tile_row[(size_t)sl] < 0) continue;
+                const uint32_t dx = (uint32_t)T.desc_x[(size_t)a * T.desc_stride + (size_t)sl];
+                if (dx >> 31) gen++; else if ((dx >> 16) == 0) box++;
+            }
+            printf("  dir %2d: K0=%d classes=%zu box=%lld generic=%lld box_dims=%dx%dx%d\n", a, dirs[(size_t)a].cls.empty() ? 0 : dirs[(size_t)a].cls[0].K,
+                   dirs[(size_t)a].cls.size(), (long long)box, (long long)gen, T.box_dims[(size_t)a * 3], T.box_dims[(size_t)a * 3 + 1], T.box_dims[(size_t)a * 3 + 2]);
+        }
     }
     if (seen_rows != n) { printf("FAIL %lld of %lld rows in tiles\n", (long long)seen_rows, (long long)n); return 1; }
     // box stores: a flagged half-tile written as one box (out-of-range points clipped) must put every row of the half at its own

@@ -315,3 +315,42 @@ def test_filter_level_schedule(tmp_path):
     for args in ["2 4 3 1 2 0 1", "2 6 5 1 3 1 2", "3 4 4 4 2 2 3", "3 3 4 2 4 3 4", "3 8 8 8 1 0 5", "2 9 7 1 4 2 6", "3 16 16 16 1 2 7"]:
         out = subprocess.run([exe, *args.split()], check=True, capture_output=True, text=True).stdout
         assert out.startswith("OK"), (args, out)
+
+
+def test_grid_tables_replay_walled(tmp_path):
+    """Walled meshes through the grid builder (multi-block file mode of tests/cpp/grid_check.cpp: bounce blocks included in the
+    replayed product): Riemann-like D2Q25H p = 2 with walls on all four sides and a y-walled D3Q19 p = 2 channel.  Regression:
+    the corner DoF of a walled mesh has a one-entry row (stuck path) and used to make that row length "class 0" for the 8
+    directions that point into a corner -- a third of all rows then left the TMA boxes (BASELINE config 4).  Now class 0 is the
+    class most rows have and only the wall layer is taken from the dictionary lists."""
+    import subprocess
+    from natrium_b200 import harness
+    exe = str(tmp_path / "grid_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "grid_check.cpp")], check=True)
+    cases = [("D2Q25H", 1.0, 2, [32, 32], 2, 1.0, [True, True], [2.0, 2.0], 512, 0.95),
+             ("D3Q19", 2.0, 3, [4, 6, 3], 2, 0.4, [False, True, False], [2.0, 1.0, 2.0], 1536, 0.80)]
+    for name, sc, dim, cells, p, cfl, walls, length, cap, min_share in cases:
+        st = Stencil(name, sc)
+        pb = harness.CartesianProblem(dim, cells, p, length=length)
+        dt = pb.timestep(st, cfl)
+        part = harness.SlabPartition(pb, st, dt)
+        num = harness.CellNumbering(part)
+        dims, coords = num.grid_coords()
+        path = str(tmp_path / "walled.bin")
+        with open(path, "wb") as f:
+            f.write(np.array([dim, p, part.n_owned, part.n_ghost, -(st.getQ() - 1)] + list(dims) + [1] * (3 - dim), dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(coords, dtype=np.int32).tobytes())
+            for a in range(1, st.getQ()):
+                bl, _ = harness.assemble_direction_walled(pb, part, st, dt, a, walls)
+                items = [(k, v) for k, v in bl.items() if len(v[2])]
+                f.write(np.array([len(items)], dtype=np.int64).tobytes())
+                for (bi, bj), (rp, col, val) in items:
+                    rp, col, val = num.renumber_csr(rp, col, val)
+                    f.write(np.array([bj, len(val)], dtype=np.int64).tobytes())
+                    f.write(np.ascontiguousarray(rp, dtype=np.int64).tobytes())
+                    f.write(np.ascontiguousarray(col, dtype=np.int32).tobytes())
+                    f.write(np.ascontiguousarray(val, dtype=np.float64).tobytes())
+        out = subprocess.run([exe, "file", path, str(cap)], check=True, capture_output=True, text=True).stdout
+        assert out.startswith("OK"), (name, out)
+        kv = dict(t.split("=") for t in out.split()[1:])
+        assert int(kv["box_rows"]) >= min_share * int(kv["checked"]), (name, out)
