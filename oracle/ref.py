@@ -186,3 +186,33 @@ def exponential_filter(dim, p, alpha, s, Nc, by_sum=False, cell_dofs=None, v=Non
     if rc:
         raise ValueError((dim, p))
     return to, fr
+
+
+# ---- the reference's own ThermalBounceBack (oracle/_ref/libnatrium_ref_walls.so, oracle/ref_walls_driver.cpp) ----
+_SO_WALLS = os.path.join(_HERE, "_ref", "libnatrium_ref_walls.so")
+_LIB_WALLS = None
+
+
+def walls_available():
+    build()
+    return os.path.exists(_SO_WALLS)
+
+
+def thermal_bounce_back(scaling, f, g, dest_index, dest_direction, wall_temperature, n=None):
+    """natrium::ThermalBounceBack<3>::calculateBoundaryValues (D3Q45) for every hit of the list, in list order, in place on
+    f and g ([45, stride])."""
+    global _LIB_WALLS
+    if _LIB_WALLS is None:
+        if not walls_available():
+            raise RuntimeError("oracle/_ref/libnatrium_ref_walls.so is missing and /root/reference is not present to build it")
+        _LIB_WALLS = C.CDLL(_SO_WALLS)
+    Q, stride = f.shape
+    assert Q == 45 and g.shape == f.shape
+    n = stride if n is None else n
+    idx = np.ascontiguousarray(dest_index, dtype=np.int32)
+    dr = np.ascontiguousarray(dest_direction, dtype=np.int32)
+    rc = _LIB_WALLS.ref_thermal_bounce_back(C.c_double(scaling), C.c_int64(n), C.c_int64(stride), _d(f), _d(g), C.c_int64(len(idx)),
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)), dr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                            C.c_double(wall_temperature))
+    if rc:
+        raise RuntimeError(rc)

@@ -354,3 +354,36 @@ def test_filter_cell_loop_vs_reference(dim, cells, p, order):
     to_o, fr_o = F.projection_matrices(p, dim)
     v_own = F.apply_filter(cd, to_o, fr_o, sg, damped, v0.copy())
     assert np.abs(v_own - v_ref).max() <= 1e-11 * np.abs(v_ref).max()
+
+
+# ---------------------------------------------------------------------------------------------------
+# f1: the reference's own ThermalBounceBack (L/boundaries/ThermalBounceBack.cpp compiled against oracle/ref_stubs_walls)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not ref.walls_available(), reason="oracle/_ref walls library not built and /root/reference absent")
+@pytest.mark.parametrize("scaling,wall_T", [(1.0, 0.85), (1.0, 1.0), (2.5, 0.85)])
+def test_thermal_bounce_back_vs_reference(scaling, wall_T):
+    """orc_apply_wall_hits (thermal kind) against ThermalBounceBack<3>::calculateBoundaryValues as compiled from the reference:
+    D3Q45 f and g near a quartic equilibrium with a temperature field that differs from the wall temperature at some DoFs and
+    equals it (within the reference's 1e-5 switch) at others; a hit list with repeated destinations (several directions hit the
+    same wall DoF: the second application starts from the first one's output) replayed in order.  <= 1e-14 relative."""
+    from oracle import fields
+    st = cpu.Stencil("D3Q45", scaling)
+    n = 64
+    rng = np.random.default_rng(4)
+    rho = 1.0 + 0.05 * rng.standard_normal(n)
+    u = 0.03 * scaling * rng.standard_normal((3, n))
+    T = wall_T + np.where(np.arange(n) % 3 == 0, 0.0, 0.05 * rng.standard_normal(n))
+    f, g = fields.quartic_equilibrium_init(st.e, st.w, st.cs2, st.scaling, rho, u, T, 1.4)
+    f = np.ascontiguousarray(f * (1.0 + 1e-3 * rng.standard_normal(f.shape)))
+    g = np.ascontiguousarray(g * (1.0 + 1e-3 * rng.standard_normal(g.shape)))
+    idx = np.concatenate([rng.integers(0, n, 40), np.arange(0, n, 5), np.arange(0, n, 5)]).astype(np.int32)
+    dirs = rng.integers(1, 45, len(idx)).astype(np.int32)
+    f_ref, g_ref = f.copy(), g.copy()
+    ref.thermal_bounce_back(scaling, f_ref, g_ref, idx, dirs, wall_T)
+    f_orc, g_orc = f.copy(), g.copy()
+    assert cpu.apply_wall_hits(st, f_orc, g_orc, idx, dirs, np.ones(len(idx), dtype=np.int32), np.full(len(idx), wall_T)) == 0
+    assert np.abs(f_ref - f).max() > 1e-6 and np.abs(g_ref - g).max() > 1e-6          # the wall did something
+    assert np.abs(f_orc - f_ref).max() <= 1e-14 * np.abs(f_ref).max()
+    assert np.abs(g_orc - g_ref).max() <= 1e-14 * np.abs(g_ref).max()
+    untouched = np.setdiff1d(np.arange(n), idx)
+    assert np.array_equal(f_ref[:, untouched], f[:, untouched]) and np.array_equal(g_ref[:, untouched], g[:, untouched])
