@@ -20,6 +20,7 @@
 //               multiplied straight from its dictionary list (rows with bounce-back blocks, truncated rows, ...).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -109,6 +110,8 @@ struct Tables {
     std::vector<int16_t> tile_store;              // [n_tiles][4]: grid origin (x, y, z) of the tile's first half, bit h of [3] = half h
                                                   // may be written to the grid copy as ONE box (TMA store) instead of per thread
     int half_dims[3] = {1, 1, 1};                 // box of a half-tile
+    std::vector<double> pair_hist;                // diagnostics (GRID_BUILD_PAIR_HIST): largest entry difference of every mismatched pair
+    int64_t pairs = 0, pairs_same = 0, pairs_unified = 0;   // row pairs of class-0 box rows: with equal pattern ids / made equal (pair_tol)
     int64_t generic_rows = 0, grid_rows = 0, total_boxes = 0, max_pass_doubles = 0;
 };
 
@@ -139,8 +142,11 @@ static inline void half_tile_dims(int dim, int p, int h[3])
 //   dirs         finished dictionary, lists still on the host, rows sorted by grid offset
 //   n_owned      rows; stride: population pitch of the canonical arrays (flat column = beta * stride + col)
 //   cap          staging buffer capacity in doubles (per distribution)
+//   pair_tol     > 0: rows t and t + rows/2 of a tile whose class-0 patterns got different ids but agree entry by entry to this
+//                tolerance (the dictionary's value tolerance) both take the first one's pattern in the grid descriptors, so that
+//                the kernels' paired product is taken by whole warps (see the note at the end of the function); 0 = ids as they are
 static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int64_t n_owned, int64_t stride, int rows_per_tile,
-                  int cap, int max_k, int empty_cls, Tables& T)
+                  int cap, int max_k, int empty_cls, Tables& T, double pair_tol = 0.0)
 {
     const int nd = (int)dirs.size();
     const int p = g.fe_order > 0 ? g.fe_order : 4;
@@ -479,6 +485,38 @@ static bool build(const std::vector<nbdict::DirBuild>& dirs, const Grid& g, int6
     }
     T.tile_pass[(size_t)n_tiles] = (int32_t)T.passes.size();
     T.total_boxes = (int64_t)T.boxes.size();
+    // Pairing.  The kernels multiply rows t and t + rows/2 of a tile together when both are class-0 box rows with the SAME pattern
+    // id (one weight load feeds both); a pair with different ids takes two separate products -- and drags its whole warp through
+    // both code paths.  With a value tolerance the dictionary keeps one representative per bucket of round-off variants, and which
+    // bucket a row falls into is decided by its noise: on the uniform 32^3-cell mesh 2.5 % of the pairs (same position in
+    // x-neighbour cells, weights equal up to round-off) ended up with different ids, sprinkled over half of all warps (ncu: 24 of
+    // 32 threads active per instruction in the product loop; thread-level instruction counts equal to a graded mesh's, warp-level
+    // 13 % higher).  Such pairs are unified here: if the two patterns agree entry by entry to pair_tol, the second row takes the
+    // first one's id.  Its stored weights then differ from its own by at most 2 pair_tol instead of pair_tol.
+    T.pairs = T.pairs_same = T.pairs_unified = 0;
+    for (int a = 0; a < nd; a++) {
+        const nbdict::DirBuild& d = dirs[(size_t)a];
+        if (d.cls.empty()) continue;
+        const nbdict::ClassBuild& C0 = d.cls[0];
+        const int K = C0.K;
+        for (int64_t b = 0; b < n_tiles; b++)
+            for (int t = 0; t < half_rows; t++) {
+                const size_t s0 = (size_t)a * T.desc_stride + (size_t)(b * rows_per_tile + t), s1 = s0 + (size_t)half_rows;
+                const uint32_t x0 = (uint32_t)T.desc_x[s0], x1 = (uint32_t)T.desc_x[s1];
+                if (((x0 | x1) >> 16) != 0) continue;                   // idle, empty or generic on either side
+                T.pairs++;
+                if (T.desc_y[s0] == T.desc_y[s1]) { T.pairs_same++; continue; }
+                if (!(pair_tol > 0.0) || C0.pats.empty()) continue;
+                const double* p0 = C0.pats.data() + (size_t)T.desc_y[s0] * K;
+                const double* p1 = C0.pats.data() + (size_t)T.desc_y[s1] * K;
+                bool close = true;
+                double worst = 0.0;
+                for (int k = 0; k < K; k++) worst = std::max(worst, std::fabs(p0[k] - p1[k]));
+                if (getenv("GRID_BUILD_PAIR_HIST")) T.pair_hist.push_back(worst);
+                close = worst <= pair_tol;
+                if (close) { T.desc_y[s1] = T.desc_y[s0]; T.pairs_unified++; }
+            }
+    }
     return true;
 }
 

@@ -159,6 +159,7 @@ struct nb200_ctx {
     int16_t* d_tile_store = nullptr;         // [n_tiles][4] (grid_build.h: Tables::tile_store)
     int grid_half_x = 1;
     int64_t grid_store_halves = 0;
+    int64_t grid_pairs = 0, grid_pairs_same = 0, grid_pairs_unified = 0;   // row pairs of the tiles: all / with one pattern / made so
     std::vector<int16_t> grid_off;           // [(Q-1)][NB_GRID_MAXK] host copy of the offset table in BYTES (constant memory of the unit)
     int32_t *d_gtile_interior = nullptr, *d_gtile_boundary = nullptr;
     int64_t n_gtile_interior = 0, n_gtile_boundary = 0;
@@ -1114,7 +1115,10 @@ static int finalize_dict(nb200_ctx* c)
                 static const char* envc = getenv("NB200_GRID_CAP");     // experiments only
                 if (envc && atoi(envc) >= 256) c->grid_cap = std::min(atoi(envc), (int)NB_GRID_CAP);
             }
-            grid_ok = nbgrid::build(c->dirs, c->grid, n, c->stride, NB_CTA_ROWS, c->grid_cap, NB_GRID_MAXK, NB_MAX_CLS - 1, GT);
+            // pairs of rows whose patterns are round-off variants of each other that fell into neighbouring tolerance buckets take
+            // one pattern (twice the value tolerance covers two representatives of adjacent buckets); nothing changes with tolerance 0
+            grid_ok = nbgrid::build(c->dirs, c->grid, n, c->stride, NB_CTA_ROWS, c->grid_cap, NB_GRID_MAXK, NB_MAX_CLS - 1, GT, 2.0 * c->dedup_tol);
+            c->grid_pairs = GT.pairs; c->grid_pairs_same = GT.pairs_same + GT.pairs_unified; c->grid_pairs_unified = GT.pairs_unified;
         }
     }
     for (int a = 0; a < nb; a++) {

@@ -46,7 +46,7 @@ static bool add_direction(Problem& P, int a)
     const double* vp = P.val[(size_t)a].data();
     if (nbgrid::sort_rows_by_grid(P.g.gidx_of_int, P.n, P.rowptr[(size_t)a].data(), cp, vp, sc, sv)) { cp = sc.data(); vp = sv.data(); }
     const char* msg = "";
-    if (!nbdict::add_block(P.dirs[(size_t)a], P.n, P.rowptr[(size_t)a].data(), cp, vp, (int64_t)(a + 1) * P.stride, 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block %s\n", msg); return false; }
+    if (!nbdict::add_block(P.dirs[(size_t)a], P.n, P.rowptr[(size_t)a].data(), cp, vp, (int64_t)(a + 1) * P.stride, getenv("GRID_CHECK_TOL") ? atof(getenv("GRID_CHECK_TOL")) : 0.0, 63, (1 << 26) - 1, &msg)) { printf("FAIL add_block %s\n", msg); return false; }
     if (P.wall) {
         const int b = (a + 1) % P.ndir;
         if (!nbdict::add_block(P.dirs[(size_t)a], P.n, P.wall_ptr[(size_t)a].data(), P.wall_col[(size_t)a].data(), P.wall_val[(size_t)a].data(),
@@ -255,8 +255,10 @@ static int check(Problem& P, int cap)
     auto &val = P.val, &wall_val = P.wall_val;
     for (auto& d : dirs) d.majority_class_first();      // as finalize_dict does
     nbgrid::Tables T;
+    double pair_share = 1.0;
     const int max_k = 128;
-    if (!nbgrid::build(dirs, g, n, stride, 128, cap, max_k, 63, T)) { printf("INFEASIBLE\n"); return 0; }
+    const double pair_tol = getenv("GRID_CHECK_TOL") ? 2.0 * atof(getenv("GRID_CHECK_TOL")) : 0.0;      // as finalize_dict: twice the value tolerance
+    if (!nbgrid::build(dirs, g, n, stride, 128, cap, max_k, 63, T, pair_tol)) { printf("INFEASIBLE\n"); return 0; }
     // grid copy of x
     const int64_t gstride = (g.G + 31) / 32 * 32;
     std::vector<double> xg((size_t)(ndir + 1) * gstride, 0.0);
@@ -335,6 +337,25 @@ static int check(Problem& P, int cap)
         }
         if (next_dir != ndir) { printf("FAIL passes do not cover all directions\n"); return 1; }
     }
+    {   // how many row pairs (slots t and t + 64 of a tile) take the paired product: both class-0 box rows with the same pattern id
+        int64_t pairs = 0, paired = 0;
+        for (int a = 0; a < ndir; a++)
+            for (int64_t b = 0; b < T.n_tiles; b++)
+                for (int t = 0; t < 64; t++) {
+                    const size_t s0 = (size_t)(b * 128 + t), s1 = s0 + 64;
+                    if (T.tile_row[s0] < 0 || T.tile_row[s1] < 0) continue;
+                    pairs++;
+                    const uint32_t x0 = (uint32_t)T.desc_x[(size_t)a * T.desc_stride + s0], x1 = (uint32_t)T.desc_x[(size_t)a * T.desc_stride + s1];
+                    if (((x0 | x1) >> 16) == 0 && T.desc_y[(size_t)a * T.desc_stride + s0] == T.desc_y[(size_t)a * T.desc_stride + s1]) paired++;
+                }
+        pair_share = pairs ? (double)paired / (double)pairs : 1.0;
+    }
+    if (!T.pair_hist.empty()) {
+        std::vector<double> h = T.pair_hist;
+        std::sort(h.begin(), h.end());
+        printf("  mismatched pairs %zu: entry difference min %.2e median %.2e p90 %.2e p99 %.2e max %.2e\n", h.size(), h.front(), h[h.size() / 2],
+               h[h.size() * 9 / 10], h[h.size() * 99 / 100], h.back());
+    }
     if (getenv("GRID_CHECK_VERBOSE")) {       // per direction: rows from boxes / from their lists, class-0 row length, box shape
         for (int a = 0; a < ndir; a++) {
             int64_t gen = 0, box = 0;
@@ -377,8 +398,8 @@ static int check(Problem& P, int cap)
             }
     }
     if (!(max_err <= 1e-13 * max_ref)) { printf("FAIL max_err %g (scale %g)\n", max_err, max_ref); return 1; }
-    printf("OK rows=%lld checked=%lld tiles=%lld boxes=%lld passes=%zu box_rows=%lld generic=%lld max_pass=%lld err=%.2e store_halves=%lld store_rows=%lld\n", (long long)n, (long long)checked,
+    printf("OK rows=%lld checked=%lld tiles=%lld boxes=%lld passes=%zu box_rows=%lld generic=%lld max_pass=%lld err=%.2e store_halves=%lld store_rows=%lld paired=%.4f unified=%lld\n", (long long)n, (long long)checked,
            (long long)T.n_tiles, (long long)T.total_boxes, T.passes.size(), (long long)T.grid_rows, (long long)T.generic_rows, (long long)T.max_pass_doubles, max_err,
-           (long long)store_halves, (long long)store_rows);
+           (long long)store_halves, (long long)store_rows, pair_share, (long long)T.pairs_unified);
     return 0;
 }

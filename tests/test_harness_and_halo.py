@@ -354,3 +354,39 @@ def test_grid_tables_replay_walled(tmp_path):
         assert out.startswith("OK"), (name, out)
         kv = dict(t.split("=") for t in out.split()[1:])
         assert int(kv["box_rows"]) >= min_share * int(kv["checked"]), (name, out)
+
+
+def test_grid_row_pairs_are_unified_within_the_tolerance(tmp_path):
+    """The kernels multiply rows t and t + 64 of a tile together when their pattern ids agree; a mismatch drags the whole warp
+    through both code paths.  At the bench's cell size (32 cells over 2 pi) round-off puts 2-5 % of those pairs -- same
+    position in x-neighbour cells, weights equal up to 1.3e-14 -- into neighbouring tolerance buckets.  The grid builder gives
+    such a pair one pattern (twice the value tolerance): >= 99.9 % paired afterwards, products still equal to the CSR product
+    (replay), nothing unified with tolerance 0."""
+    import subprocess
+    exe = str(tmp_path / "grid_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "grid_check.cpp")], check=True)
+    from natrium_b200 import harness
+    st = Stencil("D3Q19", math.sqrt(3) / 0.05)
+    cells, length = [32, 4, 2], [2 * math.pi, 2 * math.pi / 8, 2 * math.pi / 16]
+    pb = harness.CartesianProblem(3, cells, 4, length=length)
+    dt = pb.timestep(st, 0.4)
+    part = harness.SlabPartition(pb, st, dt)
+    num = harness.CellNumbering(part)
+    dims, coords = num.grid_coords()
+    path = str(tmp_path / "u32.bin")
+    with open(path, "wb") as f:
+        f.write(np.array([3, 4, part.n_owned, part.n_ghost, 18] + list(dims), dtype=np.int64).tobytes())
+        f.write(np.ascontiguousarray(coords, dtype=np.int32).tobytes())
+        for a in range(1, 19):
+            rp, col, val = num.renumber_csr(*harness.assemble_direction(pb, part, st, dt, a))
+            f.write(np.array([len(val)], dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(rp, dtype=np.int64).tobytes())
+            f.write(np.ascontiguousarray(col, dtype=np.int32).tobytes())
+            f.write(np.ascontiguousarray(val, dtype=np.float64).tobytes())
+    res = {}
+    for tol in ("0", "1e-14"):
+        out = subprocess.run([exe, "file", path, "1536"], check=True, capture_output=True, text=True, env=dict(os.environ, GRID_CHECK_TOL=tol)).stdout
+        assert out.startswith("OK"), out
+        res[tol] = dict(t.split("=") for t in out.split()[1:])
+    assert int(res["0"]["unified"]) == 0
+    assert int(res["1e-14"]["unified"]) > 0 and float(res["1e-14"]["paired"]) >= 0.999
