@@ -388,7 +388,9 @@ def parity_gate(c, cells, length, args, steps=10):
         row_sum_err = float(np.max(np.abs(ctx.download_populations(0)[1:] - 1.0)))
         gi = ctx.grid_info()
         return {"steps": steps, "max_rel_err": worst, "row_sum_err": row_sum_err, "tolerance": 1e-12,
-                "ok": bool(worst <= 1e-12 and (row_sum_err <= 1e-12 or c.get("row_noise", 0.0) > 0.0)),      # a perturbed matrix has no unit row sums "mesh": "x".join(str(v) for v in cells) + " cells", "n_dofs": n,
+                # (a matrix perturbed by --row-noise has no unit row sums)
+                "ok": bool(worst <= 1e-12 and (row_sum_err <= 1e-12 or c.get("row_noise", 0.0) > 0.0)),
+                "mesh": "x".join(str(v) for v in cells) + " cells", "n_dofs": n,
                 "kernels": "grid (TMA boxes)" if gi["in_use"] else ("staged" if ctx.matrix_format_info().get("staged") else "rows"),
                 "built_like_timed_context": {"format": args.format, "dedup_tol": args.dedup_tol, "numbering": args.numbering, "grid_hint": args.grid,
                                              "dof_order": args.dof_order}}
