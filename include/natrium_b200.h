@@ -146,7 +146,7 @@ int nb200_finalize_matrix(nb200_ctx *ctx);
  *                      the default 1e-14 is four orders below the 1e-10 below which the reference's own
  *                      assembly drops entries (L/advection/SemiLagrangian.cpp:483) and bounds the per-row
  *                      perturbation by K*1e-14*max|f| (K = row length <= (p+1)^dim).  With the grid hint
- *                      (nb200_set_dof_grid) two rows that are multiplied together (same position in two
+ *                      (nb200_set_dof_grid) and one distribution, two rows that are multiplied together (same position in two
  *                      neighbouring cells) and whose patterns differ by no more than twice the tolerance take the
  *                      first one's pattern, i.e. a stored weight is then within 3 * value_dedup_tol of its own.
  * The matrix the reference assembles on a regular mesh has only O((p+1)^dim) distinct rows per direction up
